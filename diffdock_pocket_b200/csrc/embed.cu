@@ -1,0 +1,406 @@
+// Small (HBM / latency bound) kernels around the convolutions: sigma embedding + per-graph
+// projections, node initialisation, fused edge geometry + spherical harmonics + radial basis +
+// edge-embedding MLP, node update (scatter-mean + BatchNorm + residual), heads.
+#include "ddp_common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+__global__ void graph_sigma_proj_kernel(const float *__restrict__ t, float scale, const float *__restrict__ freq,
+                                        int sig_dim, const float *__restrict__ w, const float *__restrict__ b,
+                                        int n_graphs, int ns, float *__restrict__ sig, float *__restrict__ out) {
+    extern __shared__ float s_sig[];
+    const int g = blockIdx.x, m = blockIdx.y;
+    const int half = sig_dim / 2;
+    for (int i = threadIdx.x; i < sig_dim; i += blockDim.x) {
+        float v = 0.f;
+        if (i < 2 * half) {
+            const float arg = __fmul_rn(__fmul_rn(scale, t[g]), freq[i < half ? i : i - half]);
+            v = (i < half) ? sinf(arg) : cosf(arg);
+        }
+        s_sig[i] = v;
+        if (m == 0) sig[(size_t)g * sig_dim + i] = v;
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < ns; o += blockDim.x) {
+        const float *wm = w + (size_t)m * sig_dim * ns;
+        float acc = b[(size_t)m * ns + o];
+        for (int k = 0; k < sig_dim; ++k) acc = fmaf(wm[(size_t)k * ns + o], s_sig[k], acc);
+        out[((size_t)m * n_graphs + g) * ns + o] = acc;
+    }
+}
+
+__global__ void node_init_kernel(const float *__restrict__ sp, const float *__restrict__ u,
+                                 const int32_t *__restrict__ graph_of, int n, int ns, float *__restrict__ out, int ld) {
+    const size_t total = (size_t)n * ns;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int node = (int)(i / ns), c = (int)(i % ns);
+        out[(size_t)node * ld + c] = sp[i] + u[(size_t)graph_of[node] * ns + c];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Edge geometry + embedding: 32 edges per block, 128 threads = 2 edge halves x 64 output lanes.
+constexpr int kEE = 32;
+constexpr int kEEThreads = 128;
+constexpr int kMaxNs = 64, kMaxRbf = 64, kMaxPre = 8;
+
+__global__ void __launch_bounds__(kEEThreads)
+edge_embed_kernel(const float *__restrict__ pos_a, const float *__restrict__ pos_b, const int32_t *__restrict__ edge,
+                  int cap, const int32_t *__restrict__ n_edges_dev, const int32_t *__restrict__ graph_of_a,
+                  const float *__restrict__ pre, int n_pre_rows, const float *__restrict__ u, ddp_edge_mlp_t p,
+                  float *__restrict__ sh_out, float *__restrict__ emb) {
+    __shared__ float s_in[(kMaxRbf + kMaxPre) * kEE];   // [k][edge]
+    __shared__ float s_r[kMaxNs * kEE];                 // [j][edge]
+    __shared__ float s_d[kEE];
+    __shared__ int s_g[kEE];
+    const int n_edges = min(*n_edges_dev, cap);
+    const int e0 = blockIdx.x * kEE;
+    if (e0 >= n_edges) return;
+    const int tid = threadIdx.x;
+    if (tid < kEE) {
+        const int e = e0 + tid;
+        float d = 0.f;
+        int g = 0;
+        if (e < n_edges) {
+            const int a = edge[e], b = edge[cap + e];
+            const float vx = pos_b[3 * b] - pos_a[3 * a], vy = pos_b[3 * b + 1] - pos_a[3 * a + 1],
+                        vz = pos_b[3 * b + 2] - pos_a[3 * a + 2];
+            d = sqrtf(vx * vx + vy * vy + vz * vz);
+            const float inv = 1.f / fmaxf(d, 1e-12f);
+            const float x = vx * inv, y = vy * inv, z = vz * inv;
+            const float s3 = 1.7320508075688772f;
+            float *so = sh_out + (size_t)e * p.sh_dim;
+            so[0] = 1.f; so[1] = s3 * x; so[2] = s3 * y; so[3] = s3 * z;
+            if (p.sh_dim == 9) {
+                const float s5 = 2.23606797749979f;
+                so[4] = s5 * s3 * x * z;
+                so[5] = s5 * s3 * x * y;
+                so[6] = s5 * (y * y - 0.5f * (x * x + z * z));
+                so[7] = s5 * s3 * y * z;
+                so[8] = s5 * (s3 * 0.5f) * (z * z - x * x);
+            }
+            g = graph_of_a ? graph_of_a[a] : a;
+        }
+        s_d[tid] = d;
+        s_g[tid] = g;
+    }
+    __syncthreads();
+    for (int i = tid; i < p.n_rbf * kEE; i += kEEThreads) {
+        const int k = i / kEE, el = i % kEE;
+        const float t = s_d[el] - p.rbf_offset[k];
+        s_in[i] = expf(p.rbf_coeff * (t * t));
+    }
+    for (int i = tid; i < p.n_pre * kEE; i += kEEThreads) {
+        const int k = i / kEE, el = i % kEE;
+        const int e = e0 + el;
+        s_in[p.n_rbf * kEE + i] = (pre != nullptr && e < n_pre_rows) ? pre[(size_t)e * p.n_pre + k] : 0.f;
+    }
+    __syncthreads();
+    const int o = tid & 63, half = tid >> 6;  // 16 edges per half
+    float acc[16];
+    if (o < p.ns) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int el = half * 16 + i;
+            acc[i] = (u != nullptr) ? u[(size_t)s_g[el] * p.ns + o] : p.b1[o];
+        }
+        for (int k = 0; k < p.n_rbf; ++k) {
+            const float w = __ldg(p.w_rbf + (size_t)k * p.ns + o);
+            const float4 *v = reinterpret_cast<const float4 *>(s_in + k * kEE + half * 16);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 f = v[q];
+                acc[4 * q] = fmaf(w, f.x, acc[4 * q]); acc[4 * q + 1] = fmaf(w, f.y, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(w, f.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(w, f.w, acc[4 * q + 3]);
+            }
+        }
+        for (int k = 0; k < p.n_pre; ++k) {
+            const float w = __ldg(p.w_pre + (size_t)k * p.ns + o);
+            const float *v = s_in + (p.n_rbf + k) * kEE + half * 16;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = fmaf(w, v[i], acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s_r[o * kEE + half * 16 + i] = fmaxf(acc[i], 0.f);
+    }
+    __syncthreads();
+    if (o < p.ns) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = p.b2[o];
+        for (int k = 0; k < p.ns; ++k) {
+            const float w = __ldg(p.w2 + (size_t)k * p.ns + o);
+            const float4 *v = reinterpret_cast<const float4 *>(s_r + k * kEE + half * 16);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 f = v[q];
+                acc[4 * q] = fmaf(w, f.x, acc[4 * q]); acc[4 * q + 1] = fmaf(w, f.y, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(w, f.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(w, f.w, acc[4 * q + 3]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int e = e0 + half * 16 + i;
+            if (e < n_edges) emb[(size_t)e * p.ns + o] = acc[i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxUpdates = 4;
+struct UpdatePack { ddp_update_t u[kMaxUpdates]; int n; };
+
+__global__ void node_update_kernel(const float *__restrict__ old_x, int f_old, int ld_old, UpdatePack up, int n,
+                                   int f_new, float *__restrict__ new_x, int ld_new) {
+    const size_t total = (size_t)n * f_new;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int node = (int)(i / f_new), c = (int)(i % f_new);
+        float v = (old_x != nullptr && c < f_old) ? old_x[(size_t)node * ld_old + c] : 0.f;
+        for (int k = 0; k < up.n; ++k) {
+            if (*up.u[k].n_edges_dev > 0) {
+                const int dg = up.u[k].deg[node];
+                const float cnt = (float)(dg < 1 ? 1 : dg);
+                const float m = up.u[k].sum[(size_t)node * f_new + c] / cnt;
+                const float sc = up.u[k].scale ? up.u[k].scale[c] : 1.f;
+                const float sf = up.u[k].shift ? up.u[k].shift[c] : 0.f;
+                v += fmaf(m, sc, sf);
+            }
+        }
+        new_x[(size_t)node * ld_new + c] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void segment_mean_kernel(const float *__restrict__ src, const int32_t *__restrict__ idx,
+                                    const int32_t *__restrict__ ptr, int n_seg, int width, int ld,
+                                    float *__restrict__ out, int ld_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_seg * width) return;
+    const int g = i / width, c = i % width;
+    float s = 0.f;
+    const int beg = ptr[g], end = ptr[g + 1];
+    for (int r = beg; r < end; ++r) s += src[(size_t)(idx ? idx[r] : r) * ld + c];
+    const int cnt = end - beg;
+    out[(size_t)g * ld_out + c] = s / (float)(cnt < 1 ? 1 : cnt);
+}
+
+__global__ void bond_geometry_kernel(const float *__restrict__ pos, const int32_t *__restrict__ bonds, int n_bonds,
+                                     const float *__restrict__ x, int ldx, int ns, float *__restrict__ mid,
+                                     float *__restrict__ y2, float *__restrict__ attr) {
+    const int bnd = blockIdx.x;
+    if (bnd >= n_bonds) return;
+    const int b0 = bonds[bnd], b1 = bonds[n_bonds + bnd];
+    if (threadIdx.x == 0) {
+        const float ax = pos[3 * b0], ay = pos[3 * b0 + 1], az = pos[3 * b0 + 2];
+        const float bx = pos[3 * b1], by = pos[3 * b1 + 1], bz = pos[3 * b1 + 2];
+        mid[3 * bnd] = (ax + bx) / 2.f; mid[3 * bnd + 1] = (ay + by) / 2.f; mid[3 * bnd + 2] = (az + bz) / 2.f;
+        const float vx = bx - ax, vy = by - ay, vz = bz - az;
+        const float inv = 1.f / fmaxf(sqrtf(vx * vx + vy * vy + vz * vz), 1e-12f);
+        const float X = vx * inv, Y = vy * inv, Z = vz * inv;
+        const float s3 = 1.7320508075688772f, s5 = 2.23606797749979f;
+        y2[5 * bnd + 0] = s5 * s3 * X * Z;
+        y2[5 * bnd + 1] = s5 * s3 * X * Y;
+        y2[5 * bnd + 2] = s5 * (Y * Y - 0.5f * (X * X + Z * Z));
+        y2[5 * bnd + 3] = s5 * s3 * Y * Z;
+        y2[5 * bnd + 4] = s5 * (s3 * 0.5f) * (Z * Z - X * X);
+    }
+    for (int c = threadIdx.x; c < ns; c += blockDim.x) attr[(size_t)bnd * ns + c] = x[(size_t)b0 * ldx + c] + x[(size_t)b1 * ldx + c];
+}
+
+__global__ void tor_edge_sh_kernel(const float *__restrict__ sh, int sh_dim, const float *__restrict__ y2,
+                                   const float *__restrict__ c121, const int32_t *__restrict__ edge,
+                                   const int32_t *__restrict__ n_edges_dev, int cap, float *__restrict__ sh_tor) {
+    __shared__ float sc[45];
+    for (int i = threadIdx.x; i < 45; i += blockDim.x) sc[i] = c121[i];
+    __syncthreads();
+    const int n_edges = min(*n_edges_dev, cap);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += gridDim.x * blockDim.x) {
+        const int bnd = edge[e];
+        float a[3] = {sh[(size_t)e * sh_dim + 1], sh[(size_t)e * sh_dim + 2], sh[(size_t)e * sh_dim + 3]};
+        float o[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const float ab = a[i] * y2[5 * bnd + j];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) o[k] = fmaf(sc[(i * 5 + j) * 3 + k], ab, o[k]);
+            }
+        sh_tor[3 * (size_t)e] = o[0]; sh_tor[3 * (size_t)e + 1] = o[1]; sh_tor[3 * (size_t)e + 2] = o[2];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxLayers = 4;
+struct MlpPack { ddp_mlp_layer_t l[kMaxLayers]; int n; };
+
+__global__ void row_mlp_kernel(const float *__restrict__ in, int n, int ld_in, MlpPack mp,
+                               const float *__restrict__ row_scale, float *__restrict__ out, int ld_out) {
+    __shared__ float buf[2][256];
+    const int row = blockIdx.x;
+    if (row >= n) return;
+    for (int k = threadIdx.x; k < mp.l[0].n_in; k += blockDim.x) buf[0][k] = in[(size_t)row * ld_in + k];
+    __syncthreads();
+    int cur = 0;
+    for (int l = 0; l < mp.n; ++l) {
+        const ddp_mlp_layer_t L = mp.l[l];
+        for (int o = threadIdx.x; o < L.n_out; o += blockDim.x) {
+            float acc = L.b ? L.b[o] : 0.f;
+            for (int k = 0; k < L.n_in; ++k) acc = fmaf(L.wt[(size_t)k * L.n_out + o], buf[cur][k], acc);
+            if (L.act == 1) acc = fmaxf(acc, 0.f);
+            else if (L.act == 2) acc = tanhf(acc);
+            buf[cur ^ 1][o] = acc;
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+    const float sc = row_scale ? row_scale[row] : 1.f;
+    for (int o = threadIdx.x; o < mp.l[mp.n - 1].n_out; o += blockDim.x) out[(size_t)row * ld_out + o] = buf[cur][o] * sc;
+}
+
+__global__ void tr_rot_head_kernel(const float *__restrict__ g, const float *__restrict__ sig, int sig_dim,
+                                   const float *__restrict__ tr_w1t, const float *__restrict__ tr_b1,
+                                   const float *__restrict__ tr_w2, const float *__restrict__ tr_b2,
+                                   const float *__restrict__ rot_w1t, const float *__restrict__ rot_b1,
+                                   const float *__restrict__ rot_w2, const float *__restrict__ rot_b2, int hid,
+                                   const float *__restrict__ tr_sigma, const float *__restrict__ so3_norm,
+                                   float *__restrict__ tr_out, float *__restrict__ rot_out) {
+    __shared__ float red[2][128];
+    const int b = blockIdx.x, j = threadIdx.x;
+    const float *gg = g + 12 * (size_t)b;
+    const float tx = gg[0] + gg[6], ty = gg[1] + gg[7], tz = gg[2] + gg[8];
+    const float rx = gg[3] + gg[9], ry = gg[4] + gg[10], rz = gg[5] + gg[11];
+    const float tn = sqrtf(tx * tx + ty * ty + tz * tz), rn = sqrtf(rx * rx + ry * ry + rz * rz);
+    float ht = 0.f, hr = 0.f;
+    if (j < hid) {
+        float at = fmaf(tr_w1t[j], tn, tr_b1[j]), ar = fmaf(rot_w1t[j], rn, rot_b1[j]);
+        for (int k = 0; k < sig_dim; ++k) {
+            const float s = sig[(size_t)b * sig_dim + k];
+            at = fmaf(tr_w1t[(size_t)(1 + k) * hid + j], s, at);
+            ar = fmaf(rot_w1t[(size_t)(1 + k) * hid + j], s, ar);
+        }
+        ht = fmaxf(at, 0.f) * tr_w2[j];
+        hr = fmaxf(ar, 0.f) * rot_w2[j];
+    }
+    red[0][j] = ht; red[1][j] = hr;
+    __syncthreads();
+    if (j == 0) {
+        float st = tr_b2[0], sr = rot_b2[0];
+        for (int k = 0; k < hid; ++k) { st += red[0][k]; sr += red[1][k]; }
+        const float ft = st / tn / tr_sigma[b], fr = sr / rn * so3_norm[b];
+        tr_out[3 * b] = tx * ft; tr_out[3 * b + 1] = ty * ft; tr_out[3 * b + 2] = tz * ft;
+        rot_out[3 * b] = rx * fr; rot_out[3 * b + 1] = ry * fr; rot_out[3 * b + 2] = rz * fr;
+    }
+}
+
+}  // namespace
+
+static inline int grid_for(size_t total, int threads) {
+    size_t g = (total + threads - 1) / threads;
+    const size_t cap = (size_t)ddp_num_sms() * 8;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+extern "C" int ddp_graph_sigma_proj(const float *t, int32_t n_graphs, float scale, const float *freq, int32_t sig_dim,
+                                    const float *w, const float *b, int32_t n_proj, int32_t ns, float *sig, float *out,
+                                    void *stream) {
+    if (!t || !freq || !w || !b || !sig || !out) return DDP_E_ARG;
+    if (n_graphs <= 0 || n_proj <= 0 || sig_dim <= 0 || sig_dim > 1024 || ns <= 0) return DDP_E_SHAPE;
+    graph_sigma_proj_kernel<<<dim3(n_graphs, n_proj), 64, sig_dim * sizeof(float), (cudaStream_t)stream>>>(
+        t, scale, freq, sig_dim, w, b, n_graphs, ns, sig, out);
+    DDP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ddp_node_init(const float *static_part, const float *u, const int32_t *graph_of, int32_t n, int32_t ns,
+                             float *out, int32_t ld_out, void *stream) {
+    if (!static_part || !u || !graph_of || !out) return DDP_E_ARG;
+    if (n <= 0) return 0;
+    node_init_kernel<<<grid_for((size_t)n * ns, 256), 256, 0, (cudaStream_t)stream>>>(static_part, u, graph_of, n, ns, out, ld_out);
+    DDP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ddp_edge_embed(const float *pos_a, const float *pos_b, const int32_t *edge, int32_t edge_cap,
+                              const int32_t *n_edges_dev, const int32_t *graph_of_a, const float *pre,
+                              int32_t n_pre_rows, const float *u, const ddp_edge_mlp_t *mlp, float *sh, float *emb,
+                              void *stream) {
+    if (!pos_a || !pos_b || !edge || !n_edges_dev || !mlp || !sh || !emb) return DDP_E_ARG;
+    if (mlp->ns > kMaxNs || mlp->n_rbf > kMaxRbf || mlp->n_pre > kMaxPre || (mlp->sh_dim != 4 && mlp->sh_dim != 9))
+        return DDP_E_SHAPE;
+    if (!u && !mlp->b1) return DDP_E_ARG;
+    if (edge_cap <= 0) return 0;
+    edge_embed_kernel<<<(edge_cap + kEE - 1) / kEE, kEEThreads, 0, (cudaStream_t)stream>>>(
+        pos_a, pos_b, edge, edge_cap, n_edges_dev, graph_of_a, pre, n_pre_rows, u, *mlp, sh, emb);
+    DDP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ddp_node_update(const float *old_x, int32_t f_old, int32_t ld_old, const ddp_update_t *updates,
+                               int32_t n_updates, int32_t n, int32_t f_new, float *new_x, int32_t ld_new, void *stream) {
+    if (!updates || !new_x || n_updates < 0 || n_updates > kMaxUpdates) return DDP_E_ARG;
+    if (n <= 0) return 0;
+    UpdatePack up;
+    up.n = n_updates;
+    for (int i = 0; i < n_updates; ++i) up.u[i] = updates[i];
+    node_update_kernel<<<grid_for((size_t)n * f_new, 256), 256, 0, (cudaStream_t)stream>>>(old_x, f_old, ld_old, up, n, f_new,
+                                                                                         new_x, ld_new);
+    DDP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ddp_segment_mean(const float *src, const int32_t *idx, const int32_t *ptr, int32_t n_seg, int32_t width,
+                                int32_t ld, float *out, int32_t ld_out, void *stream) {
+    if (!src || !ptr || !out) return DDP_E_ARG;
+    if (n_seg <= 0 || width <= 0) return 0;
+    segment_mean_kernel<<<(n_seg * width + 127) / 128, 128, 0, (cudaStream_t)stream>>>(src, idx, ptr, n_seg, width, ld, out, ld_out);
+    DDP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ddp_bond_geometry(const float *pos, const int32_t *bonds, int32_t n_bonds, const float *x, int32_t ldx,
+                                 int32_t ns, float *mid, float *y2, float *attr, void *stream) {
+    if (!pos || !bonds || !x || !mid || !y2 || !attr) return DDP_E_ARG;
+    if (n_bonds <= 0) return 0;
+    bond_geometry_kernel<<<n_bonds, 64, 0, (cudaStream_t)stream>>>(pos, bonds, n_bonds, x, ldx, ns, mid, y2, attr);
+    DDP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ddp_tor_edge_sh(const float *sh, int32_t sh_dim, const float *y2, const float *c121, const int32_t *edge,
+                               const int32_t *n_edges_dev, int32_t edge_cap, float *sh_tor, void *stream) {
+    if (!sh || !y2 || !c121 || !edge || !n_edges_dev || !sh_tor) return DDP_E_ARG;
+    if (edge_cap <= 0) return 0;
+    tor_edge_sh_kernel<<<grid_for(edge_cap, 128), 128, 0, (cudaStream_t)stream>>>(sh, sh_dim, y2, c121, edge, n_edges_dev,
+                                                                                 edge_cap, sh_tor);
+    DDP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ddp_row_mlp(const float *in, int32_t n, int32_t ld_in, const ddp_mlp_layer_t *layers_host, int32_t n_layers,
+                           const float *row_scale, float *out, int32_t ld_out, void *stream) {
+    if (!in || !layers_host || !out || n_layers <= 0 || n_layers > kMaxLayers) return DDP_E_ARG;
+    MlpPack mp;
+    mp.n = n_layers;
+    for (int i = 0; i < n_layers; ++i) {
+        mp.l[i] = layers_host[i];
+        if (mp.l[i].n_in > 256 || mp.l[i].n_out > 256 || !mp.l[i].wt) return DDP_E_SHAPE;
+    }
+    if (n <= 0) return 0;
+    row_mlp_kernel<<<n, 64, 0, (cudaStream_t)stream>>>(in, n, ld_in, mp, row_scale, out, ld_out);
+    DDP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ddp_tr_rot_head(const float *g, const float *sig, int32_t sig_dim, int32_t n_graphs, const float *tr_w1t,
+                               const float *tr_b1, const float *tr_w2, const float *tr_b2, const float *rot_w1t,
+                               const float *rot_b1, const float *rot_w2, const float *rot_b2, int32_t hid,
+                               const float *tr_sigma, const float *so3_norm, float *tr_out, float *rot_out, void *stream) {
+    if (!g || !sig || !tr_w1t || !rot_w1t || !tr_out || !rot_out || !tr_sigma || !so3_norm) return DDP_E_ARG;
+    if (hid > 128 || hid <= 0) return DDP_E_SHAPE;
+    if (n_graphs <= 0) return 0;
+    tr_rot_head_kernel<<<n_graphs, 128, 0, (cudaStream_t)stream>>>(g, sig, sig_dim, tr_w1t, tr_b1, tr_w2, tr_b2, rot_w1t, rot_b1,
+                                                                 rot_w2, rot_b2, hid, tr_sigma, so3_norm, tr_out, rot_out);
+    DDP_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,257 @@
+// Graph construction kernels: segmented radius search, kNN graph, degree counts.
+// Semantics of pytorch-cluster 1.6.1's CUDA kernels (see include/ddp_b200.h), redesigned as
+// warp-per-query ordered scans (radius) and shared-memory-staged per-thread scans (kNN) that keep
+// the exact fp32 arithmetic and the first-K-by-index / tie-by-index rules, with device-side edge
+// counts (no host synchronisation) and a scan + compaction into fixed-capacity edge buffers.
+#include "ddp_common.cuh"
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+
+__global__ void radius_scan_kernel(const float *__restrict__ x, const float *__restrict__ y,
+                                   const int32_t *__restrict__ ptr_x, const int32_t *__restrict__ ptr_y,
+                                   int num_examples, int n_y, const float *__restrict__ inv_scale, float r2,
+                                   int max_nbr, int graph_mode, int32_t *__restrict__ slab, int slab_w,
+                                   int32_t *__restrict__ counts) {
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (j >= n_y) return;
+    const int b = ddp_find_segment(ptr_y, num_examples, j);
+    float yx = y[3 * j], yy = y[3 * j + 1], yz = y[3 * j + 2];
+    float c = 1.f;
+    if (inv_scale != nullptr) {
+        c = inv_scale[b];
+        yx = __fdiv_rn(yx, c); yy = __fdiv_rn(yy, c); yz = __fdiv_rn(yz, c);
+    }
+    const int beg = ptr_x[b], end = ptr_x[b + 1];
+    int cnt_all = 0, cnt_emit = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int base = beg; base < end && cnt_all < max_nbr; base += 32) {
+        const int i = base + lane;
+        bool hit = false;
+        if (i < end) {
+            float xx = x[3 * i], xy = x[3 * i + 1], xz = x[3 * i + 2];
+            if (inv_scale != nullptr) { xx = __fdiv_rn(xx, c); xy = __fdiv_rn(xy, c); xz = __fdiv_rn(xz, c); }
+            hit = ddp_sqdist(xx, xy, xz, yx, yy, yz) < r2;
+        }
+        const unsigned m_all = __ballot_sync(0xffffffffu, hit);
+        const bool in_cap = hit && (cnt_all + __popc(m_all & lt) < max_nbr);
+        const bool emit = in_cap && !(graph_mode && i == j);
+        const unsigned m_emit = __ballot_sync(0xffffffffu, emit);
+        if (emit) slab[(size_t)j * slab_w + cnt_emit + __popc(m_emit & lt)] = i;
+        cnt_all += __popc(m_all);
+        cnt_emit += __popc(m_emit);
+    }
+    if (lane == 0) counts[j] = cnt_emit;
+}
+
+template <int KP>
+__device__ __forceinline__ void knn_insert(float (&bd)[KP], int (&bi)[KP], float d, int i) {
+    if (bd[KP - 1] > d) {
+        bd[KP - 1] = d; bi[KP - 1] = i;
+#pragma unroll
+        for (int e = KP - 1; e > 0; --e) {
+            if (bd[e - 1] > bd[e]) {
+                float td = bd[e - 1]; bd[e - 1] = bd[e]; bd[e] = td;
+                int ti = bi[e - 1]; bi[e - 1] = bi[e]; bi[e] = ti;
+            }
+        }
+    }
+}
+
+constexpr int kKnnThreads = 128;
+constexpr int kKnnStage = 2048;  // points staged per pass (24 KB)
+
+// One thread per centre; the centre's example is staged through shared memory in chunks when the
+// whole block lies inside one example (the common case), otherwise threads read global memory.
+template <int KP>
+__global__ void knn_scan_kernel(const float *__restrict__ x, const int32_t *__restrict__ ptr, int num_examples, int n,
+                                int32_t *__restrict__ slab, int slab_w, int32_t *__restrict__ counts) {
+    __shared__ float sx[kKnnStage * 3];
+    const int j = blockIdx.x * kKnnThreads + threadIdx.x;
+    const int j_first = blockIdx.x * kKnnThreads;
+    const int j_last = min(j_first + kKnnThreads, n) - 1;
+    const int b_first = ddp_find_segment(ptr, num_examples, j_first);
+    const int b_last = ddp_find_segment(ptr, num_examples, j_last);
+    float bd[KP];
+    int bi[KP];
+#pragma unroll
+    for (int e = 0; e < KP; ++e) { bd[e] = 1e10f; bi[e] = -1; }
+    float yx = 0.f, yy = 0.f, yz = 0.f;
+    if (j < n) { yx = x[3 * j]; yy = x[3 * j + 1]; yz = x[3 * j + 2]; }
+    if (b_first == b_last) {
+        const int beg = ptr[b_first], end = ptr[b_first + 1];
+        for (int base = beg; base < end; base += kKnnStage) {
+            const int m = min(kKnnStage, end - base);
+            __syncthreads();
+            for (int t = threadIdx.x; t < 3 * m; t += kKnnThreads) sx[t] = x[3 * base + t];
+            __syncthreads();
+            if (j < n) {
+                for (int t = 0; t < m; ++t)
+                    knn_insert<KP>(bd, bi, ddp_sqdist(sx[3 * t], sx[3 * t + 1], sx[3 * t + 2], yx, yy, yz), base + t);
+            }
+        }
+    } else if (j < n) {
+        const int b = ddp_find_segment(ptr, num_examples, j);
+        for (int i = ptr[b]; i < ptr[b + 1]; ++i)
+            knn_insert<KP>(bd, bi, ddp_sqdist(x[3 * i], x[3 * i + 1], x[3 * i + 2], yx, yy, yz), i);
+    }
+    if (j < n) {
+        int c = 0;
+#pragma unroll
+        for (int e = 0; e < KP; ++e) {
+            if (bi[e] != -1 && bi[e] != j) { slab[(size_t)j * slab_w + c] = bi[e]; ++c; }
+        }
+        counts[j] = c;
+    }
+}
+
+// Generic-k fallback (k + 1 <= 101, arrays in local memory).
+__global__ void knn_scan_generic_kernel(const float *__restrict__ x, const int32_t *__restrict__ ptr, int num_examples,
+                                        int n, int kp, int32_t *__restrict__ slab, int slab_w,
+                                        int32_t *__restrict__ counts) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    float bd[101];
+    int bi[101];
+    for (int e = 0; e < kp; ++e) { bd[e] = 1e10f; bi[e] = -1; }
+    const float yx = x[3 * j], yy = x[3 * j + 1], yz = x[3 * j + 2];
+    const int b = ddp_find_segment(ptr, num_examples, j);
+    for (int i = ptr[b]; i < ptr[b + 1]; ++i) {
+        const float d = ddp_sqdist(x[3 * i], x[3 * i + 1], x[3 * i + 2], yx, yy, yz);
+        for (int e1 = 0; e1 < kp; ++e1) {
+            if (bd[e1] > d) {
+                for (int e2 = kp - 1; e2 > e1; --e2) { bd[e2] = bd[e2 - 1]; bi[e2] = bi[e2 - 1]; }
+                bd[e1] = d; bi[e1] = i;
+                break;
+            }
+        }
+    }
+    int c = 0;
+    for (int e = 0; e < kp; ++e)
+        if (bi[e] != -1 && bi[e] != j) { slab[(size_t)j * slab_w + c] = bi[e]; ++c; }
+    counts[j] = c;
+}
+
+// Exclusive scan of counts[0..n) in place (single block), counts[n] = total, *n_edges = prefix + total.
+__global__ void scan_counts_kernel(int32_t *__restrict__ counts, int n, int prefix, int32_t *__restrict__ n_edges) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int v = (i < n) ? counts[i] : 0;
+        int s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += t;
+        }
+        if (lane == 31) warp_sums[wid] = s;
+        __syncthreads();
+        if (wid == 0) {
+            int w = (lane < (int)(blockDim.x >> 5)) ? warp_sums[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            warp_sums[lane] = w;  // inclusive
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        const int excl = carry + (wid > 0 ? warp_sums[wid - 1] : 0) + s - v;
+        if (i < n) counts[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry_s = carry + warp_sums[(blockDim.x >> 5) - 1];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        counts[n] = carry_s;
+        *n_edges = prefix + carry_s;
+    }
+}
+
+__global__ void compact_edges_kernel(const int32_t *__restrict__ slab, int slab_w, const int32_t *__restrict__ offs,
+                                     int n_y, int swap_rows, int prefix, int32_t *__restrict__ edge, int edge_cap) {
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (j >= n_y) return;
+    const int o = offs[j], c = offs[j + 1] - o;
+    for (int t = lane; t < c; t += 32) {
+        const int e = prefix + o + t;
+        if (e < edge_cap) {
+            const int i = slab[(size_t)j * slab_w + t];
+            edge[e] = swap_rows ? i : j;
+            edge[edge_cap + e] = swap_rows ? j : i;
+        }
+    }
+}
+
+__global__ void degree_kernel(const int32_t *__restrict__ idx, const int32_t *__restrict__ n_edges, int32_t *__restrict__ deg) {
+    const int n = *n_edges;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) atomicAdd(&deg[idx[e]], 1);
+}
+
+}  // namespace
+
+extern "C" int ddp_radius(const float *x, const float *y, const int32_t *ptr_x, const int32_t *ptr_y,
+                          int32_t num_examples, int32_t n_y, const float *inv_scale, float r, int32_t max_nbr,
+                          int32_t mode, int32_t prefix, int32_t *slab, int32_t slab_w, int32_t *counts,
+                          int32_t *edge, int32_t edge_cap, int32_t *n_edges_dev, void *stream) {
+    if (!x || !y || !ptr_x || !ptr_y || !slab || !counts || !edge || !n_edges_dev) return DDP_E_ARG;
+    if (num_examples <= 0 || n_y < 0 || max_nbr <= 0 || slab_w <= 0 || prefix < 0) return DDP_E_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const float r2 = (float)((double)r * (double)r);
+    if (n_y > 0) {
+        radius_scan_kernel<<<(n_y + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, st>>>(
+            x, y, ptr_x, ptr_y, num_examples, n_y, inv_scale, r2, max_nbr, mode & DDP_RADIUS_GRAPH, slab, slab_w, counts);
+        DDP_LAUNCH_CHECK();
+    }
+    scan_counts_kernel<<<1, 1024, 0, st>>>(counts, n_y, prefix, n_edges_dev);
+    DDP_LAUNCH_CHECK();
+    if (n_y > 0) {
+        compact_edges_kernel<<<(n_y + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, st>>>(
+            slab, slab_w, counts, n_y, mode & DDP_RADIUS_GRAPH, prefix, edge, edge_cap);
+        DDP_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" int ddp_knn_graph(const float *x, const int32_t *ptr, int32_t num_examples, int32_t n, int32_t k,
+                             int32_t *slab, int32_t slab_w, int32_t *counts, int32_t *edge, int32_t edge_cap,
+                             int32_t *n_edges_dev, void *stream) {
+    if (!x || !ptr || !slab || !counts || !edge || !n_edges_dev) return DDP_E_ARG;
+    if (num_examples <= 0 || n < 0 || k <= 0 || k > 100 || slab_w < k + 1) return DDP_E_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int kp = k + 1;
+    if (n > 0) {
+        const int grid = (n + kKnnThreads - 1) / kKnnThreads;
+        if (kp == 9) knn_scan_kernel<9><<<grid, kKnnThreads, 0, st>>>(x, ptr, num_examples, n, slab, slab_w, counts);
+        else if (kp == 13) knn_scan_kernel<13><<<grid, kKnnThreads, 0, st>>>(x, ptr, num_examples, n, slab, slab_w, counts);
+        else if (kp == 33) knn_scan_kernel<33><<<grid, kKnnThreads, 0, st>>>(x, ptr, num_examples, n, slab, slab_w, counts);
+        else knn_scan_generic_kernel<<<grid, kKnnThreads, 0, st>>>(x, ptr, num_examples, n, kp, slab, slab_w, counts);
+        DDP_LAUNCH_CHECK();
+    }
+    scan_counts_kernel<<<1, 1024, 0, st>>>(counts, n, 0, n_edges_dev);
+    DDP_LAUNCH_CHECK();
+    if (n > 0) {
+        compact_edges_kernel<<<(n + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, st>>>(
+            slab, slab_w, counts, n, 1, 0, edge, edge_cap);
+        DDP_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" int ddp_degree(const int32_t *idx, const int32_t *n_edges_dev, int32_t edge_cap, int32_t *deg, void *stream) {
+    if (!idx || !n_edges_dev || !deg) return DDP_E_ARG;
+    if (edge_cap <= 0) return 0;
+    int grid = (edge_cap + 255) / 256;
+    if (grid > 4 * ddp_num_sms()) grid = 4 * ddp_num_sms();
+    degree_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(idx, n_edges_dev, deg);
+    DDP_LAUNCH_CHECK();
+    return 0;
+}
