@@ -1,0 +1,632 @@
+"""All-atom score / confidence model: host mirror of ``models/all_atom_score_model.py``.
+
+``TensorProductScoreModel`` keeps the reference constructor signature (all_atom_score_model.py:22-32),
+module attribute names (so reference checkpoints load) and ``forward(data)``
+contract (:238-436), but evaluates everything through the ddp_b200 CUDA kernels:
+
+* ``make_plan(data)`` uploads one collated batch once and allocates every workspace (static tensors,
+  fixed-capacity dynamic edge buffers with device-side counts);
+* ``run_plan(plan, t)`` launches the forward without a single host synchronisation, which is what lets
+  ``sampling()`` keep the batch resident on the GPU for all steps.
+
+Supported configuration: ``parallel == 1``, no affinity head, ``separate_noise_schedule`` /
+``asyncronous_noise_schedule`` off, ``odd_parity`` off (the reference inference path).
+The per-graph diffusion time is read from ``data.complex_t['tr']`` (``set_time`` broadcasts the same
+value to every node of a graph, utils/diffusion_utils.py:124-149).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib, so3, torus, tp as tpmod
+from ._lib import ptr
+from .score_model import (FEATURE_DIMS, AtomEncoder, GaussianSmearing, OldAtomEncoder, TensorProductConvLayer, _TP)
+
+
+def _mlp(i, h, o, dropout):
+    return nn.Sequential(nn.Linear(i, h), nn.ReLU(), nn.Dropout(dropout), nn.Linear(h, o))
+
+
+class _EdgeSet:
+    """Fixed-capacity device edge buffer: row 0 = edge[:cap], row 1 = edge[cap:], live count on device."""
+
+    def __init__(self, cap, ns, sh_dim, device, with_slab=None):
+        self.cap = max(int(cap), 1)
+        self.edge = torch.zeros(2 * self.cap, dtype=torch.int32, device=device)
+        self.n_dev = torch.zeros(1, dtype=torch.int32, device=device)
+        self.sh = torch.zeros(self.cap, sh_dim, device=device)
+        self.emb = torch.zeros(self.cap, ns, device=device)
+        self.deg = {}
+        if with_slab is not None:
+            n_q, w = with_slab
+            self.slab_w = max(int(w), 1)
+            self.slab = torch.zeros(max(int(n_q), 1) * self.slab_w, dtype=torch.int32, device=device)
+            self.counts = torch.zeros(max(int(n_q), 1) + 1, dtype=torch.int32, device=device)
+
+    def row(self, r):
+        return self.edge.data_ptr() + 4 * self.cap * r
+
+    def set_static(self, ei):
+        n = ei.shape[1]
+        self.edge[:n] = ei[0].to(torch.int32)
+        self.edge[self.cap:self.cap + n] = ei[1].to(torch.int32)
+        self.n_dev.fill_(n)
+
+    def edge_index(self):
+        """Host-synchronising view [2, E] int64 (tests / drop-in side effects only)."""
+        n = int(self.n_dev.item())
+        return torch.stack([self.edge[:n], self.edge[self.cap:self.cap + n]]).long()
+
+
+class Plan:
+    pass
+
+
+class TensorProductScoreModel(nn.Module):
+    def __init__(self, t_to_sigma, device, timestep_emb_func, in_lig_edge_features=4, sigma_embed_dim=32, sh_lmax=2,
+                 ns=16, nv=4, num_conv_layers=2, lig_max_radius=5, rec_max_radius=30, cross_max_distance=250,
+                 center_max_distance=30, distance_embed_dim=32, cross_distance_embed_dim=32, no_torsion=False,
+                 scale_by_sigma=True, norm_by_sigma=True, use_second_order_repr=False, batch_norm=True,
+                 dynamic_max_cross=False, dropout=0.0, smooth_edges=False, odd_parity=False,
+                 separate_noise_schedule=False, lm_embedding_type=False, confidence_mode=False,
+                 confidence_dropout=0, confidence_no_batchnorm=False, asyncronous_noise_schedule=False,
+                 affinity_prediction=False, parallel=1, parallel_aggregators="mean max min std",
+                 num_confidence_outputs=1, fixed_center_conv=False, atom_max_neighbors=None,
+                 no_aminoacid_identities=False, flexible_sidechains=False, include_miscellaneous_atoms=False,
+                 use_old_atom_encoder=False):
+        super().__init__()
+        if parallel != 1 or affinity_prediction or separate_noise_schedule or asyncronous_noise_schedule or odd_parity \
+                or smooth_edges or include_miscellaneous_atoms:
+            raise NotImplementedError('configuration outside the accelerated inference path (see module docstring)')
+        if not lm_embedding_type:
+            lm_embedding_type = None
+        self.t_to_sigma, self.timestep_emb_func = t_to_sigma, timestep_emb_func
+        self.in_lig_edge_features, self.sigma_embed_dim = in_lig_edge_features, sigma_embed_dim
+        self.lig_max_radius, self.rec_max_radius = lig_max_radius, rec_max_radius
+        self.cross_max_distance, self.dynamic_max_cross = cross_max_distance, dynamic_max_cross
+        self.center_max_distance, self.distance_embed_dim = center_max_distance, distance_embed_dim
+        self.cross_distance_embed_dim = cross_distance_embed_dim
+        self.sh_lmax = sh_lmax
+        self.sh_irreps = [(1, l, (-1) ** l) for l in range(sh_lmax + 1)]
+        self.sh_dim = (sh_lmax + 1) ** 2
+        self.ns, self.nv = ns, nv
+        self.scale_by_sigma, self.device, self.no_torsion = scale_by_sigma, device, no_torsion
+        self.num_conv_layers, self.confidence_mode = num_conv_layers, confidence_mode
+        self.fixed_center_conv, self.atom_max_neighbors = fixed_center_conv, atom_max_neighbors
+        self.no_aminoacid_identities, self.flexible_sidechains = no_aminoacid_identities, flexible_sidechains
+        self.lm_embedding_type = lm_embedding_type
+        self.conv_mode = 'fp32'          # 'fp32' | 'bf16' | 'bf16x3'  (tensor-core modes need FasterTP convs)
+
+        enc = OldAtomEncoder if use_old_atom_encoder else AtomEncoder
+        self.lig_node_embedding = enc(ns, FEATURE_DIMS['lig'], sigma_embed_dim)
+        self.lig_edge_embedding = _mlp(in_lig_edge_features + sigma_embed_dim + distance_embed_dim, ns, ns, dropout)
+        self.rec_node_embedding = enc(ns, FEATURE_DIMS['rec_residue'], sigma_embed_dim, lm_embedding_type)
+        self.rec_edge_embedding = _mlp(sigma_embed_dim + distance_embed_dim, ns, ns, dropout)
+        self.atom_node_embedding = enc(ns, FEATURE_DIMS['rec_atom'], sigma_embed_dim)
+        self.atom_edge_embedding = _mlp(sigma_embed_dim + distance_embed_dim, ns, ns, dropout)
+        self.lr_edge_embedding = _mlp(sigma_embed_dim + cross_distance_embed_dim, ns, ns, dropout)
+        self.ar_edge_embedding = _mlp(sigma_embed_dim + distance_embed_dim, ns, ns, dropout)
+        self.la_edge_embedding = _mlp(sigma_embed_dim + cross_distance_embed_dim, ns, ns, dropout)
+        self.lig_distance_expansion = GaussianSmearing(0.0, lig_max_radius, distance_embed_dim)
+        self.rec_distance_expansion = GaussianSmearing(0.0, rec_max_radius, distance_embed_dim)
+        self.cross_distance_expansion = GaussianSmearing(0.0, cross_max_distance, cross_distance_embed_dim)
+
+        if use_second_order_repr:
+            seq = [f'{ns}x0e', f'{ns}x0e + {nv}x1o + {nv}x2e', f'{ns}x0e + {nv}x1o + {nv}x2e + {nv}x1e + {nv}x2o',
+                   f'{ns}x0e + {nv}x1o + {nv}x2e + {nv}x1e + {nv}x2o + {ns}x0o']
+        else:
+            seq = [f'{ns}x0e', f'{ns}x0e + {nv}x1o', f'{ns}x0e + {nv}x1o + {nv}x1e', f'{ns}x0e + {nv}x1o + {nv}x1e + {ns}x0o']
+        self.irrep_seq = seq
+        faster = sh_lmax == 1 and not use_second_order_repr
+        self.faster = faster
+        convs = []
+        for i in range(num_conv_layers):
+            for _ in range(9):
+                convs.append(TensorProductConvLayer(seq[min(i, 3)], self.sh_irreps, seq[min(i + 1, 3)], 3 * ns, residual=False,
+                                                    batch_norm=batch_norm, dropout=dropout, faster=faster))
+        self.conv_layers = nn.ModuleList(convs)
+        last = seq[min(num_conv_layers, 3)]
+        if confidence_mode:
+            cin = (2 * ns if num_conv_layers >= 3 else ns) * (2 if flexible_sidechains else 1)
+            bn = (lambda: nn.Identity()) if confidence_no_batchnorm else (lambda: nn.BatchNorm1d(ns))
+            self.confidence_predictor = nn.Sequential(
+                nn.Linear(cin, ns), bn(), nn.ReLU(), nn.Dropout(confidence_dropout),
+                nn.Linear(ns, ns), bn(), nn.ReLU(), nn.Dropout(confidence_dropout),
+                nn.Linear(ns, num_confidence_outputs))
+        else:
+            self.center_distance_expansion = GaussianSmearing(0.0, center_max_distance, distance_embed_dim)
+            self.center_edge_embedding = _mlp(distance_embed_dim + sigma_embed_dim, ns, ns, dropout)
+            self.final_conv = TensorProductConvLayer(last, self.sh_irreps, '2x1o + 2x1e', 2 * ns, residual=False,
+                                                     dropout=dropout, batch_norm=batch_norm, faster=faster)
+            self.tr_final_layer = nn.Sequential(nn.Linear(1 + sigma_embed_dim, ns), nn.Dropout(dropout), nn.ReLU(), nn.Linear(ns, 1))
+            self.rot_final_layer = nn.Sequential(nn.Linear(1 + sigma_embed_dim, ns), nn.Dropout(dropout), nn.ReLU(), nn.Linear(ns, 1))
+            tor_sh = tpmod.full_tp_out_irreps(self.sh_irreps, '1x2e')
+            if not no_torsion:
+                self.final_edge_embedding = _mlp(distance_embed_dim, ns, ns, dropout)
+                self.final_tp_tor = nn.Module()          # o3.FullTensorProduct has no parameters
+                self.tor_bond_conv = self._tor_conv(last, tor_sh, ns, dropout, batch_norm)
+                self.tor_final_layer = nn.Sequential(nn.Linear(2 * ns, ns, bias=False), nn.Tanh(), nn.Dropout(dropout),
+                                                     nn.Linear(ns, 1, bias=False))
+            if flexible_sidechains:
+                self.sidechain_final_edge_embedding = _mlp(distance_embed_dim, ns, ns, dropout)
+                self.final_tp_sc_tor = nn.Module()
+                self.sc_tor_bond_conv = self._tor_conv(last, tor_sh, ns, dropout, batch_norm)
+                self.sc_tor_final_layer = nn.Sequential(nn.Linear(2 * ns, ns, bias=False), nn.Tanh(), nn.Dropout(dropout),
+                                                        nn.Linear(ns, 1, bias=False))
+        self._packed = None
+
+    @staticmethod
+    def _tor_conv(last, tor_sh, ns, dropout, batch_norm):
+        conv = TensorProductConvLayer(last, tor_sh, f'{ns}x0o + {ns}x0e', 3 * ns, residual=False, dropout=dropout,
+                                      batch_norm=batch_norm)
+        # only the 1o part of sh_tor is materialised (ddp_tor_edge_sh); valid while node irreps have l <= 1
+        spec = tpmod.fctp_spec(last, tor_sh, f'{ns}x0o + {ns}x0e', sh_keep=[0])
+        assert spec.weight_numel == conv.tp.weight_numel
+        conv.tp = _TP(spec)
+        return conv
+
+    # ------------------------------------------------------------------------------------------ packing
+    def _load_from_state_dict(self, *a, **k):
+        self._packed = None
+        return super()._load_from_state_dict(*a, **k)
+
+    def _edge_mlp_pack(self, seq, rbf, dev, layout):
+        """layout: tuple of ('pre', n) / ('sig', n) / ('rbf', n) giving the column order of Linear 0."""
+        W, b1 = seq[0].weight.detach(), seq[0].bias.detach()
+        cols, o = {}, 0
+        for kind, n in layout:
+            cols[kind] = W[:, o:o + n]
+            o += n
+        assert o == W.shape[1]
+        f32 = dict(dtype=torch.float32, device=dev)
+        pk = dict(w_pre=cols['pre'].T.contiguous().to(**f32) if 'pre' in cols else None,
+                  w_rbf=cols['rbf'].T.contiguous().to(**f32),
+                  w_sig=cols['sig'].T.contiguous().to(**f32) if 'sig' in cols else None,
+                  b1=b1.contiguous().to(**f32), w2=seq[3].weight.detach().T.contiguous().to(**f32),
+                  b2=seq[3].bias.detach().contiguous().to(**f32), offset=rbf.offset.detach().contiguous().to(**f32))
+        pk['desc'] = _lib.EdgeMlp(w_pre=ptr(pk['w_pre']), w_rbf=ptr(pk['w_rbf']), w2=ptr(pk['w2']), b2=ptr(pk['b2']),
+                                  b1=ptr(pk['b1']), rbf_offset=ptr(pk['offset']), rbf_coeff=float(rbf.coeff),
+                                  n_pre=cols['pre'].shape[1] if 'pre' in cols else 0, n_rbf=cols['rbf'].shape[1],
+                                  ns=self.ns, sh_dim=self.sh_dim)
+        return pk
+
+    def packed(self):
+        dev = next(self.parameters()).device
+        if self._packed is not None and self._packed['device'] == dev:
+            return self._packed
+        if dev.type != 'cuda':
+            raise RuntimeError('the ddp_b200 score model runs on CUDA only (no CPU fallback); call model.to("cuda")')
+        P = dict(device=dev)
+        sd, dd, cd, ns = self.sigma_embed_dim, self.distance_embed_dim, self.cross_distance_embed_dim, self.ns
+        f32 = dict(dtype=torch.float32, device=dev)
+        em = {}
+        em['ll'] = self._edge_mlp_pack(self.lig_edge_embedding, self.lig_distance_expansion, dev,
+                                       (('pre', self.in_lig_edge_features), ('sig', sd), ('rbf', dd)))
+        em['rr'] = self._edge_mlp_pack(self.rec_edge_embedding, self.rec_distance_expansion, dev, (('sig', sd), ('rbf', dd)))
+        em['aa'] = self._edge_mlp_pack(self.atom_edge_embedding, self.lig_distance_expansion, dev, (('sig', sd), ('rbf', dd)))
+        em['lr'] = self._edge_mlp_pack(self.lr_edge_embedding, self.cross_distance_expansion, dev, (('sig', sd), ('rbf', cd)))
+        em['la'] = self._edge_mlp_pack(self.la_edge_embedding, self.cross_distance_expansion, dev, (('sig', sd), ('rbf', cd)))
+        em['ar'] = self._edge_mlp_pack(self.ar_edge_embedding, self.rec_distance_expansion, dev, (('sig', sd), ('rbf', dd)))
+        proj_names = ['lig_node', 'rec_node', 'atom_node', 'll', 'rr', 'aa', 'lr', 'la', 'ar']
+        ws, bs = [], []
+        for enc in (self.lig_node_embedding, self.rec_node_embedding, self.atom_node_embedding):
+            w, b = enc.sigma_proj()
+            ws.append(w.detach().to(**f32))
+            bs.append(b.detach().to(**f32))
+        for k in ('ll', 'rr', 'aa', 'lr', 'la', 'ar'):
+            ws.append(em[k]['w_sig'])
+            bs.append(em[k]['b1'])
+        if not self.confidence_mode:
+            em['center'] = self._edge_mlp_pack(self.center_edge_embedding, self.center_distance_expansion, dev,
+                                               (('rbf', dd), ('sig', sd)))
+            proj_names.append('center')
+            ws.append(em['center']['w_sig'])
+            bs.append(em['center']['b1'])
+            if not self.no_torsion:
+                em['tor'] = self._edge_mlp_pack(self.final_edge_embedding, self.lig_distance_expansion, dev, (('rbf', dd),))
+            if self.flexible_sidechains:
+                em['sc'] = self._edge_mlp_pack(self.sidechain_final_edge_embedding, self.lig_distance_expansion, dev, (('rbf', dd),))
+        P['em'], P['proj_names'] = em, proj_names
+        P['proj_w'], P['proj_b'] = torch.stack(ws).contiguous(), torch.stack(bs).contiguous()
+        half = sd // 2
+        P['freq'] = torch.exp(torch.arange(half, dtype=torch.float32) * -(np.log(10000) / (half - 1))).to(dev)
+        P['convs'] = [c.packed(dev, ns, ns) for c in self.conv_layers]
+        if not self.confidence_mode:
+            P['final_conv'] = self.final_conv.packed(dev, ns, ns)
+            def lin(l):
+                return l.weight.detach().T.contiguous().to(**f32), (l.bias.detach().contiguous().to(**f32) if l.bias is not None else None)
+            P['tr'] = lin(self.tr_final_layer[0]) + lin(self.tr_final_layer[3])
+            P['rot'] = lin(self.rot_final_layer[0]) + lin(self.rot_final_layer[3])
+            P['c121'] = torch.tensor((tpmod.wigner_3j(1, 2, 1) * np.sqrt(3.0)).reshape(-1), **f32)
+            if not self.no_torsion:
+                P['tor_conv'] = self.tor_bond_conv.packed(dev, ns, ns)
+                P['tor_mlp'] = [lin(self.tor_final_layer[0]), lin(self.tor_final_layer[3])]
+            if self.flexible_sidechains:
+                P['sc_conv'] = self.sc_tor_bond_conv.packed(dev, ns, ns)
+                P['sc_mlp'] = [lin(self.sc_tor_final_layer[0]), lin(self.sc_tor_final_layer[3])]
+        else:
+            cp = self.confidence_predictor
+            layers = []
+            for li, bi in ((0, 1), (4, 5), (8, None)):
+                W, b = cp[li].weight.detach().double(), cp[li].bias.detach().double()
+                if bi is not None and isinstance(cp[bi], nn.BatchNorm1d):
+                    bnm = cp[bi]
+                    s = bnm.weight.detach().double() / torch.sqrt(bnm.running_var.detach().double() + bnm.eps)
+                    W, b = W * s[:, None], (b - bnm.running_mean.detach().double()) * s + bnm.bias.detach().double()
+                layers.append((W.T.float().contiguous().to(dev), b.float().contiguous().to(dev)))
+            P['conf_mlp'] = layers
+        self._packed = P
+        return P
+
+    # ------------------------------------------------------------------------------------------ plan
+    def make_plan(self, data):
+        """Upload one collated batch and allocate all workspaces (no per-step allocation afterwards)."""
+        P = self.packed()
+        dev = P['device']
+        ns, sh_dim = self.ns, self.sh_dim
+        i32 = dict(dtype=torch.int32, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        pl = Plan()
+        pl.device = dev
+        lig, rec, atom = data['ligand'], data['receptor'], data['atom']
+        B = int(data.num_graphs) if hasattr(data, 'num_graphs') or 'num_graphs' in data else 1
+        pl.B = B
+
+        def batch_of(store):
+            return store.batch if 'batch' in store else torch.zeros(store.pos.shape[0], dtype=torch.long)
+
+        def ptr_of(batch):
+            cnt = torch.bincount(batch.cpu(), minlength=B)
+            return torch.cat([torch.zeros(1, dtype=torch.long), cnt.cumsum(0)])
+        lb, rb, ab = batch_of(lig).cpu(), batch_of(rec).cpu(), batch_of(atom).cpu()
+        lp, rp, ap = ptr_of(lb), ptr_of(rb), ptr_of(ab)
+        pl.NL, pl.NR, pl.NA = int(lp[-1]), int(rp[-1]), int(ap[-1])
+        pl.lig_ptr_h, pl.rec_ptr_h, pl.atom_ptr_h = lp, rp, ap
+        pl.lig_ptr, pl.rec_ptr, pl.atom_ptr = lp.to(**i32), rp.to(**i32), ap.to(**i32)
+        pl.lig_batch, pl.rec_batch, pl.atom_batch = lb.to(**i32), rb.to(**i32), ab.to(**i32)
+        pl.lig_pos = lig.pos.to(**f32).contiguous().clone()
+        pl.rec_pos = rec.pos.to(**f32).contiguous().clone()
+        pl.atom_pos = atom.pos.to(**f32).contiguous().clone()
+        # static node-embedding parts (time independent, once per complex)
+        with torch.no_grad():
+            rx = rec.x.to(dev)
+            if self.no_aminoacid_identities:
+                rx = rx * 0
+            pl.lig_static = self.lig_node_embedding.static_part(lig.x.to(dev)).float().contiguous()
+            pl.atom_static = self.atom_node_embedding.static_part(atom.x.to(dev)).float().contiguous()
+            pl.rec_static = self.rec_node_embedding.static_part(rx[:, :1], rx[:, 1:].float() if self.lm_embedding_type else None).float().contiguous()
+        F = tpmod.irreps_dim(tpmod.parse_irreps(self.irrep_seq[3]))
+        pl.F = F
+        pl.x = {k: [torch.zeros(n, F, **f32), torch.zeros(n, F, **f32)] for k, n in (('l', pl.NL), ('r', pl.NR), ('a', pl.NA))}
+        # ---- edge sets ---------------------------------------------------------------------------
+        nl_g, nr_g, na_g = (lp[1:] - lp[:-1]), (rp[1:] - rp[:-1]), (ap[1:] - ap[:-1])
+        bond_ei = data['ligand', 'ligand'].edge_index
+        Eb = bond_ei.shape[1]
+        pl.Eb = Eb
+        es = {}
+        es['ll'] = _EdgeSet(Eb + int(torch.minimum(nl_g - 1, torch.tensor(32)).clamp(min=0).mul(nl_g).sum()), ns, sh_dim, dev,
+                            with_slab=(pl.NL, 33))
+        es['ll'].edge[:Eb] = bond_ei[0].to(**i32)
+        es['ll'].edge[es['ll'].cap:es['ll'].cap + Eb] = bond_ei[1].to(**i32)
+        pl.bond_attr = data['ligand', 'ligand'].edge_attr.to(**f32).contiguous()
+        k = self.atom_max_neighbors if self.atom_max_neighbors else 32
+        pl.knn_k = k
+        es['aa'] = _EdgeSet(int(torch.minimum(na_g - 1, torch.tensor(k + 1)).clamp(min=0).mul(na_g).sum()), ns, sh_dim, dev,
+                            with_slab=(pl.NA, k + 1))
+        es['lr'] = _EdgeSet(int((nl_g * nr_g).sum()), ns, sh_dim, dev, with_slab=(pl.NL, int(nr_g.max())))
+        es['la'] = _EdgeSet(int((nl_g * na_g).sum()), ns, sh_dim, dev, with_slab=(pl.NL, int(na_g.max())))
+        rr = data['receptor', 'receptor'].edge_index
+        es['rr'] = _EdgeSet(rr.shape[1], ns, sh_dim, dev)
+        es['rr'].set_static(rr.to(dev))
+        ar = data['atom', 'receptor'].edge_index
+        es['ar'] = _EdgeSet(ar.shape[1], ns, sh_dim, dev)
+        es['ar'].set_static(ar.to(dev))
+        pl.es = es
+        # degree buffers: (edge set, row) -> int32 [n nodes of that side]
+        sides = {('ll', 0): pl.NL, ('lr', 0): pl.NL, ('lr', 1): pl.NR, ('la', 0): pl.NL, ('la', 1): pl.NA, ('aa', 0): pl.NA,
+                 ('ar', 0): pl.NA, ('ar', 1): pl.NR, ('rr', 0): pl.NR}
+        pl.deg_arena = torch.zeros(sum(sides.values()), **i32)
+        o = 0
+        pl.deg_static = {}
+        for (nm, r), n in sides.items():
+            es[nm].deg[r] = pl.deg_arena[o:o + n]
+            o += n
+        # scatter-sum arena: three updates per node type
+        pl.sum_arena = torch.zeros(3 * (pl.NL + pl.NA + pl.NR) * F, **f32)
+        pl.sig = torch.zeros(B, self.sigma_embed_dim, **f32)
+        pl.U = torch.zeros(len(P['proj_names']), B, ns, **f32)
+        # ---- per-forward host scalars -> one pinned staging buffer ------------------------------
+        T = 0 if self.no_torsion or self.confidence_mode else int(lig.edge_mask.sum())
+        pl.T = T
+        S = 0
+        has_flex = self.flexible_sidechains and 'flexResidues' in data and len(data['flexResidues']) > 0 \
+            and 'edge_idx' in data['flexResidues']
+        if has_flex:
+            S = int(data['flexResidues'].edge_idx.shape[0])
+        pl.S = S
+        pl.n_scal = 4 * B + T + S
+        pl.scal = torch.zeros(pl.n_scal, **f32)
+        if not self.confidence_mode:
+            ce = torch.stack([lb, torch.arange(pl.NL)])
+            es['center'] = _EdgeSet(pl.NL, ns, sh_dim, dev)
+            es['center'].set_static(ce.to(dev))
+            pl.center = torch.zeros(B, 3, **f32)
+            pl.center_deg = (lp[1:] - lp[:-1]).to(**i32)
+            pl.g_sum = torch.zeros(B, 12, **f32)
+            pl.g = torch.zeros(B, 12, **f32)
+            pl.tr_out, pl.rot_out = torch.zeros(B, 3, **f32), torch.zeros(B, 3, **f32)
+            if T > 0:
+                bonds = bond_ei[:, lig.edge_mask.bool()].long()
+                pl.tor_batch_h = lb[bonds[0]]
+                pl.tor = self._bond_head_plan(bonds, pl.tor_batch_h, B, pl.NL, int(nl_g.max()), dev)
+            if S > 0:
+                fr = data['flexResidues']
+                frb = fr.batch.cpu() if 'batch' in fr else torch.zeros(S, dtype=torch.long)
+                bonds = ap[:-1][frb] + fr.edge_idx.T.long().cpu()          # get_sc_tor_bonds, :638-652
+                pl.sc_batch_h = frb
+                pl.sc = self._bond_head_plan(bonds, frb, B, pl.NA, int(na_g.max()), dev)
+            pl.tor_out = torch.zeros(max(T, 1), **f32)
+            pl.sc_out = torch.zeros(max(S, 1), **f32)
+        else:
+            w = 2 * ns if self.num_conv_layers >= 3 else ns
+            pl.conf_in = torch.zeros(B, w * (2 if self.flexible_sidechains else 1), **f32)
+            nout = self.confidence_predictor[8].out_features
+            pl.conf_out = torch.zeros(B, nout, **f32)
+            if self.flexible_sidechains and S > 0:
+                fr = data['flexResidues']
+                frb = fr.batch.cpu() if 'batch' in fr else torch.zeros(S, dtype=torch.long)
+                fa = (ap[:-1][frb] + fr.edge_idx.T.long().cpu()).unique()
+                fcnt = torch.bincount(ab[fa], minlength=B)
+                pl.flex_atoms = fa.to(**i32)
+                pl.flex_ptr = torch.cat([torch.zeros(1, dtype=torch.long), fcnt.cumsum(0)]).to(**i32)
+        return pl
+
+    def _bond_head_plan(self, bonds, bond_batch, B, n_nodes, max_seg, dev):
+        i32 = dict(dtype=torch.int32, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        h = Plan()
+        n = bonds.shape[1]
+        h.n = n
+        h.bonds = bonds.to(**i32).contiguous()                      # [2, n]
+        cnt = torch.bincount(bond_batch, minlength=B)
+        h.ptr = torch.cat([torch.zeros(1, dtype=torch.long), cnt.cumsum(0)]).to(**i32)
+        h.batch = bond_batch.to(**i32)
+        h.mid, h.y2, h.attr = torch.zeros(n, 3, **f32), torch.zeros(n, 5, **f32), torch.zeros(n, self.ns, **f32)
+        h.es = _EdgeSet(n * min(32, max_seg), self.ns, self.sh_dim, dev, with_slab=(n, min(32, max_seg)))
+        h.sh_tor = torch.zeros(h.es.cap, 3, **f32)
+        h.deg = torch.zeros(n, **i32)
+        h.sum = torch.zeros(n, 2 * self.ns, **f32)
+        h.feat = torch.zeros(n, 2 * self.ns, **f32)
+        return h
+
+    # ------------------------------------------------------------------------------------------ scalars
+    def _host_scalars(self, pl, complex_t):
+        """t, sigma, score norms and cutoffs per graph, computed on the host exactly like the reference
+        (all_atom_score_model.py:243-245, 263, 383-384, 405-407, 432-433) and staged in one pinned buffer."""
+        B, T, S = pl.B, pl.T, pl.S
+        ct = [torch.as_tensor(complex_t[k]).detach().float().cpu().reshape(-1)[:B] for k in ('tr', 'rot', 'tor', 'sc_tor')]
+        if self.confidence_mode:
+            tr_s, rot_s, tor_s, sc_s = ct
+        else:
+            tr_s, rot_s, tor_s, sc_s = self.t_to_sigma(*ct)
+        # fresh pinned staging buffer per call: the caching host allocator keeps it alive until the async copy ran
+        h = torch.zeros(pl.n_scal, dtype=torch.float32).pin_memory()
+        h[0:B] = ct[0]
+        h[B:2 * B] = tr_s
+        if not self.confidence_mode:
+            h[2 * B:3 * B] = so3.score_norm(rot_s.float())
+        h[3 * B:4 * B] = (tr_s * 3 + 20) if self.dynamic_max_cross else float(self.cross_max_distance)
+        if T > 0:
+            es = tor_s[pl.tor_batch_h]
+            h[4 * B:4 * B + T] = torch.sqrt(torch.tensor(torus.score_norm(es.numpy()))).float()
+        if S > 0 and not self.confidence_mode:
+            es = sc_s[pl.sc_batch_h]
+            h[4 * B + T:4 * B + T + S] = torch.sqrt(torch.tensor(torus.score_norm(es.numpy()))).float()
+        pl.scal.copy_(h, non_blocking=True)
+
+    # ------------------------------------------------------------------------------------------ forward
+    def _conv(self, L, st, layer, pk, es, flip, x, p1, i1_row, p2, i2_row, sum_buf, ew=None):
+        """One fused tensor-product convolution: agg / gather rows follow ``flip`` (torch.flip of edge_index)."""
+        agg_r, gat_r = (1, 0) if flip else (0, 1)
+        ed = _lib.TpEdges(emb=ptr(es.emb), p1=ptr(p1) if p1 is not None else None,
+                          i1=es.row(i1_row) if p1 is not None else None, ld1=p1.shape[1] if p1 is not None else 0,
+                          p2=ptr(p2) if p2 is not None else None, i2=es.row(i2_row) if p2 is not None else None,
+                          ld2=p2.shape[1] if p2 is not None else 0, x=ptr(x), gather=es.row(gat_r), ldx=x.shape[1],
+                          sh=ptr(es.sh_conv if hasattr(es, 'sh_conv') else es.sh), agg=es.row(agg_r), ew=None,
+                          n_edges_dev=ptr(es.n_dev), edge_cap=es.cap)
+        if self.conv_mode != 'fp32' and pk.spec.faster:
+            mode = 0 if self.conv_mode == 'bf16' else 1
+            img = pk.umma_image(layer, mode, x.device)
+            _lib.check(L.ddp_tpconv_umma(C.byref(pk.cdesc), ptr(img), mode, C.byref(ed), ptr(sum_buf), st), 'ddp_tpconv_umma')
+        else:
+            _lib.check(L.ddp_tpconv_fp32(C.byref(pk.cdesc), C.byref(ed), ptr(sum_buf), st), 'ddp_tpconv_fp32')
+
+    def run_plan(self, pl, complex_t, return_layers=False):
+        """Forward on a resident plan.  Returns device tensors; performs no host synchronisation."""
+        P = self.packed()
+        L = _lib.lib()
+        st = _lib.stream_ptr()
+        B, ns, F = pl.B, self.ns, pl.F
+        es = pl.es
+        self._host_scalars(pl, complex_t)
+        t_dev, tr_sigma, so3n, cutoff = pl.scal[0:B], pl.scal[B:2 * B], pl.scal[2 * B:3 * B], pl.scal[3 * B:4 * B]
+        chk = _lib.check
+        names = P['proj_names']
+        scale = float(self.timestep_emb_func.keywords.get('scale', 1.0)) if hasattr(self.timestep_emb_func, 'keywords') else float(getattr(self.timestep_emb_func, 'scale', 1.0))
+        chk(L.ddp_graph_sigma_proj(ptr(t_dev), B, scale, ptr(P['freq']), self.sigma_embed_dim, ptr(P['proj_w']), ptr(P['proj_b']),
+                                   len(names), ns, ptr(pl.sig), ptr(pl.U), st), 'ddp_graph_sigma_proj')
+        U = {n: pl.U[i] for i, n in enumerate(names)}
+        cur = {k: 0 for k in 'lra'}
+        xl, xr, xa = pl.x['l'][0], pl.x['r'][0], pl.x['a'][0]
+        chk(L.ddp_node_init(ptr(pl.lig_static), ptr(U['lig_node']), ptr(pl.lig_batch), pl.NL, ns, ptr(xl), F, st), 'node_init')
+        chk(L.ddp_node_init(ptr(pl.rec_static), ptr(U['rec_node']), ptr(pl.rec_batch), pl.NR, ns, ptr(xr), F, st), 'node_init')
+        chk(L.ddp_node_init(ptr(pl.atom_static), ptr(U['atom_node']), ptr(pl.atom_batch), pl.NA, ns, ptr(xa), F, st), 'node_init')
+        # ---- dynamic graphs --------------------------------------------------------------------
+        e = es['ll']
+        chk(L.ddp_radius(ptr(pl.lig_pos), ptr(pl.lig_pos), ptr(pl.lig_ptr), ptr(pl.lig_ptr), B, pl.NL, None,
+                         float(self.lig_max_radius), 33, 1, pl.Eb, ptr(e.slab), e.slab_w, ptr(e.counts), ptr(e.edge), e.cap,
+                         ptr(e.n_dev), st), 'ddp_radius(ll)')
+        e = es['aa']
+        chk(L.ddp_knn_graph(ptr(pl.atom_pos), ptr(pl.atom_ptr), B, pl.NA, pl.knn_k, ptr(e.slab), e.slab_w, ptr(e.counts),
+                            ptr(e.edge), e.cap, ptr(e.n_dev), st), 'ddp_knn_graph')
+        e = es['lr']
+        if self.dynamic_max_cross:
+            chk(L.ddp_radius(ptr(pl.rec_pos), ptr(pl.lig_pos), ptr(pl.rec_ptr), ptr(pl.lig_ptr), B, pl.NL, ptr(cutoff), 1.0, 10000,
+                             0, 0, ptr(e.slab), e.slab_w, ptr(e.counts), ptr(e.edge), e.cap, ptr(e.n_dev), st), 'ddp_radius(lr)')
+        else:
+            chk(L.ddp_radius(ptr(pl.rec_pos), ptr(pl.lig_pos), ptr(pl.rec_ptr), ptr(pl.lig_ptr), B, pl.NL, None,
+                             float(self.cross_max_distance), 10000, 0, 0, ptr(e.slab), e.slab_w, ptr(e.counts), ptr(e.edge), e.cap,
+                             ptr(e.n_dev), st), 'ddp_radius(lr)')
+        e = es['la']
+        chk(L.ddp_radius(ptr(pl.atom_pos), ptr(pl.lig_pos), ptr(pl.atom_ptr), ptr(pl.lig_ptr), B, pl.NL, None,
+                         float(self.lig_max_radius), 10000, 0, 0, ptr(e.slab), e.slab_w, ptr(e.counts), ptr(e.edge), e.cap,
+                         ptr(e.n_dev), st), 'ddp_radius(la)')
+        pl.deg_arena.zero_()
+        for nm in ('ll', 'lr', 'la', 'aa', 'ar', 'rr'):
+            for r, d in es[nm].deg.items():
+                chk(L.ddp_degree(es[nm].row(r), ptr(es[nm].n_dev), es[nm].cap, ptr(d), st), 'ddp_degree')
+        # ---- edge geometry + embeddings ------------------------------------------------------------
+        em = P['em']
+        geo = {'ll': (pl.lig_pos, pl.lig_pos, pl.lig_batch), 'rr': (pl.rec_pos, pl.rec_pos, pl.rec_batch),
+               'aa': (pl.atom_pos, pl.atom_pos, pl.atom_batch), 'lr': (pl.lig_pos, pl.rec_pos, pl.lig_batch),
+               'la': (pl.lig_pos, pl.atom_pos, pl.lig_batch), 'ar': (pl.atom_pos, pl.rec_pos, pl.atom_batch)}
+        for nm, (pa, pb, ga) in geo.items():
+            e = es[nm]
+            pre, npre = (pl.bond_attr, pl.Eb) if nm == 'll' else (None, 0)
+            chk(L.ddp_edge_embed(ptr(pa), ptr(pb), ptr(e.edge), e.cap, ptr(e.n_dev), ptr(ga), ptr(pre), npre, ptr(U[nm]),
+                                 C.byref(em[nm]['desc']), ptr(e.sh), ptr(e.emb), st), f'ddp_edge_embed({nm})')
+        # ---- interaction layers (all_atom_score_model.py:271-324) --------------------------------
+        layers_out = []
+        seq_dims = [tpmod.irreps_dim(tpmod.parse_irreps(s)) for s in self.irrep_seq]
+        for l in range(self.num_conv_layers):
+            last = l == self.num_conv_layers - 1
+            f_old, f_new = seq_dims[min(l, 3)], seq_dims[min(l + 1, 3)]
+            Cv, Pk = self.conv_layers, P['convs']
+            pl.sum_arena.zero_()
+            o = 0
+
+            def take(n):
+                nonlocal o
+                v = pl.sum_arena[o:o + n * f_new].view(n, f_new)
+                o += n * f_new
+                return v
+            s_ll, s_lr, s_la = take(pl.NL), take(pl.NL), take(pl.NL)
+            self._conv(L, st, Cv[9 * l], Pk[9 * l], es['ll'], False, xl, xl, 0, xl, 1, s_ll)
+            self._conv(L, st, Cv[9 * l + 1], Pk[9 * l + 1], es['lr'], False, xr, xl, 0, xr, 1, s_lr)
+            self._conv(L, st, Cv[9 * l + 2], Pk[9 * l + 2], es['la'], False, xa, xl, 0, xa, 1, s_la)
+            do_atom = self.flexible_sidechains or not last
+            if do_atom:
+                s_aa, s_al, s_ar = take(pl.NA), take(pl.NA), take(pl.NA)
+                self._conv(L, st, Cv[9 * l + 3], Pk[9 * l + 3], es['aa'], False, xa, xa, 0, xa, 1, s_aa)
+                self._conv(L, st, Cv[9 * l + 4], Pk[9 * l + 4], es['la'], True, xl, xa, 1, xl, 0, s_al)
+                self._conv(L, st, Cv[9 * l + 5], Pk[9 * l + 5], es['ar'], False, xr, xa, 0, xr, 1, s_ar)
+                if not last:
+                    s_rr, s_rl, s_ra = take(pl.NR), take(pl.NR), take(pl.NR)
+                    self._conv(L, st, Cv[9 * l + 6], Pk[9 * l + 6], es['rr'], False, xr, xr, 0, xr, 1, s_rr)
+                    self._conv(L, st, Cv[9 * l + 7], Pk[9 * l + 7], es['lr'], True, xl, xr, 1, xl, 0, s_rl)
+                    self._conv(L, st, Cv[9 * l + 8], Pk[9 * l + 8], es['ar'], True, xa, xr, 1, xa, 0, s_ra)
+
+            def update(key, x_old, n, items):
+                ups = (_lib.Update * len(items))(*[
+                    _lib.Update(sum=ptr(s), deg=ptr(es[nm].deg[r]), scale=ptr(Pk[ci].bn_scale), shift=ptr(Pk[ci].bn_shift),
+                                n_edges_dev=ptr(es[nm].n_dev)) for (s, nm, r, ci) in items])
+                x_new = pl.x[key][1 - cur[key]]
+                chk(L.ddp_node_update(ptr(x_old), f_old, F, ups, len(items), n, f_new, ptr(x_new), F, st), 'ddp_node_update')
+                cur[key] = 1 - cur[key]
+                return x_new
+            xl_new = update('l', xl, pl.NL, [(s_ll, 'll', 0, 9 * l), (s_la, 'la', 0, 9 * l + 2), (s_lr, 'lr', 0, 9 * l + 1)])
+            if do_atom:
+                xa_new = update('a', xa, pl.NA, [(s_aa, 'aa', 0, 9 * l + 3), (s_al, 'la', 1, 9 * l + 4), (s_ar, 'ar', 0, 9 * l + 5)])
+                if not last:
+                    xr = update('r', xr, pl.NR, [(s_rr, 'rr', 0, 9 * l + 6), (s_ra, 'ar', 1, 9 * l + 8), (s_rl, 'lr', 1, 9 * l + 7)])
+                xa = xa_new
+            xl = xl_new
+            if return_layers:
+                layers_out.append((xl[:, :f_new].clone(), xa[:, :f_new if do_atom else f_old].clone(), xr.clone()))
+        pl.last_layers = layers_out
+        f_last = seq_dims[min(self.num_conv_layers, 3)]
+
+        if self.confidence_mode:                                       # :329-353
+            w = 2 * ns if self.num_conv_layers >= 3 else ns
+            ld = pl.conf_in.shape[1]
+            chk(L.ddp_segment_mean(ptr(xl), None, ptr(pl.lig_ptr), B, ns, F, ptr(pl.conf_in), ld, st), 'segment_mean')
+            if self.num_conv_layers >= 3:
+                chk(L.ddp_segment_mean(xl.data_ptr() + 4 * (f_last - ns), None, ptr(pl.lig_ptr), B, ns, F,
+                                       pl.conf_in.data_ptr() + 4 * ns, ld, st), 'segment_mean')
+            if self.flexible_sidechains:
+                if pl.S > 0:
+                    chk(L.ddp_segment_mean(ptr(xa), ptr(pl.flex_atoms), ptr(pl.flex_ptr), B, ns, F, pl.conf_in.data_ptr() + 4 * w, ld, st), 'segment_mean')
+                    if self.num_conv_layers >= 3:
+                        chk(L.ddp_segment_mean(xa.data_ptr() + 4 * (f_last - ns), ptr(pl.flex_atoms), ptr(pl.flex_ptr), B, ns, F,
+                                               pl.conf_in.data_ptr() + 4 * (w + ns), ld, st), 'segment_mean')
+                else:
+                    pl.conf_in[:, w:].zero_()
+            lay = P['conf_mlp']
+            arr = (_lib.MlpLayer * 3)(*[_lib.MlpLayer(wt=ptr(wt), b=ptr(b), n_in=wt.shape[0], n_out=wt.shape[1], act=a)
+                                       for (wt, b), a in zip(lay, (1, 1, 0))])
+            chk(L.ddp_row_mlp(ptr(pl.conf_in), B, ld, arr, 3, None, ptr(pl.conf_out), pl.conf_out.shape[1], st), 'row_mlp')
+            return pl.conf_out.squeeze(dim=-1)
+
+        # ---- translation / rotation head (:357-384) ---------------------------------------------------
+        ec = es['center']
+        chk(L.ddp_segment_mean(ptr(pl.lig_pos), None, ptr(pl.lig_ptr), B, 3, 3, ptr(pl.center), 3, st), 'segment_mean')
+        chk(L.ddp_edge_embed(ptr(pl.center), ptr(pl.lig_pos), ptr(ec.edge), ec.cap, ptr(ec.n_dev), None, None, 0, ptr(U['center']),
+                             C.byref(em['center']['desc']), ptr(ec.sh), ptr(ec.emb), st), 'ddp_edge_embed(center)')
+        pl.g_sum.zero_()
+        self._conv(L, st, self.final_conv, P['final_conv'], ec, False, xl, xl, 1 if self.fixed_center_conv else 0, None, 0, pl.g_sum)
+        fc = P['final_conv']
+        up = _lib.Update(sum=ptr(pl.g_sum), deg=ptr(pl.center_deg), scale=ptr(fc.bn_scale), shift=ptr(fc.bn_shift), n_edges_dev=ptr(ec.n_dev))
+        chk(L.ddp_node_update(None, 0, 0, C.byref(up), 1, B, 12, ptr(pl.g), 12, st), 'ddp_node_update')
+        (tw1, tb1, tw2, tb2), (rw1, rb1, rw2, rb2) = P['tr'], P['rot']
+        if self.scale_by_sigma:
+            trs, son = tr_sigma, so3n
+        else:
+            trs = son = torch.ones(B, device=pl.device)
+        chk(L.ddp_tr_rot_head(ptr(pl.g), ptr(pl.sig), self.sigma_embed_dim, B, ptr(tw1), ptr(tb1), ptr(tw2), ptr(tb2), ptr(rw1),
+                              ptr(rb1), ptr(rw2), ptr(rb2), ns, ptr(trs), ptr(son), ptr(pl.tr_out), ptr(pl.rot_out), st), 'tr_rot_head')
+        # ---- torsion heads (:386-434) ----------------------------------------------------------------------
+        outs = []
+        for key, n, pos, xn, nptr, conv, mlp_key, emk, out, soff in (
+                ('tor', pl.T, pl.lig_pos, xl, pl.lig_ptr, getattr(self, 'tor_bond_conv', None), 'tor_mlp', 'tor', pl.tor_out, 4 * B),
+                ('sc', pl.S, pl.atom_pos, xa, pl.atom_ptr, getattr(self, 'sc_tor_bond_conv', None), 'sc_mlp', 'sc', pl.sc_out, 4 * B + pl.T)):
+            if n == 0:
+                outs.append(torch.empty(0, device=pl.device))
+                continue
+            h = getattr(pl, key)
+            e = h.es
+            chk(L.ddp_bond_geometry(ptr(pos), ptr(h.bonds), n, ptr(xn), F, ns, ptr(h.mid), ptr(h.y2), ptr(h.attr), st), 'bond_geometry')
+            chk(L.ddp_radius(ptr(pos), ptr(h.mid), ptr(nptr), ptr(h.ptr), B, n, None, float(self.lig_max_radius), 32, 0, 0,
+                             ptr(e.slab), e.slab_w, ptr(e.counts), ptr(e.edge), e.cap, ptr(e.n_dev), st), f'ddp_radius({key})')
+            chk(L.ddp_edge_embed(ptr(h.mid), ptr(pos), ptr(e.edge), e.cap, ptr(e.n_dev), ptr(h.batch), None, 0, None,
+                                 C.byref(em[emk]['desc']), ptr(e.sh), ptr(e.emb), st), f'ddp_edge_embed({key})')
+            chk(L.ddp_tor_edge_sh(ptr(e.sh), self.sh_dim, ptr(h.y2), ptr(P['c121']), ptr(e.edge), ptr(e.n_dev), e.cap, ptr(h.sh_tor), st), 'tor_edge_sh')
+            e.sh_conv = h.sh_tor
+            h.sum.zero_()
+            h.deg.zero_()
+            chk(L.ddp_degree(e.row(0), ptr(e.n_dev), e.cap, ptr(h.deg), st), 'ddp_degree')
+            pk = P[key + '_conv']
+            self._conv(L, st, conv, pk, e, False, xn, xn, 1, h.attr, 0, h.sum)
+            up = _lib.Update(sum=ptr(h.sum), deg=ptr(h.deg), scale=ptr(pk.bn_scale), shift=ptr(pk.bn_shift), n_edges_dev=ptr(e.n_dev))
+            chk(L.ddp_node_update(None, 0, 0, C.byref(up), 1, n, 2 * ns, ptr(h.feat), 2 * ns, st), 'ddp_node_update')
+            (w1, _), (w2, _) = P[mlp_key]
+            arr = (_lib.MlpLayer * 2)(_lib.MlpLayer(wt=ptr(w1), b=None, n_in=2 * ns, n_out=ns, act=2),
+                                      _lib.MlpLayer(wt=ptr(w2), b=None, n_in=ns, n_out=1, act=0))
+            rs = pl.scal[soff:soff + n] if self.scale_by_sigma else None
+            chk(L.ddp_row_mlp(ptr(h.feat), n, 2 * ns, arr, 2, ptr(rs), ptr(out), 1, st), 'row_mlp')
+            outs.append(out[:n])
+        return pl.tr_out, pl.rot_out, outs[0], outs[1]
+
+    def forward(self, data):
+        """Drop-in ``model(data)`` on a collated batch (uploads the batch, runs, returns device tensors)."""
+        pl = self.make_plan(data)
+        out = self.run_plan(pl, data.complex_t)
+        # side effects the reference's forward leaves on ``data`` (all_atom_score_model.py:373,530)
+        try:
+            data['atom', 'atom'].edge_index = pl.es['aa'].edge_index()
+            data.graph_sigma_emb = pl.sig
+        except Exception:
+            pass
+        self._last_plan = pl
+        return out

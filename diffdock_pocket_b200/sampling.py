@@ -1,0 +1,208 @@
+"""Reverse-diffusion sampler: host mirror of ``utils/sampling.py``.
+
+``sampling()`` keeps the reference signature and return values (utils/sampling.py:70-286) and draws
+its noise from the same generators in the same order (``torch.normal`` on the CPU default generator:
+tr_z, rot_z, tor_z, sidechain_tor_z per step), but the loop body is restructured for the GPU:
+
+* every mini-batch of ``batch_size`` samples is collated and uploaded ONCE (``model.make_plan``) and
+  stays resident; the reference re-collates and re-uploads every step (utils/sampling.py:100,114);
+* per step and batch: one H2D copy of the step's noise slice, the score-model forward
+  (``model.run_plan``, no host sync) and one fused pose-update launch (``ddp_pose_update``) that turns
+  scores + noise into the new ligand / side-chain coordinates on the device; the reference makes
+  N x (n_sc + 1) CPU round trips per step (utils/sampling.py:245-251);
+* poses return to the host once, after the last step (and the confidence pass).
+
+SVGD (svgd_weight > 0) and ``pivot`` are outside the accelerated path and raise NotImplementedError.
+"""
+import copy
+
+import numpy as np
+import torch
+from scipy.spatial.transform import Rotation as R
+
+from .diffusion_utils import PoseState, modify_conformer, modify_sidechains
+from .hetero import Batch
+
+
+def randomize_position(data_list, no_torsion, no_random, tr_sigma_max, pocket_knowledge=False, pocket_cutoff=7,
+                       flexible_sidechains=False):
+    """utils/sampling.py:16-60 (in-place).  Host-side initial-state generator (once per complex)."""
+    from .torsion import modify_conformer_torsion_angles
+    center_pocket = 0
+    if pocket_knowledge:
+        g = data_list[0]
+        d = torch.cdist(g['receptor'].pos, torch.from_numpy(g['ligand'].orig_pos[0]).float() - g.original_center)
+        label = torch.any(d < pocket_cutoff, dim=1)
+        center_pocket = g['receptor'].pos[label].mean(dim=0) if torch.any(label) else \
+            g['receptor'].pos[torch.argmin(torch.min(d, dim=1)[0])]
+    if not no_torsion:
+        for g in data_list:
+            upd = np.random.uniform(low=-np.pi, high=np.pi, size=int(g['ligand'].edge_mask.sum()))
+            mr = g['ligand'].mask_rotate
+            mr = mr if isinstance(mr, np.ndarray) else mr[0]
+            g['ligand'].pos = modify_conformer_torsion_angles(
+                g['ligand'].pos, g['ligand', 'ligand'].edge_index.T[g['ligand'].edge_mask], mr, upd)
+    if flexible_sidechains:
+        from .torsion import modify_sidechains_host
+        for g in data_list:
+            upd = np.random.uniform(low=-np.pi, high=np.pi, size=len(g['flexResidues'].edge_idx))
+            modify_sidechains_host(g, upd)
+    for g in data_list:
+        center = torch.mean(g['ligand'].pos, dim=0, keepdim=True)
+        rot = torch.from_numpy(R.random().as_matrix()).float()
+        g['ligand'].pos = (g['ligand'].pos - center) @ rot.T + center_pocket
+        if not no_random:
+            g['ligand'].pos += torch.normal(mean=0, std=tr_sigma_max, size=(1, 3))
+
+
+def is_iterable(arr):
+    try:
+        iter(arr)
+        return True
+    except TypeError:
+        return False
+
+
+def step_coefficients(t_idx, inference_steps, schedules, t_to_sigma, model_args, ode, temp_sampling, temp_psi,
+                      temp_sigma_data, flexible_sidechains):
+    """Host scalars of one step (utils/sampling.py:94-98, 110, 129-195): perturb = a * score + b * z."""
+    ma = model_args
+    tr_s, rot_s, tor_s, sc_s = schedules
+    last = t_idx == inference_steps - 1
+    t = [s[t_idx] for s in schedules]
+    dt = [s[t_idx] - s[t_idx + 1] if not last else s[t_idx] for s in schedules]
+    sig = t_to_sigma(*t)
+    rng = [(ma.tr_sigma_max, ma.tr_sigma_min), (ma.rot_sigma_max, ma.rot_sigma_min), (ma.tor_sigma_max, ma.tor_sigma_min),
+           (getattr(ma, 'sidechain_tor_sigma_max', 1.0), getattr(ma, 'sidechain_tor_sigma_min', 1.0))]
+    g = [sig[0] * np.sqrt(2 * np.log(rng[0][0] / rng[0][1])), 2 * sig[1] * np.sqrt(np.log(rng[1][0] / rng[1][1])),
+         sig[2] * np.sqrt(2 * np.log(rng[2][0] / rng[2][1])), sig[3] * np.sqrt(2 * np.log(rng[3][0] / rng[3][1]))]
+    ts = list(temp_sampling) if is_iterable(temp_sampling) else [temp_sampling] * 4
+    tp = list(temp_psi) if is_iterable(temp_psi) else [temp_psi] * 4
+    assert len(ts) == 4 and len(tp) == 4
+    coef = []
+    for k in range(4):
+        if ode:
+            a, b = 0.5 * g[k] ** 2 * dt[k], 0.0
+        else:
+            a, b = g[k] ** 2 * dt[k], g[k] * np.sqrt(dt[k])
+        active = (k < 2) or (k == 2 and not ma.no_torsion) or (k == 3 and flexible_sidechains)
+        if ts[k] != 1.0 and active:
+            sd = np.exp(temp_sigma_data * np.log(rng[k][0]) + (1 - temp_sigma_data) * np.log(rng[k][1]))
+            lam = (sd + sig[k]) / (sd + sig[k] / ts[k])
+            a, b = g[k] ** 2 * dt[k] * (lam + ts[k] * tp[k] / 2), g[k] * np.sqrt(dt[k] * (1 + tp[k]))
+        coef += [float(a), float(b)]
+    return t, coef
+
+
+def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_schedule, sidechain_tor_schedule, device,
+             t_to_sigma, model_args, no_random=False, ode=False, visualization_list=None, sidechain_visualization_list=None,
+             confidence_model=None, filtering_data_list=None, filtering_model_args=None, asyncronous_noise_schedule=False,
+             t_schedule=None, batch_size=32, no_final_step_noise=False, pivot=None, return_full_trajectory=False,
+             svgd_weight=0.0, svgd_repulsive_weight=1.0, svgd_only=False, svgd_rot_rel_weight=1.0, svgd_tor_rel_weight=1.0,
+             svgd_sidechain_tor_rel_weight=1.0, temp_sampling=1.0, temp_psi=0.0, temp_sigma_data=0.5,
+             flexible_sidechains=None, max_steps=None, trace=None):
+    if svgd_weight > 0 or pivot is not None or asyncronous_noise_schedule:
+        raise NotImplementedError('SVGD / pivot / asynchronous schedules are outside the accelerated path')
+    flexible_sidechains = model_args.flexible_sidechains if flexible_sidechains is None else flexible_sidechains
+    no_sidechains_in_batch = False
+    if flexible_sidechains:
+        no_sidechains_in_batch = sum(len(c['flexResidues'].subcomponents) for c in data_list) == 0
+        if no_sidechains_in_batch:
+            data_list = copy.deepcopy(data_list)
+            for c in data_list:
+                del c['flexResidues']
+    N = len(data_list)
+    ma = model_args
+    device = torch.device(device) if not isinstance(device, torch.device) else device
+    trajectory, sidechain_trajectory = [], []
+    schedules = (tr_schedule, rot_schedule, tor_schedule, sidechain_tor_schedule)
+
+    # one resident plan + pose state per mini-batch
+    chunks = [list(range(i, min(i + batch_size, N))) for i in range(0, N, batch_size)]
+    plans, poses = [], []
+    with torch.no_grad():
+        for idx in chunks:
+            sub = [data_list[i] for i in idx]
+            pl = model.make_plan(Batch.from_data_list(sub))
+            plans.append(pl)
+            poses.append(PoseState(sub, pl.device, lig_pos=pl.lig_pos, atom_pos=pl.atom_pos,
+                                   flexible_sidechains=flexible_sidechains, no_torsion=ma.no_torsion))
+    T_tot = sum(p.T for p in poses)
+    S_tot = sum(p.S for p in poses)
+    use_sc = flexible_sidechains and S_tot > 0
+    n_steps = inference_steps if max_steps is None else min(max_steps, inference_steps)
+    M = 6 * N + T_tot + S_tot
+    # Noise for all steps is drawn up front, in the reference's order (per step: tr_z, rot_z, tor_z,
+    # sidechain_tor_z; utils/sampling.py:136-163) -- nothing else consumes the CPU generator in between, so
+    # the stream is identical -- and uploaded with a single H2D copy.
+    noise_host = torch.zeros(max(n_steps, 1), M)
+    if not ode:
+        for t_idx in range(n_steps):
+            zero_noise = no_random or (no_final_step_noise and t_idx == inference_steps - 1)
+            draw = (lambda shape: torch.zeros(shape)) if zero_noise else (lambda shape: torch.normal(mean=0, std=1, size=shape))
+            noise_host[t_idx, :3 * N] = draw((N, 3)).reshape(-1)
+            noise_host[t_idx, 3 * N:6 * N] = draw((N, 3)).reshape(-1)
+            if not ma.no_torsion:
+                noise_host[t_idx, 6 * N:6 * N + T_tot] = draw((T_tot,))
+            if flexible_sidechains:
+                noise_host[t_idx, 6 * N + T_tot:] = draw((S_tot,))
+    noise_all = noise_host.pin_memory().to(plans[0].device, non_blocking=True)
+
+    with torch.no_grad():
+        for t_idx in range(n_steps):
+            t, coef = step_coefficients(t_idx, inference_steps, schedules, t_to_sigma, ma, ode, temp_sampling, temp_psi,
+                                        temp_sigma_data, flexible_sidechains)
+            if return_full_trajectory:
+                for idx, p in zip(chunks, poses):
+                    p.write_back([data_list[i] for i in idx])
+                trajectory.append(np.asarray([g['ligand'].pos.cpu().numpy() for g in data_list]))
+                sidechain_trajectory.append(np.asarray([]) if no_sidechains_in_batch or not flexible_sidechains else np.asarray(
+                    [g['atom'].pos.cpu().numpy()[g['flexResidues'].subcomponents.unique().cpu().numpy()] for g in data_list]))
+            noise_dev = noise_all[t_idx]
+            s0 = t0 = c0 = 0
+            step_scores = []
+            for idx, pl, ps in zip(chunks, plans, poses):
+                b = len(idx)
+                ct = {'tr': torch.full((b,), float(t[0])), 'rot': torch.full((b,), float(t[1])),
+                      'tor': torch.full((b,), float(t[2])), 'sc_tor': torch.full((b,), float(t[3]))}
+                tr_score, rot_score, tor_score, sc_score = model.run_plan(pl, ct)
+                if trace is not None:
+                    step_scores.append((tr_score.clone(), rot_score.clone(), tor_score.clone(), sc_score.clone()))
+                z = None if ode else noise_dev
+                ps.update(coef, tr_score, rot_score, tor_score if ps.has_tor else None, sc_score if (ps.has_sc and use_sc) else None,
+                          tr_z=z[3 * s0:3 * (s0 + b)] if z is not None else None,
+                          rot_z=z[3 * N + 3 * s0:3 * N + 3 * (s0 + b)] if z is not None else None,
+                          tor_z=z[6 * N + t0:6 * N + t0 + ps.T] if z is not None and ps.has_tor else None,
+                          sc_z=z[6 * N + T_tot + c0:6 * N + T_tot + c0 + ps.S] if z is not None and ps.has_sc and use_sc else None)
+                s0, t0, c0 = s0 + b, t0 + ps.T, c0 + ps.S
+            if trace is not None:
+                trace.append(tuple(torch.cat([s[k] for s in step_scores]).cpu() for k in range(4)))
+            if visualization_list is not None or sidechain_visualization_list is not None:
+                for idx, ps in zip(chunks, poses):
+                    ps.write_back([data_list[i] for i in idx])
+                if visualization_list is not None:
+                    for i, v in enumerate(visualization_list):
+                        v.add((data_list[i]['ligand'].pos + data_list[i].original_center).detach().cpu(), part=1, order=t_idx + 2)
+                if sidechain_visualization_list is not None:
+                    for i, v in enumerate(sidechain_visualization_list):
+                        v.append(data_list[i]['atom'].pos + data_list[i]['original_center'])
+
+        for idx, ps in zip(chunks, poses):
+            ps.write_back([data_list[i] for i in idx])
+        confidence = None
+        if confidence_model is not None:                              # utils/sampling.py:263-281
+            conf = []
+            for idx, ps in zip(chunks, poses):
+                if filtering_data_list is not None:
+                    sub = [filtering_data_list[i] for i in idx]
+                    for g, i in zip(sub, idx):
+                        g['ligand'].pos = data_list[i]['ligand'].pos
+                else:
+                    sub = [data_list[i] for i in idx]
+                cpl = confidence_model.make_plan(Batch.from_data_list(sub))
+                zt = torch.zeros(len(idx))
+                conf.append(confidence_model.run_plan(cpl, {'tr': zt, 'rot': zt, 'tor': zt, 'sc_tor': zt}).clone())
+            confidence = torch.cat(conf, dim=0)
+    if return_full_trajectory:
+        return data_list, confidence, trajectory, sidechain_trajectory
+    return data_list, confidence

@@ -1,0 +1,256 @@
+"""Host mirrors of the shared classes of the reference's ``models/score_model.py``.
+
+Same class names, constructor arguments and ``state_dict`` keys as the reference
+(``TensorProductConvLayer`` models/score_model.py:84-125, ``AtomEncoder`` :54-82, ``OldAtomEncoder``
+:17-52, ``GaussianSmearing`` :661-671), but every ``forward`` runs on the ddp_b200 CUDA kernels through
+the C ABI (``include/ddp_b200.h``); there is no PyTorch/CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib, tp as tpmod
+from ._lib import ptr
+
+FEATURE_DIMS = {  # datasets/process_mols.py:69-97
+    'lig': ([119, 4, 12, 12, 8, 10, 6, 6, 2, 8, 2, 2, 2, 2, 2, 2], 0),
+    'rec_atom': ([38, 119, 23, 38], 0),
+    'rec_residue': ([38], 0),
+}
+
+
+class GaussianSmearing(nn.Module):
+    def __init__(self, start=0.0, stop=5.0, num_gaussians=50):
+        super().__init__()
+        offset = torch.linspace(start, stop, num_gaussians)
+        self.coeff = -0.5 / (offset[1] - offset[0]).item() ** 2
+        self.register_buffer('offset', offset)
+
+
+class AtomEncoder(nn.Module):
+    """Parameter holder; the encoder is evaluated as static part (once per complex) + per-graph sigma
+    projection (``ddp_graph_sigma_proj`` / ``ddp_node_init``)."""
+
+    def __init__(self, emb_dim, feature_dims, sigma_embed_dim, lm_embedding_type=None):
+        super().__init__()
+        self.atom_embedding_list = nn.ModuleList()
+        self.num_categorical_features = len(feature_dims[0])
+        self.lm_embedding_dim = 1280 if lm_embedding_type == 'esm' else 0
+        if lm_embedding_type not in (None, 'esm'):
+            raise ValueError('LM Embedding type was not correctly determined. LM embedding type: ', lm_embedding_type)
+        self.sigma_embed_dim, self.emb_dim = sigma_embed_dim, emb_dim
+        self.additional_features_dim = feature_dims[1] + sigma_embed_dim + self.lm_embedding_dim
+        for dim in feature_dims[0]:
+            emb = nn.Embedding(dim, emb_dim)
+            nn.init.xavier_uniform_(emb.weight.data)
+            self.atom_embedding_list.append(emb)
+        if self.additional_features_dim > 0:
+            self.additional_features_embedder = nn.Linear(self.additional_features_dim + emb_dim, emb_dim)
+
+    def _emb_sum(self, cat):
+        h = 0
+        for i in range(self.num_categorical_features):
+            h = h + self.atom_embedding_list[i](cat[:, i].long())
+        return h
+
+    def static_part(self, cat, lm=None):
+        """Time-independent part of the Linear: W[:, :ns] sum_k Emb_k + W[:, ns:ns+1280] lm."""
+        W = self.additional_features_embedder.weight
+        ns = self.emb_dim
+        out = self._emb_sum(cat) @ W[:, :ns].T
+        if self.lm_embedding_dim:
+            out = out + lm @ W[:, ns:ns + self.lm_embedding_dim].T
+        return out.contiguous()
+
+    def sigma_proj(self):
+        """(W_sigma^T [sig, ns], bias) of the per-graph part."""
+        W = self.additional_features_embedder.weight
+        return W[:, -self.sigma_embed_dim:].T.contiguous(), self.additional_features_embedder.bias
+
+
+class OldAtomEncoder(nn.Module):
+    def __init__(self, emb_dim, feature_dims, sigma_embed_dim, lm_embedding_type=None):
+        super().__init__()
+        self.atom_embedding_list = nn.ModuleList()
+        self.num_categorical_features = len(feature_dims[0])
+        self.num_scalar_features = feature_dims[1] + sigma_embed_dim
+        self.lm_embedding_type = lm_embedding_type
+        self.sigma_embed_dim, self.emb_dim = sigma_embed_dim, emb_dim
+        for dim in feature_dims[0]:
+            emb = nn.Embedding(dim, emb_dim)
+            nn.init.xavier_uniform_(emb.weight.data)
+            self.atom_embedding_list.append(emb)
+        if self.num_scalar_features > 0:
+            self.linear = nn.Linear(self.num_scalar_features, emb_dim)
+        if lm_embedding_type is not None:
+            if lm_embedding_type != 'esm':
+                raise ValueError('LM Embedding type was not correctly determined. LM embedding type: ', lm_embedding_type)
+            self.lm_embedding_dim = 1280
+            self.lm_embedding_layer = nn.Linear(self.lm_embedding_dim + emb_dim, emb_dim)
+
+    def _emb_sum(self, cat):
+        h = 0
+        for i in range(self.num_categorical_features):
+            h = h + self.atom_embedding_list[i](cat[:, i].long())
+        return h
+
+    def static_part(self, cat, lm=None):
+        ns, sd = self.emb_dim, self.sigma_embed_dim
+        if self.lm_embedding_type is None:
+            return self._emb_sum(cat).contiguous()
+        # reference quirk (models/score_model.py:48-51): the "scalar" slice x[:, nc:nc+nsf] of
+        # [aa | ESM | sigma] is ESM[:, :sd]; the LM layer sees [ESM[:, sd:] | sigma].
+        Wl = self.lm_embedding_layer.weight
+        h = self._emb_sum(cat) + lm[:, :sd] @ self.linear.weight.T
+        return (h @ Wl[:, :ns].T + lm[:, sd:] @ Wl[:, ns:ns + self.lm_embedding_dim - sd].T).contiguous()
+
+    def sigma_proj(self):
+        ns, sd = self.emb_dim, self.sigma_embed_dim
+        if self.lm_embedding_type is None:
+            return self.linear.weight.T.contiguous(), self.linear.bias
+        Wl = self.lm_embedding_layer.weight
+        return Wl[:, -sd:].T.contiguous(), self.lm_embedding_layer.bias + Wl[:, :ns] @ self.linear.bias
+
+
+class BatchNorm(nn.Module):
+    """Parameter holder with e3nn.nn.BatchNorm's state_dict layout (eval mode is folded into the
+    node-update kernel as per-channel scale / shift)."""
+
+    def __init__(self, irreps, eps=1e-5):
+        super().__init__()
+        self.irreps, self.eps = tpmod.parse_irreps(irreps), eps
+        n_scalar = sum(m for m, l, p in self.irreps if l == 0 and p == 1)
+        n_feat = sum(m for m, _, _ in self.irreps)
+        self.register_buffer('running_mean', torch.zeros(n_scalar))
+        self.register_buffer('running_var', torch.ones(n_feat))
+        self.weight = nn.Parameter(torch.ones(n_feat))
+        self.bias = nn.Parameter(torch.zeros(n_scalar))
+
+    def folded(self):
+        sc, sh = tpmod.batch_norm_fold(self.irreps, self.running_mean.detach().cpu().numpy().astype(np.float64),
+                                       self.running_var.detach().cpu().numpy().astype(np.float64),
+                                       self.weight.detach().cpu().numpy().astype(np.float64),
+                                       self.bias.detach().cpu().numpy().astype(np.float64), self.eps)
+        return torch.from_numpy(sc), torch.from_numpy(sh)
+
+
+class _TP(nn.Module):
+    """Stands where the reference keeps ``FasterTensorProduct`` / ``o3.FullyConnectedTensorProduct``."""
+
+    def __init__(self, spec):
+        super().__init__()
+        self.spec = spec
+        self.weight_numel = spec.weight_numel
+
+
+class PackedConv:
+    """Device-side, kernel-friendly image of one TensorProductConvLayer (built once per weight load)."""
+
+    def __init__(self, layer, device, n_emb, ns):
+        spec = layer.tp.spec
+        f32 = dict(dtype=torch.float32, device=device)
+        fc0, fc3 = layer.fc[0], layer.fc[3]
+        self.w1t = fc0.weight.detach().T.contiguous().to(**f32)
+        self.b1 = fc0.bias.detach().contiguous().to(**f32)
+        self.w2t = fc3.weight.detach().T.contiguous().to(**f32)
+        self.b2 = fc3.bias.detach().contiguous().to(**f32)
+        self.k1, self.hid = fc0.in_features, fc0.out_features
+        garr = (_lib.TpGroup * len(spec.groups))(*[_lib.TpGroup(**g) for g in spec.groups])
+        self.groups_host = garr
+        self.groups = torch.frombuffer(bytearray(bytes(garr)), dtype=torch.uint8).to(device)
+        self.ctab = torch.tensor(spec.ctab, **f32)
+        self.col_group = torch.from_numpy(spec.col_group()).to(device)
+        self.spec = spec
+        if layer.batch_norm is not None:
+            sc, sh = layer.batch_norm.folded()
+            self.bn_scale, self.bn_shift = sc.to(**f32), sh.to(**f32)
+        else:
+            self.bn_scale = self.bn_shift = None
+        self.cdesc = _lib.TpConv(w1t=ptr(self.w1t), b1=ptr(self.b1), w2t=ptr(self.w2t), b2=ptr(self.b2), k1=self.k1,
+                                 hid=self.hid, w_numel=spec.weight_numel, n_emb=n_emb, ns=ns, groups=ptr(self.groups),
+                                 ctab=ptr(self.ctab), ctab_len=len(spec.ctab), col_group=ptr(self.col_group),
+                                 n_groups=len(spec.groups), f_in=spec.f_in, f_out=spec.f_out, sh_dim=spec.sh_dim)
+        self.umma = {}   # mode -> packed device image (tensor-core kernel)
+
+    def umma_image(self, layer, mode, device):
+        if mode not in self.umma:
+            L = _lib.lib()
+            size = L.ddp_tpconv_pack_size(C.byref(self.cdesc), mode)
+            if size <= 0:
+                raise RuntimeError(f'ddp_tpconv_pack_size failed ({size}): conv is not tensor-core eligible')
+            host = torch.empty(size, dtype=torch.uint8)
+            fc0, fc3 = layer.fc[0], layer.fc[3]
+            w1 = fc0.weight.detach().cpu().float().contiguous()
+            b1 = fc0.bias.detach().cpu().float().contiguous()
+            w2 = fc3.weight.detach().cpu().float().contiguous()
+            b2 = fc3.bias.detach().cpu().float().contiguous()
+            _lib.check(L.ddp_tpconv_pack(C.byref(self.cdesc), self.groups_host, ptr(w1), ptr(b1), ptr(w2), ptr(b2), mode,
+                                         ptr(host)), 'ddp_tpconv_pack')
+            self.umma[mode] = host.to(device)
+        return self.umma[mode]
+
+
+class TensorProductConvLayer(nn.Module):
+    """models/score_model.py:84-125 (operator-level drop-in)."""
+
+    def __init__(self, in_irreps, sh_irreps, out_irreps, n_edge_features, residual=True, batch_norm=True, dropout=0.0,
+                 hidden_features=None, faster=False):
+        super().__init__()
+        self.in_irreps, self.out_irreps, self.sh_irreps = in_irreps, out_irreps, sh_irreps
+        self.residual = residual
+        if hidden_features is None:
+            hidden_features = n_edge_features
+        sh_ir = tpmod.parse_irreps(sh_irreps) if isinstance(sh_irreps, str) else list(sh_irreps)
+        if faster:
+            assert [tuple(t) for t in sh_ir] == [(1, 0, 1), (1, 1, -1)], "sh_irreps don't look like 1st order spherical harmonics"
+            spec = tpmod.faster_tp_spec(in_irreps, out_irreps)
+        else:
+            spec = tpmod.fctp_spec(in_irreps, sh_ir, out_irreps)
+        self.tp = _TP(spec)
+        self.fc = nn.Sequential(nn.Linear(n_edge_features, hidden_features), nn.ReLU(), nn.Dropout(dropout),
+                                nn.Linear(hidden_features, spec.weight_numel))
+        self.batch_norm = BatchNorm(out_irreps) if batch_norm else None
+        self._packed = None
+
+    def _load_from_state_dict(self, *a, **k):
+        self._packed = None
+        return super()._load_from_state_dict(*a, **k)
+
+    def packed(self, device, n_emb, ns):
+        if self._packed is None or self._packed.w1t.device != torch.device(device) or self._packed.cdesc.n_emb != n_emb:
+            self._packed = PackedConv(self, device, n_emb, ns)
+        return self._packed
+
+    def forward(self, node_attr, edge_index, edge_attr, edge_sh, out_nodes=None, reduce='mean', edge_weight=1.0):
+        """Stand-alone operator call (fp32 kernel): edge_attr is the already concatenated [E, n_edge_features]."""
+        if edge_index.numel() == 0:
+            return torch.tensor(0, dtype=node_attr.dtype, device=node_attr.device)
+        assert reduce == 'mean' and not self.residual
+        dev = node_attr.device
+        if dev.type != 'cuda':
+            raise RuntimeError('TensorProductConvLayer runs on CUDA only (no CPU fallback)')
+        L = _lib.lib()
+        pk = self.packed(dev, self.fc[0].in_features, 0)
+        E = edge_index.shape[1]
+        out_nodes = int(out_nodes or node_attr.shape[0])
+        ei = edge_index.to(torch.int32).contiguous()
+        x = node_attr.float().contiguous()
+        ea, sh = edge_attr.float().contiguous(), edge_sh.float().contiguous()
+        ew = None
+        if torch.is_tensor(edge_weight):
+            ew = edge_weight.float().reshape(-1).contiguous()
+        n_dev = torch.tensor([E], dtype=torch.int32, device=dev)
+        f_out = pk.spec.f_out
+        s = torch.zeros(out_nodes, f_out, device=dev)
+        ed = _lib.TpEdges(emb=ptr(ea), p1=None, i1=None, ld1=0, p2=None, i2=None, ld2=0, x=ptr(x), gather=ei[1].data_ptr(),
+                          ldx=x.shape[1], sh=ptr(sh), agg=ei[0].data_ptr(), ew=ptr(ew), n_edges_dev=ptr(n_dev), edge_cap=E)
+        _lib.check(L.ddp_tpconv_fp32(C.byref(pk.cdesc), C.byref(ed), ptr(s), _lib.stream_ptr()), 'ddp_tpconv_fp32')
+        deg = torch.zeros(out_nodes, dtype=torch.int32, device=dev)
+        _lib.check(L.ddp_degree(ei[0].data_ptr(), ptr(n_dev), E, ptr(deg), _lib.stream_ptr()), 'ddp_degree')
+        up = _lib.Update(sum=ptr(s), deg=ptr(deg), scale=ptr(pk.bn_scale), shift=ptr(pk.bn_shift), n_edges_dev=ptr(n_dev))
+        out = torch.empty(out_nodes, f_out, device=dev)
+        _lib.check(L.ddp_node_update(None, 0, 0, C.byref(up), 1, out_nodes, f_out, ptr(out), f_out, _lib.stream_ptr()),
+                   'ddp_node_update')
+        return out

@@ -1,0 +1,211 @@
+"""GPU parity tests: the CUDA path through the C ABI against the CPU oracle on the same seeded inputs.
+
+Gates: graphs / edge indices bit-exact; per-layer outputs within 1e-4 relative
+(max |a-b| / max |b|) in the fp32-grade modes and 1e-2 in the BF16 edge-MLP mode; final poses within 0.1 A RMSD.
+"""
+import copy
+import os
+from functools import partial
+
+import numpy as np
+import pytest
+import torch
+
+import _common as T
+from diffdock_pocket_b200 import diffusion_utils as du, inputs, ops, sampling as ps, utils
+from diffdock_pocket_b200.hetero import Batch
+from diffdock_pocket_b200.score_model import TensorProductConvLayer
+from oracle import cluster, diffusion_ref as D, e3nn_mini as E, sampling_ref as S
+from oracle.score_model_ref import TensorProductConvLayer as RefConv
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device('cuda:0')
+
+
+# ------------------------------------------------------------------------------------------- graphs
+def _ragged(seed, sizes, scale=4.0):
+    rng = np.random.RandomState(seed)
+    pts = torch.from_numpy(rng.randn(sum(sizes), 3).astype(np.float32) * scale)
+    batch = torch.repeat_interleave(torch.arange(len(sizes)), torch.tensor(sizes))
+    return pts, batch
+
+
+@pytest.mark.parametrize('cap', [2, 32, 10000])
+def test_radius_bit_exact(cap):
+    x, bx = _ragged(0, [40, 0, 7, 130, 1])
+    y, by = _ragged(1, [9, 3, 0, 55, 2])
+    ref = cluster.radius(x, y, 5.0, bx, by, cap)
+    got = ops.radius(x.to(DEV), y.to(DEV), 5.0, bx.to(DEV), by.to(DEV), cap).cpu()
+    assert torch.equal(got, ref)
+    c = torch.tensor([3.3, 1.0, 2.0, 0.77, 5.0])
+    ref = cluster.radius(x / c[bx][:, None], y / c[by][:, None], 1, bx, by, cap)
+    got = ops.radius(x.to(DEV), y.to(DEV), 1, bx.to(DEV), by.to(DEV), cap, inv_scale=c.to(DEV)).cpu()
+    assert torch.equal(got, ref)
+
+
+def test_radius_graph_and_knn_graph_bit_exact():
+    x, b = _ragged(2, [37, 1, 64, 300, 5], scale=3.0)
+    x[10] = x[11]                                                     # exact duplicates: tie-breaking by index
+    x[200:240] = x[200]                                               # > k+1 coincident points
+    for r, cap in ((5.0, 32), (3.0, 4)):
+        assert torch.equal(ops.radius_graph(x.to(DEV), r, b.to(DEV), max_num_neighbors=cap).cpu(),
+                           cluster.radius_graph(x, r, b, max_num_neighbors=cap))
+    for k in (8, 12, 5, 32):
+        assert torch.equal(ops.knn_graph(x.to(DEV), k, b.to(DEV)).cpu(), cluster.knn_graph(x, k, b))
+    assert ops.radius(x[:0].to(DEV), x.to(DEV), 1.0, b[:0].to(DEV), b.to(DEV)).shape == (2, 0)
+
+
+def test_graphs_on_3dpf_batch_bit_exact():
+    m, c, om, oc, sa, ca = T.models(DEV)
+    dl = T.randomized_list(T.graph(), 3, sa, seed=0)
+    b = T.batch_at(dl, 0.7)
+    lig, atom, rec = b['ligand'], b['atom'], b['receptor']
+    assert torch.equal(ops.knn_graph(atom.pos.to(DEV), 8, atom.batch.to(DEV)).cpu(), cluster.knn_graph(atom.pos, 8, atom.batch))
+    assert torch.equal(ops.radius(atom.pos.to(DEV), lig.pos.to(DEV), 5.0, atom.batch.to(DEV), lig.batch.to(DEV), 10000).cpu(),
+                       cluster.radius(atom.pos, lig.pos, 5.0, atom.batch, lig.batch, 10000))
+    bonds = b['flexResidues'].edge_idx.T + torch.tensor([0, 1111, 2222])[b['flexResidues'].batch]
+    mid = (atom.pos[bonds[0]] + atom.pos[bonds[1]]) / 2
+    ref = cluster.radius(atom.pos, mid, 5.0, atom.batch, b['flexResidues'].batch)            # cap 32 binds
+    got = ops.radius(atom.pos.to(DEV), mid.to(DEV), 5.0, atom.batch.to(DEV), b['flexResidues'].batch.to(DEV)).cpu()
+    assert torch.equal(got, ref) and int(torch.bincount(ref[0]).max()) == 32
+
+
+# ------------------------------------------------------------------------------------------- conv operator
+SEQ = ['60x0e', '60x0e + 10x1o', '60x0e + 10x1o + 10x1e', '60x0e + 10x1o + 10x1e + 60x0o']
+
+
+def _conv_pair(in_ir, sh_ir, out_ir, n_feat, faster, seed=0):
+    torch.manual_seed(seed)
+    prod = TensorProductConvLayer(in_ir, sh_ir, out_ir, n_feat, residual=False, batch_norm=True, faster=faster)
+    bn = prod.batch_norm
+    bn.running_mean.normal_(0, 0.2); bn.running_var.uniform_(0.5, 1.5); bn.weight.data.uniform_(0.7, 1.3); bn.bias.data.normal_(0, 0.2)
+    ref = RefConv(in_ir, sh_ir, out_ir, n_feat, residual=False, batch_norm=True, faster=faster)
+    ref.load_state_dict(prod.state_dict())
+    return prod.to(DEV).eval(), ref.eval()
+
+
+@pytest.mark.parametrize('case', ['l0', 'l1', 'l2', 'l3', 'final', 'lmax2'])
+def test_conv_layer_operator_fp32(case):
+    cfg = {'l0': (SEQ[0], SEQ[1], 180, True), 'l1': (SEQ[1], SEQ[2], 180, True), 'l2': (SEQ[2], SEQ[3], 180, True),
+           'l3': (SEQ[3], SEQ[3], 180, True), 'final': (SEQ[3], '2x1o + 2x1e', 120, True), 'lmax2': (SEQ[3], SEQ[3], 180, False)}[case]
+    in_ir, out_ir, nf, faster = cfg
+    sh_ir = '1x0e+1x1o' if faster else '1x0e+1x1o+1x2e'
+    prod, ref = _conv_pair(in_ir, sh_ir, out_ir, nf, faster)
+    torch.manual_seed(1)
+    n, e = 50, 333
+    x = torch.randn(n, E.Irreps(in_ir).dim)
+    ei = torch.randint(0, n, (2, e))
+    ei[0, :40] = 7                                                   # a hub node; nodes without edges exist too
+    ea = torch.randn(e, nf)
+    sh = E.spherical_harmonics(sh_ir, torch.randn(e, 3))
+    with torch.no_grad():
+        want = ref(x, ei, ea, sh, out_nodes=n + 3)
+        got = prod(x.to(DEV), ei.to(DEV), ea.to(DEV), sh.to(DEV), out_nodes=n + 3)
+    assert T.rel_err(got, want) < 1e-4
+    assert prod(x.to(DEV), ei[:, :0].to(DEV), ea[:0].to(DEV), sh[:0].to(DEV)).item() == 0       # score_model.py:109-111
+
+
+# ------------------------------------------------------------------------------------------- full forward
+@pytest.mark.parametrize('t', [0.7, 0.05])
+def test_score_model_forward_vs_oracle_and_golden(t):
+    m, c, om, oc, sa, ca = T.models(DEV)
+    gold = np.load(os.path.join(T.GOLD, 'golden_forward.npz'))
+    dl = T.randomized_list(T.graph(), 3, sa, seed=0)
+    b = T.batch_at(dl, t)
+    m.conv_mode = 'fp32'
+    with torch.no_grad():
+        pl = m.make_plan(copy.deepcopy(b))
+        tr, rot, tor, sc = m.run_plan(pl, b.complex_t, return_layers=True)
+        want = om(copy.deepcopy(b))
+    dbg = om._debug
+    for nm in ('ll', 'aa', 'lr', 'la'):                               # graphs bit-exact
+        assert torch.equal(pl.es[nm].edge_index().cpu(), dbg[nm].long()), nm
+    for l, ((gl, ga, gr), (wl, wa, wr)) in enumerate(zip(pl.last_layers, dbg['layers'])):
+        assert T.rel_err(gl, wl) < 1e-4 and T.rel_err(ga[:, :wa.shape[1]], wa) < 1e-4, l
+        assert T.rel_err(gr[:, :wr.shape[1]], wr) < 1e-4, l
+    tag = 't70' if t == 0.7 else 't05'
+    for got, w, key in ((tr, want[0], 'tr'), (rot, want[1], 'rot'), (tor, want[2], 'tor'), (sc, want[3], 'sc')):
+        assert T.rel_err(got, w) < 1e-4, key
+        assert T.rel_err(got, gold[f'{tag}_{key}']) < 1e-4, key
+
+
+def test_forward_drop_in_call_and_confidence():
+    m, c, om, oc, sa, ca = T.models(DEV)
+    gold = np.load(os.path.join(T.GOLD, 'golden_forward.npz'))
+    dl = T.randomized_list(T.graph(), 3, sa, seed=0)
+    b = T.batch_at(dl, 0.0)
+    with torch.no_grad():
+        conf = c(copy.deepcopy(b))
+        want = oc(copy.deepcopy(b))
+    assert T.rel_err(conf, want) < 1e-4 and T.rel_err(conf, gold['confidence']) < 1e-4
+    b = T.batch_at(dl[:1], 0.3)                                        # single un-batched graph goes through forward()
+    with torch.no_grad():
+        got = m(copy.deepcopy(b))
+        want = om(copy.deepcopy(b))
+    for g_, w_ in zip(got, want):
+        assert T.rel_err(g_, w_) < 1e-4
+    assert b['atom', 'atom'].edge_index is not None
+
+
+def test_forward_apo_graph_and_empty_cross_edges():
+    """Config-2 graph, plus a ligand pushed 60 A away: no ligand-atom edges -> those convs contribute exactly 0."""
+    m, c, om, oc, sa, ca = T.models(DEV)
+    dl = T.randomized_list(T.graph('3dpf_apo'), 2, sa, seed=3)
+    dl[1]['ligand'].pos = dl[1]['ligand'].pos + torch.tensor([60.0, 0, 0])
+    b = T.batch_at(dl, 0.2)
+    with torch.no_grad():
+        got = m(copy.deepcopy(b))
+        want = om(copy.deepcopy(b))
+    for g_, w_ in zip(got, want):
+        assert T.rel_err(g_, w_) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------- pose update + sampler
+def test_pose_update_vs_oracle():
+    sa = utils.score_model_args()
+    g = T.graph()
+    dl = T.randomized_list(g, 3, sa, seed=4)
+    rng = np.random.RandomState(0)
+    tr, rot = rng.randn(3, 3).astype(np.float32), (rng.randn(3, 3) * 0.4).astype(np.float32)
+    tor, sc = (rng.randn(3, 5) * 0.5).astype(np.float32), (rng.randn(3, 17) * 0.5).astype(np.float32)
+    tor[1, 2] = 0.0                                                   # utils/torsion.py:76 skips exact zeros
+    ref = copy.deepcopy(dl)
+    for i, d in enumerate(ref):
+        D.modify_sidechains(d, sc[i])
+        D.modify_conformer(d, torch.from_numpy(tr[i:i + 1]), torch.from_numpy(rot[i]), tor[i])
+    got = copy.deepcopy(dl)
+    st = du.PoseState(got, DEV)
+    f = lambda a: torch.from_numpy(a.reshape(-1)).to(DEV)
+    st.update((1, 0, 1, 0, 1, 0, 1, 0), f(tr), f(rot), f(tor), f(sc))
+    st.write_back(got)
+    for a, r in zip(got, ref):
+        assert (a['ligand'].pos - r['ligand'].pos).abs().max() < 2e-4
+        assert (a['atom'].pos - r['atom'].pos).abs().max() < 2e-4
+    one = copy.deepcopy(dl[0])                                         # single-graph drop-ins
+    du.modify_sidechains(one, sc[0])
+    du.modify_conformer(one, torch.from_numpy(tr[0:1]), torch.from_numpy(rot[0]), tor[0])
+    assert (one['ligand'].pos.cpu() - ref[0]['ligand'].pos).abs().max() < 2e-4
+    assert (one['atom'].pos.cpu() - ref[0]['atom'].pos).abs().max() < 2e-4
+
+
+def test_sampling_parity_small_model():
+    """Same weights, same initial poses, same CPU noise stream -> poses within 0.1 A RMSD (north-star gate)."""
+    m, c, om, oc, sa, ca = T.models(DEV, small=True)
+    g = inputs.synthetic_complex(5, n_lig=20, n_res=40, flexible_residues=3)
+    dl = T.randomized_list(g, 5, sa, seed=2)
+    steps = 6
+    sch = D.get_t_schedule(steps)
+    kw = dict(temp_sampling=[0.9766, 6.0774, 6.7616, 1.4488], temp_psi=[1.5103, 0.8141, 0.7662, 1.3396], temp_sigma_data=0.48884)
+    torch.manual_seed(11)
+    ref, ref_conf = S.sampling(copy.deepcopy(dl), om, steps, sch, sch, sch, sch, partial(D.t_to_sigma, args=sa), sa,
+                               confidence_model=oc, batch_size=3, **kw)
+    torch.manual_seed(11)
+    m.conv_mode = 'fp32'
+    got, conf = ps.sampling(copy.deepcopy(dl), m, steps, sch, sch, sch, sch, DEV, partial(du.t_to_sigma, args=sa), sa,
+                            confidence_model=c, filtering_model_args=ca, batch_size=3, **kw)
+    for a, r in zip(got, ref):
+        rmsd = float(((a['ligand'].pos.cpu() - r['ligand'].pos) ** 2).sum(-1).mean().sqrt())
+        idx = g['flexResidues'].subcomponents.unique()
+        rmsd_sc = float(((a['atom'].pos.cpu()[idx] - r['atom'].pos[idx]) ** 2).sum(-1).mean().sqrt())
+        assert rmsd < 0.1 and rmsd_sc < 0.1, (rmsd, rmsd_sc)
+    assert T.rel_err(conf, ref_conf) < 1e-2
