@@ -69,8 +69,7 @@ _SIGS = {
     'ddp_graph_sigma_proj': (i32, [vp, i32, f32, vp, i32, vp, vp, i32, i32, vp, vp, vp]),
     'ddp_node_init': (i32, [vp, vp, vp, i32, i32, vp, i32, vp]),
     'ddp_tpconv_fp32': (i32, [C.POINTER(TpConv), C.POINTER(TpEdges), vp, vp]),
-    'ddp_tpconv_pack_size': (C.c_int64, [C.POINTER(TpConv), i32]),
-    'ddp_tpconv_pack': (i32, [C.POINTER(TpConv), C.POINTER(TpGroup), vp, vp, vp, vp, i32, vp]),
+    'ddp_tpconv_pack': (C.c_int64, [C.POINTER(TpConv), C.POINTER(TpGroup), vp, vp, vp, vp, vp, i32, vp]),
     'ddp_tpconv_umma': (i32, [C.POINTER(TpConv), vp, i32, C.POINTER(TpEdges), vp, vp]),
     'ddp_node_update': (i32, [vp, i32, i32, C.POINTER(Update), i32, i32, i32, vp, i32, vp]),
     'ddp_segment_mean': (i32, [vp, vp, vp, i32, i32, i32, vp, i32, vp]),
@@ -82,6 +81,26 @@ _SIGS = {
 }
 EXPORTS = sorted(_SIGS)
 _LIB = None
+# kernels launched per C-ABI call (for the bench's gpu_launches claim)
+KERNELS_PER_CALL = {'ddp_radius': 3, 'ddp_knn_graph': 3, 'ddp_version': 0, 'ddp_tpconv_pack': 0}
+COUNTS = {}
+
+
+def launch_count():
+    return sum(n * KERNELS_PER_CALL.get(k, 1) for k, n in COUNTS.items())
+
+
+class _Counted:
+    def __init__(self, name, fn):
+        self.name, self.fn = name, fn
+
+    def __call__(self, *a):
+        COUNTS[self.name] = COUNTS.get(self.name, 0) + 1
+        return self.fn(*a)
+
+
+class _Lib:
+    pass
 
 
 def build(verbose=False):
@@ -105,10 +124,13 @@ def lib():
         if not os.path.exists(SO_PATH):
             raise RuntimeError(f'{SO_PATH} is missing: run `python -c "import __graft_entry__ as g; g.build()"` '
                                '(there is no CPU fallback for the ddp_b200 kernels)')
-        L = C.CDLL(SO_PATH)
+        dll = C.CDLL(SO_PATH)
+        L = _Lib()
         for name, (res, args) in _SIGS.items():
-            fn = getattr(L, name)
+            fn = getattr(dll, name)
             fn.restype, fn.argtypes = res, args
+            setattr(L, name, _Counted(name, fn))
+        L.dll = dll
         _LIB = L
     return _LIB
 

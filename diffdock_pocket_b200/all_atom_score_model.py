@@ -436,12 +436,20 @@ class TensorProductScoreModel(nn.Module):
                           ld2=p2.shape[1] if p2 is not None else 0, x=ptr(x), gather=es.row(gat_r), ldx=x.shape[1],
                           sh=ptr(es.sh_conv if hasattr(es, 'sh_conv') else es.sh), agg=es.row(agg_r), ew=None,
                           n_edges_dev=ptr(es.n_dev), edge_cap=es.cap)
-        if self.conv_mode != 'fp32' and pk.spec.faster:
+        prof = getattr(self, 'profile', None)
+        if prof is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        if self.conv_mode != 'fp32' and pk.spec.faster and p1 is not None and p2 is not None:
             mode = 0 if self.conv_mode == 'bf16' else 1
             img = pk.umma_image(layer, mode, x.device)
             _lib.check(L.ddp_tpconv_umma(C.byref(pk.cdesc), ptr(img), mode, C.byref(ed), ptr(sum_buf), st), 'ddp_tpconv_umma')
         else:
             _lib.check(L.ddp_tpconv_fp32(C.byref(pk.cdesc), C.byref(ed), ptr(sum_buf), st), 'ddp_tpconv_fp32')
+        if prof is not None:
+            ev1.record()
+            if p1 is not None and p2 is not None and pk.spec.faster:
+                prof.append((ev0, ev1, pk.spec.weight_numel, es, self.ns))
 
     def run_plan(self, pl, complex_t, return_layers=False):
         """Forward on a resident plan.  Returns device tensors; performs no host synchronisation."""

@@ -1,10 +1,654 @@
-// Tensor-core (tcgen05 / TMEM) tensor-product convolution -- placeholder entry points until the
-// kernel lands (the fp32 path is the only conv path in this build).
+// Tensor-core tensor-product convolution for sm_100a: tcgen05.mma (bf16 x bf16 -> fp32 in TMEM),
+// weights streamed by TMA bulk copies (cp.async.bulk, UBLKCP) through an mbarrier ring, per-edge
+// weight tiles consumed straight out of TMEM by the tensor-product epilogue.  The per-edge weight
+// vector (up to 10000 floats) never exists in shared or global memory.
+//
+// One CTA = one tile of 128 edges (TMEM lane = edge).  Warp roles:
+//   warps 0-3  gather + epilogue: stage [emb | node scalars] as the bf16 A operand and the gathered node
+//              features (fp32) in shared memory; after GEMM1 apply ReLU and write the hidden activations back
+//              as the A operand of GEMM2; then, per weight tile, tcgen05.ld the [128 x N] accumulator,
+//              multiply with the tensor-product basis and accumulate the edge's output in registers;
+//              red.global.add into the aggregation node at the end of each output block.
+//   warp 4     TMA producer: streams the pre-packed weight image (already in UMMA core-matrix order and in
+//              consumption order) slab by slab.
+//   warp 5     MMA issuer (one elected lane) + TMEM allocator.
+//
+// Biases ride in the GEMMs: A has a constant-one column (padding slot of the first 64-wide source block)
+// and the images carry b1 / b2 in that K row; the hidden unit `hid` regenerates the one for GEMM2.
+// mode 1 ("bf16x3") splits both operands into bf16 hi + lo and issues hi*hi + lo*hi + hi*lo, which gives
+// fp32-grade products (error ~2^-17 per product) for the 1e-4 parity gate.
+#include <cuda_bf16.h>
+#include <string.h>
+
+#include <vector>
+
 #include "ddp_common.cuh"
 
-extern "C" int64_t ddp_tpconv_pack_size(const ddp_tpconv_t *, int32_t) { return DDP_E_UNSUPPORTED; }
-extern "C" int ddp_tpconv_pack(const ddp_tpconv_t *, const ddp_tp_group_t *, const float *, const float *, const float *,
-                               const float *, int32_t, void *) { return DDP_E_UNSUPPORTED; }
-extern "C" int ddp_tpconv_umma(const ddp_tpconv_t *, const void *, int32_t, const ddp_tpconv_edges_t *, float *, void *) {
-    return DDP_E_UNSUPPORTED;
+namespace umma {
+
+constexpr int TILE_M = 128;
+constexpr int MAX_ROWS = 16;
+constexpr uint32_t MAGIC = 0x44445055u;  // "DDPU"
+
+struct TileDesc {
+    uint16_t n_cols;      // UMMA N of this weight tile (multiple of 16)
+    uint8_t type;         // 0 scalar block (NS outputs), 1 vector block (NV x 3 outputs)
+    uint8_t n_rows;       // basis rows covered (rest is zero padding)
+    uint16_t out_off;     // first output feature of the block
+    uint8_t first, last;  // first / last tile of its block
+    uint8_t row_kind[MAX_ROWS];  // 0 x*s0, 1 dot(xv,s1), 2 x*s1, 3 xv*s0, 4 cross(xv,s1), 255 padding
+    uint8_t row_x[MAX_ROWS];     // offset of the row's input feature(s)
+};
+
+struct Header {
+    uint32_t magic;
+    int32_t mode, ns, nv, ks, kp, n1, stage_k, n_tiles, n_slabs_per_edge_tile;
+    int32_t f_in, f_out, n_parts;
+    int32_t slab_elems_max;   // elements (bf16) of the largest slab part (one of hi / lo)
+    int64_t tiles_off, slabs_off, total_bytes;
+};
+
+__host__ __device__ inline int slab_bytes(int n_cols, int stage_k, int mode) { return n_cols * stage_k * 2 * (mode ? 2 : 1); }
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra W_%=;\n\t}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate, both operands K-major
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// no-swizzle K-major shared-memory descriptor: 8x(16 B) core matrices, LBO = stride between the two
+// K-chunks of one MMA, SBO = stride between 8-row groups (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+__device__ __forceinline__ uint32_t instr_desc(int n) {
+    // c=f32 (1<<4), a=bf16 (1<<7), b=bf16 (1<<10), K-major A and B, N>>3 at bit 17, M>>4 at bit 24
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void red_add(float *p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&t);
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+// NS scalar multiplicity, NV vector multiplicity, KS padded width of one A source block (>= NS + 1).
+template <int NS, int NV, int KS, bool SPLIT>
+struct Cfg {
+    static constexpr int KP = 3 * KS;                       // padded K of both GEMMs (and padded hidden width N1)
+    static constexpr int N1 = KP;
+    static constexpr int ROWS_S = 240 / NS;                 // basis rows per scalar tile
+    static constexpr int NCOL_S = ROWS_S * NS;
+    static constexpr int ROWS_V = 16;
+    static constexpr int NCOL_V = ROWS_V * NV;
+    static constexpr int NCOL_MAX = (NCOL_S > N1 ? NCOL_S : N1);
+    static constexpr int STAGE_K = SPLIT ? 16 : 32;
+    static constexpr int STAGES = SPLIT ? 2 : (KS == 64 ? 5 : 6);
+    static constexpr int STAGE_BYTES = NCOL_MAX * STAGE_K * 2 * (SPLIT ? 2 : 1);
+    static constexpr int A_BYTES = TILE_M * KP * 2;         // one bf16 A image
+    static constexpr int F_MAX = 2 * NS + 6 * NV;
+    static constexpr int XLD = F_MAX + 1;                   // odd row stride: conflict-free per-thread rows
+    static constexpr int X_BYTES = TILE_M * XLD * 4;
+    static constexpr int MAX_TILES = 64;
+    static constexpr size_t SMEM = 1024 + (size_t)A_BYTES * (SPLIT ? 2 : 1) + X_BYTES + (size_t)STAGES * STAGE_BYTES +
+                                   MAX_TILES * sizeof(TileDesc) + 256;
+    static_assert(NCOL_S % 16 == 0 && NCOL_V % 16 == 0 && N1 % 16 == 0 && NCOL_MAX <= 256, "UMMA N constraints");
+    static_assert(KS >= NS + 1 && KP % STAGE_K == 0, "K padding");
+};
+
+template <int NS, int NV, int KS, bool SPLIT>
+__global__ void __launch_bounds__(192, 1)
+tpconv_umma_kernel(const uint8_t *__restrict__ image, ddp_tpconv_edges_t ed, int f_in, int f_out, int n_parts,
+                   float *__restrict__ sum) {
+    using C = Cfg<NS, NV, KS, SPLIT>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve (everything 128 B aligned)
+    uint8_t *p = smem_raw;
+    uint8_t *a_hi = p;                     p += C::A_BYTES;
+    uint8_t *a_lo = p;                     p += SPLIT ? C::A_BYTES : 0;
+    float *xs = reinterpret_cast<float *>(p); p += (C::X_BYTES + 127) / 128 * 128;
+    uint8_t *ring = p;                     p += (size_t)C::STAGES * C::STAGE_BYTES;
+    TileDesc *tiles = reinterpret_cast<TileDesc *>(p); p += C::MAX_TILES * sizeof(TileDesc);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(p);
+    uint64_t *full = bars, *empty = bars + C::STAGES;
+    uint64_t *tmem_full = bars + 2 * C::STAGES, *tmem_empty = tmem_full + 2;
+    uint64_t *a_ready = tmem_empty + 2, *h_ready = a_ready + 1;
+    uint32_t *tmem_base_smem = reinterpret_cast<uint32_t *>(h_ready + 1);
+
+    const Header *hdr = reinterpret_cast<const Header *>(image);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = hdr->n_tiles;
+    const int n_edges = min(*ed.n_edges_dev, ed.edge_cap);
+    const int n_etiles = (n_edges + TILE_M - 1) / TILE_M;
+
+    for (int i = threadIdx.x; i < n_tiles * (int)(sizeof(TileDesc) / 4); i += blockDim.x)
+        reinterpret_cast<uint32_t *>(tiles)[i] = reinterpret_cast<const uint32_t *>(image + hdr->tiles_off)[i];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], TILE_M); }
+        mbar_init(a_ready, TILE_M);
+        mbar_init(h_ready, TILE_M);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) tmem_alloc(tmem_base_smem, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+
+    if (warp == 4) {
+        // =============================== TMA producer ===========================================
+        if (lane == 0) {
+            const uint8_t *slabs = image + hdr->slabs_off;
+            uint32_t stage = 0, phase = 0;
+            for (int et = blockIdx.x; et < n_etiles; et += gridDim.x) {
+                const uint8_t *src = slabs;
+                for (int t = -1; t < n_tiles; ++t) {
+                    const int ncol = (t < 0) ? C::N1 : tiles[t].n_cols;
+                    const uint32_t bytes = slab_bytes(ncol, C::STAGE_K, SPLIT);
+                    for (int ks = 0; ks < C::KP / C::STAGE_K; ++ks) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        mbar_expect_tx(&full[stage], bytes);
+                        bulk_g2s(ring + (size_t)stage * C::STAGE_BYTES, src, bytes, &full[stage]);
+                        src += bytes;
+                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // =============================== MMA issuer =============================================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            uint32_t te_phase[2] = {0, 0};       // parity to wait on tmem_empty[b]
+            uint32_t ar_phase = 0, hr_phase = 0;
+            const uint32_t a_hi_addr = smem_u32(a_hi), a_lo_addr = smem_u32(a_lo);
+            for (int et = blockIdx.x; et < n_etiles; et += gridDim.x) {
+                for (int t = -1; t < n_tiles; ++t) {
+                    const int ncol = (t < 0) ? C::N1 : tiles[t].n_cols;
+                    const int buf = (t + 1) & 1;
+                    if (t < 0) { mbar_wait(a_ready, ar_phase); ar_phase ^= 1; }
+                    if (t == 0) { mbar_wait(h_ready, hr_phase); hr_phase ^= 1; }
+                    mbar_wait(&tmem_empty[buf], te_phase[buf] ^ 1);
+                    te_phase[buf] ^= 1;
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u;
+                    const uint32_t idesc = instr_desc(ncol);
+                    const uint32_t b_lbo = (uint32_t)ncol * 16u;
+                    uint32_t acc = 0;
+                    for (int ks = 0; ks < C::KP / C::STAGE_K; ++ks) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t b_addr = smem_u32(ring + (size_t)stage * C::STAGE_BYTES);
+#pragma unroll
+                        for (int kk = 0; kk < C::STAGE_K / 16; ++kk) {
+                            const uint32_t a_off = (uint32_t)((ks * (C::STAGE_K / 8) + 2 * kk) * (TILE_M * 16));
+                            const uint32_t b_off = (uint32_t)(2 * kk) * b_lbo;
+                            const uint64_t ah = smem_desc(a_hi_addr + a_off, TILE_M * 16, 128);
+                            const uint64_t bh = smem_desc(b_addr + b_off, b_lbo, 128);
+                            umma_bf16(d_tmem, ah, bh, idesc, acc);
+                            acc = 1;
+                            if (SPLIT) {
+                                const uint64_t al = smem_desc(a_lo_addr + a_off, TILE_M * 16, 128);
+                                const uint64_t bl = smem_desc(b_addr + (uint32_t)(ncol * C::STAGE_K * 2) + b_off, b_lbo, 128);
+                                umma_bf16(d_tmem, al, bh, idesc, 1);
+                                umma_bf16(d_tmem, ah, bl, idesc, 1);
+                            }
+                        }
+                        umma_commit(&empty[stage]);
+                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit(&tmem_full[buf]);
+                }
+            }
+        }
+    } else {
+        // =============================== gather + epilogue warps ===================================
+        const int r = threadIdx.x;                       // edge row = TMEM lane
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        uint32_t tf_phase[2] = {0, 0};
+        float *xrow = xs + (size_t)r * C::XLD;
+        const uint32_t a_row_off = (uint32_t)((r >> 3) * 128 + (r & 7) * 16);
+        for (int et = blockIdx.x; et < n_etiles; et += gridDim.x) {
+            const int e = et * TILE_M + r;
+            const bool valid = e < n_edges;
+            int agg = -1;
+            float s0 = 0.f, s1x = 0.f, s1y = 0.f, s1z = 0.f;
+            // ---- stage the A operand [emb | p1 | p2] (bf16, constant one in slot NS of source 0) and x ----
+            const float *srcs[3] = {nullptr, nullptr, nullptr};
+            if (valid) {
+                agg = ed.agg[e];
+                const float4 sh4 = *reinterpret_cast<const float4 *>(ed.sh + (size_t)e * 4);
+                s0 = sh4.x; s1x = sh4.y; s1y = sh4.z; s1z = sh4.w;
+                srcs[0] = ed.emb + (size_t)e * NS;
+                if (ed.p1) srcs[1] = ed.p1 + (size_t)ed.i1[e] * ed.ld1;
+                if (ed.p2) srcs[2] = ed.p2 + (size_t)ed.i2[e] * ed.ld2;
+            }
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+#pragma unroll
+                for (int c8 = 0; c8 < KS / 8; ++c8) {
+                    float v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int j = c8 * 8 + q;
+                        v[q] = (srcs[s] != nullptr && j < NS) ? __ldg(srcs[s] + j) : 0.f;
+                        if (s == 0 && j == NS) v[q] = 1.f;
+                    }
+                    uint4 hi;
+                    hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
+                    hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
+                    const uint32_t off = (uint32_t)((s * (KS / 8) + c8) * (TILE_M * 16)) + a_row_off;
+                    *reinterpret_cast<uint4 *>(a_hi + off) = hi;
+                    if (SPLIT) {
+                        float w[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) w[q] = v[q] - __bfloat162float(__float2bfloat16_rn(v[q]));
+                        uint4 lo;
+                        lo.x = pack_bf16x2(w[0], w[1]); lo.y = pack_bf16x2(w[2], w[3]);
+                        lo.z = pack_bf16x2(w[4], w[5]); lo.w = pack_bf16x2(w[6], w[7]);
+                        *reinterpret_cast<uint4 *>(a_lo + off) = lo;
+                    }
+                }
+            }
+            {
+                const float *xg = valid ? ed.x + (size_t)ed.gather[e] * ed.ldx : nullptr;
+                for (int c = 0; c < f_in; ++c) xrow[c] = valid ? __ldg(xg + c) : 0.f;
+            }
+            fence_proxy_async();
+            mbar_arrive(a_ready);
+
+            // ---- GEMM1 result -> ReLU -> hidden activations become the A operand of GEMM2 ----
+            mbar_wait(&tmem_full[0], tf_phase[0]);
+            tf_phase[0] ^= 1;
+            tc_fence_after();
+#pragma unroll 1
+            for (int c16 = 0; c16 < C::N1 / 16; ++c16) {
+                float v[16];
+                tmem_ld16(tmem_base + lane_base + (uint32_t)(c16 * 16), v);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) v[q] = fmaxf(v[q], 0.f);
+#pragma unroll
+                for (int h8 = 0; h8 < 2; ++h8) {
+                    uint4 hi;
+                    hi.x = pack_bf16x2(v[8 * h8 + 0], v[8 * h8 + 1]); hi.y = pack_bf16x2(v[8 * h8 + 2], v[8 * h8 + 3]);
+                    hi.z = pack_bf16x2(v[8 * h8 + 4], v[8 * h8 + 5]); hi.w = pack_bf16x2(v[8 * h8 + 6], v[8 * h8 + 7]);
+                    const uint32_t off = (uint32_t)((c16 * 2 + h8) * (TILE_M * 16)) + a_row_off;
+                    *reinterpret_cast<uint4 *>(a_hi + off) = hi;
+                    if (SPLIT) {
+                        float w[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) w[q] = v[8 * h8 + q] - __bfloat162float(__float2bfloat16_rn(v[8 * h8 + q]));
+                        uint4 lo;
+                        lo.x = pack_bf16x2(w[0], w[1]); lo.y = pack_bf16x2(w[2], w[3]);
+                        lo.z = pack_bf16x2(w[4], w[5]); lo.w = pack_bf16x2(w[6], w[7]);
+                        *reinterpret_cast<uint4 *>(a_lo + off) = lo;
+                    }
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            mbar_arrive(h_ready);
+            mbar_arrive(&tmem_empty[0]);
+
+            // ---- weight tiles: TMEM accumulator x tensor-product basis -> per-edge output registers ----
+            float acc[NS];
+#pragma unroll 1
+            for (int t = 0; t < n_tiles; ++t) {
+                const TileDesc &td = tiles[t];
+                const int buf = (t + 1) & 1;
+                const uint32_t taddr = tmem_base + lane_base + (uint32_t)buf * 256u;
+                if (td.first) {
+#pragma unroll
+                    for (int o = 0; o < NS; ++o) acc[o] = 0.f;
+                }
+                if (td.type == 0) {
+                    float b[C::ROWS_S];
+#pragma unroll
+                    for (int rr = 0; rr < C::ROWS_S; ++rr) {
+                        const int kind = td.row_kind[rr], xo = td.row_x[rr];
+                        float bv = 0.f;
+                        if (kind == 0) bv = xrow[xo] * s0;
+                        else if (kind == 1) bv = xrow[xo] * s1x + xrow[xo + 1] * s1y + xrow[xo + 2] * s1z;
+                        b[rr] = bv;
+                    }
+                    mbar_wait(&tmem_full[buf], tf_phase[buf]);
+                    tf_phase[buf] ^= 1;
+                    tc_fence_after();
+#pragma unroll
+                    for (int c16 = 0; c16 < C::NCOL_S / 16; ++c16) {
+                        float w[16];
+                        tmem_ld16(taddr + (uint32_t)(c16 * 16), w);
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            const int c = c16 * 16 + q;
+                            acc[c % NS] = fmaf(w[q], b[c / NS], acc[c % NS]);
+                        }
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&tmem_empty[buf]);
+                    if (td.last && valid) {
+                        float *dst = sum + (size_t)agg * f_out + td.out_off;
+#pragma unroll
+                        for (int o = 0; o < NS; ++o) red_add(dst + o, acc[o]);
+                    }
+                } else {
+                    float bx[C::ROWS_V], by[C::ROWS_V], bz[C::ROWS_V];
+#pragma unroll
+                    for (int rr = 0; rr < C::ROWS_V; ++rr) {
+                        const int kind = td.row_kind[rr], xo = td.row_x[rr];
+                        float vx = 0.f, vy = 0.f, vz = 0.f;
+                        if (kind == 2) { const float x0 = xrow[xo]; vx = x0 * s1x; vy = x0 * s1y; vz = x0 * s1z; }
+                        else if (kind == 3) { vx = xrow[xo] * s0; vy = xrow[xo + 1] * s0; vz = xrow[xo + 2] * s0; }
+                        else if (kind == 4) {
+                            const float ax = xrow[xo], ay = xrow[xo + 1], az = xrow[xo + 2];
+                            vx = ay * s1z - az * s1y; vy = az * s1x - ax * s1z; vz = ax * s1y - ay * s1x;
+                        }
+                        bx[rr] = vx; by[rr] = vy; bz[rr] = vz;
+                    }
+                    mbar_wait(&tmem_full[buf], tf_phase[buf]);
+                    tf_phase[buf] ^= 1;
+                    tc_fence_after();
+#pragma unroll
+                    for (int c16 = 0; c16 < C::NCOL_V / 16; ++c16) {
+                        float w[16];
+                        tmem_ld16(taddr + (uint32_t)(c16 * 16), w);
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            const int c = c16 * 16 + q;
+                            const int rr = c / NV, o = c % NV;
+                            acc[3 * o] = fmaf(w[q], bx[rr], acc[3 * o]);
+                            acc[3 * o + 1] = fmaf(w[q], by[rr], acc[3 * o + 1]);
+                            acc[3 * o + 2] = fmaf(w[q], bz[rr], acc[3 * o + 2]);
+                        }
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&tmem_empty[buf]);
+                    if (td.last && valid) {
+                        float *dst = sum + (size_t)agg * f_out + td.out_off;
+#pragma unroll
+                        for (int o = 0; o < 3 * NV; ++o) red_add(dst + o, acc[o]);
+                    }
+                }
+            }
+        }
+    }
+    // ------------------------------------------------------------------------------------------ teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------ host: packing
+struct HostPlan {
+    Header h;
+    std::vector<TileDesc> tiles;
+    std::vector<std::vector<std::pair<int, float>>> tile_cols;  // per tile: (weight column or -1, scale) per UMMA column
+};
+
+static bool pick_cfg(int ns, int nv, int &ks) {
+    if (ns == 60 && nv == 10) { ks = 64; return true; }
+    if (ns == 24 && nv == 6) { ks = 32; return true; }
+    if (ns == 16 && nv == 4) { ks = 32; return true; }
+    return false;
+}
+
+// Classify a row group of a FasterTensorProduct-shaped spec from its dims and coefficient pattern.
+static int group_kind(const ddp_tp_group_t &g, const float *ctab, float &scale) {
+    const float *c = ctab + g.c_off;
+    if (g.d1 == 1 && g.d2 == 1 && g.d_out == 1) { scale = c[0]; return 0; }
+    if (g.d1 == 3 && g.d2 == 3 && g.d_out == 1) { scale = c[0]; return 1; }          // delta_ij * scale
+    if (g.d1 == 1 && g.d2 == 3 && g.d_out == 3) { scale = c[0]; return 2; }          // delta_jk * scale
+    if (g.d1 == 3 && g.d2 == 1 && g.d_out == 3) { scale = c[0]; return 3; }          // delta_ik * scale
+    if (g.d1 == 3 && g.d2 == 3 && g.d_out == 3) { scale = c[(0 * 3 + 1) * 3 + 2]; return 4; }  // eps_ijk * scale
+    return -1;
+}
+
+static int build_plan(const ddp_tpconv_t &c, const ddp_tp_group_t *groups, const float *ctab_host, int mode, HostPlan &P) {
+    int ks;
+    const int ns = c.ns;
+    // vector multiplicity = mul_out of the first vector-output group
+    int nv = 0;
+    for (int g = 0; g < c.n_groups; ++g)
+        if (groups[g].d_out == 3) { nv = groups[g].mul_out; break; }
+    if (nv == 0) nv = (ns == 60) ? 10 : (ns == 24 ? 6 : 4);
+    if (!pick_cfg(ns, nv, ks)) return DDP_E_UNSUPPORTED;
+    if (c.k1 != 3 * ns || c.hid != 3 * ns || c.n_emb != ns || c.sh_dim != 4) return DDP_E_UNSUPPORTED;
+    if (c.f_in > 2 * ns + 6 * nv) return DDP_E_UNSUPPORTED;
+    const int rows_s = 240 / ns, rows_v = 16;
+    Header &h = P.h;
+    memset(&h, 0, sizeof(h));
+    h.magic = MAGIC; h.mode = mode; h.ns = ns; h.nv = nv; h.ks = ks; h.kp = 3 * ks; h.n1 = 3 * ks;
+    h.stage_k = mode ? 16 : 32; h.f_in = c.f_in; h.f_out = c.f_out;
+    // groups sharing (out_off, d_out) form one weight block; they are contiguous in w_off order
+    int g = 0;
+    while (g < c.n_groups) {
+        int g_end = g;
+        while (g_end < c.n_groups && groups[g_end].out_off == groups[g].out_off && groups[g_end].d_out == groups[g].d_out) ++g_end;
+        const bool vec = groups[g].d_out == 3;
+        const int mul_out = groups[g].mul_out;
+        if (mul_out != (vec ? nv : ns)) return DDP_E_UNSUPPORTED;
+        struct Row { int kind, xo, wcol; float scale; };
+        std::vector<Row> rows;
+        for (int q = g; q < g_end; ++q) {
+            float sc;
+            const int kind = group_kind(groups[q], ctab_host, sc);
+            if (kind < 0 || (vec != (kind >= 2))) return DDP_E_UNSUPPORTED;
+            if (groups[q].sh_off != ((kind == 0 || kind == 3) ? 0 : 1)) return DDP_E_UNSUPPORTED;
+            for (int u = 0; u < groups[q].mul_in; ++u)
+                rows.push_back({kind, groups[q].x_off + u * groups[q].d1, groups[q].w_off + u * mul_out, sc});
+        }
+        const int per = vec ? rows_v : rows_s;
+        const int n_t = ((int)rows.size() + per - 1) / per;
+        for (int t = 0; t < n_t; ++t) {
+            TileDesc td;
+            memset(&td, 0, sizeof(td));
+            td.n_cols = (uint16_t)(per * mul_out);
+            td.type = vec ? 1 : 0;
+            td.out_off = (uint16_t)groups[g].out_off;
+            td.first = t == 0; td.last = t == n_t - 1;
+            std::vector<std::pair<int, float>> cols(td.n_cols, {-1, 0.f});
+            int nr = 0;
+            for (int rr = 0; rr < per; ++rr) {
+                const int ri = t * per + rr;
+                if (ri < (int)rows.size()) {
+                    td.row_kind[rr] = (uint8_t)rows[ri].kind; td.row_x[rr] = (uint8_t)rows[ri].xo; ++nr;
+                    for (int o = 0; o < mul_out; ++o) cols[rr * mul_out + o] = {rows[ri].wcol + o, rows[ri].scale};
+                } else {
+                    td.row_kind[rr] = 255;
+                }
+            }
+            td.n_rows = (uint8_t)nr;
+            P.tiles.push_back(td);
+            P.tile_cols.push_back(cols);
+        }
+        g = g_end;
+    }
+    h.n_tiles = (int)P.tiles.size();
+    if (h.n_tiles > 64) return DDP_E_UNSUPPORTED;
+    int64_t off = (sizeof(Header) + 127) / 128 * 128;
+    h.tiles_off = off;
+    off += (int64_t)((h.n_tiles * sizeof(TileDesc) + 127) / 128 * 128);
+    h.slabs_off = off;
+    int64_t slab_total = (int64_t)slab_bytes(h.n1, h.stage_k, mode) * (h.kp / h.stage_k);
+    for (auto &td : P.tiles) slab_total += (int64_t)slab_bytes(td.n_cols, h.stage_k, mode) * (h.kp / h.stage_k);
+    h.total_bytes = off + slab_total;
+    h.n_slabs_per_edge_tile = (h.n_tiles + 1) * (h.kp / h.stage_k);
+    return 0;
+}
+
+static inline uint16_t f2bf(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+static inline float bf2f(uint16_t b) {
+    uint32_t u = (uint32_t)b << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+// Write one [n_cols x KP] operand (value(n, k) callback) as K-slabs in UMMA no-swizzle core-matrix order:
+// slab ks: [k-chunk (stage_k/8)][row group (n_cols/8)][8 rows][8 elements]; split mode appends the lo image.
+template <class F>
+static uint8_t *emit_operand(uint8_t *dst, int n_cols, int kp, int stage_k, int mode, F value) {
+    for (int ks = 0; ks < kp / stage_k; ++ks) {
+        uint16_t *hi = reinterpret_cast<uint16_t *>(dst);
+        uint16_t *lo = hi + (size_t)n_cols * stage_k;
+        for (int kc = 0; kc < stage_k / 8; ++kc)
+            for (int n = 0; n < n_cols; ++n)
+                for (int q = 0; q < 8; ++q) {
+                    const float v = value(n, ks * stage_k + kc * 8 + q);
+                    const size_t idx = ((size_t)kc * (n_cols / 8) + n / 8) * 64 + (n % 8) * 8 + q;
+                    const uint16_t h = f2bf(v);
+                    hi[idx] = h;
+                    if (mode) lo[idx] = f2bf(v - bf2f(h));
+                }
+        dst += slab_bytes(n_cols, stage_k, mode);
+    }
+    return dst;
+}
+
+}  // namespace umma
+
+extern "C" int64_t ddp_tpconv_pack(const ddp_tpconv_t *conv, const ddp_tp_group_t *groups_host, const float *ctab_host,
+                                    const float *w1, const float *b1, const float *w2, const float *b2, int32_t mode,
+                                    void *packed_host) {
+    using namespace umma;
+    if (!conv || !groups_host || !ctab_host) return DDP_E_ARG;
+    if (mode != 0 && mode != 1) return DDP_E_ARG;
+    HostPlan P;
+    const int rc = build_plan(*conv, groups_host, ctab_host, mode, P);
+    if (rc != 0) return rc;
+    if (packed_host == nullptr) return P.h.total_bytes;
+    if (!w1 || !b1 || !w2 || !b2) return DDP_E_ARG;
+    const Header &h = P.h;
+    uint8_t *base = static_cast<uint8_t *>(packed_host);
+    memset(base, 0, (size_t)h.total_bytes);
+    memcpy(base, &h, sizeof(h));
+    memcpy(base + h.tiles_off, P.tiles.data(), P.tiles.size() * sizeof(TileDesc));
+    const int ns = h.ns, ks = h.ks, hid = conv->hid, k1 = conv->k1;
+    uint8_t *dst = base + h.slabs_off;
+    // GEMM1 operand: rows n = hidden unit, k' = source * ks + j; bias in (source 0, j = ns); row `hid` regenerates the one
+    dst = emit_operand(dst, h.n1, h.kp, h.stage_k, mode, [&](int n, int kq) -> float {
+        const int s = kq / ks, j = kq % ks;
+        if (n < hid) {
+            if (j < ns) return w1[(size_t)n * k1 + s * ns + j];
+            if (s == 0 && j == ns) return b1[n];
+            return 0.f;
+        }
+        return (n == hid && s == 0 && j == ns) ? 1.f : 0.f;
+    });
+    // GEMM2 operands: rows = UMMA columns of the tile, k = hidden unit (bias at k = hid)
+    for (size_t t = 0; t < P.tiles.size(); ++t) {
+        const auto &cols = P.tile_cols[t];
+        dst = emit_operand(dst, P.tiles[t].n_cols, h.kp, h.stage_k, mode, [&](int n, int k) -> float {
+            const int wc = cols[n].first;
+            if (wc < 0) return 0.f;
+            if (k < hid) return cols[n].second * w2[(size_t)wc * hid + k];
+            if (k == hid) return cols[n].second * b2[wc];
+            return 0.f;
+        });
+    }
+    return (dst - base) == h.total_bytes ? 0 : DDP_E_SHAPE;
+}
+
+template <int NS, int NV, int KS, bool SPLIT>
+static int launch_umma(const uint8_t *image, const ddp_tpconv_t &c, const ddp_tpconv_edges_t &e, float *sum, cudaStream_t st) {
+    using C = umma::Cfg<NS, NV, KS, SPLIT>;
+    auto kern = umma::tpconv_umma_kernel<NS, NV, KS, SPLIT>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (err != cudaSuccess) return (int)err;
+        configured = true;
+    }
+    const int tiles = (e.edge_cap + umma::TILE_M - 1) / umma::TILE_M;
+    const int grid = tiles < ddp_num_sms() ? tiles : ddp_num_sms();
+    const int parts = (e.p1 != nullptr) + (e.p2 != nullptr);
+    kern<<<grid, 192, C::SMEM, st>>>(image, e, c.f_in, c.f_out, parts, sum);
+    DDP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ddp_tpconv_umma(const ddp_tpconv_t *conv, const void *packed, int32_t mode, const ddp_tpconv_edges_t *edges,
+                               float *sum, void *stream) {
+    if (!conv || !packed || !edges || !sum) return DDP_E_ARG;
+    const ddp_tpconv_t &c = *conv;
+    const ddp_tpconv_edges_t &e = *edges;
+    if (!e.emb || !e.x || !e.gather || !e.sh || !e.agg || !e.n_edges_dev || !e.p1 || !e.p2 || !e.i1 || !e.i2) return DDP_E_ARG;
+    if (e.ew != nullptr) return DDP_E_UNSUPPORTED;
+    if (e.edge_cap <= 0) return 0;
+    int nv = 0;
+    if (c.ns == 60) nv = 10; else if (c.ns == 24) nv = 6; else if (c.ns == 16) nv = 4; else return DDP_E_UNSUPPORTED;
+    const uint8_t *img = static_cast<const uint8_t *>(packed);
+    cudaStream_t st = (cudaStream_t)stream;
+    (void)nv;
+    if (c.ns == 60) return mode ? launch_umma<60, 10, 64, true>(img, c, e, sum, st) : launch_umma<60, 10, 64, false>(img, c, e, sum, st);
+    if (c.ns == 24) return mode ? launch_umma<24, 6, 32, true>(img, c, e, sum, st) : launch_umma<24, 6, 32, false>(img, c, e, sum, st);
+    return mode ? launch_umma<16, 4, 32, true>(img, c, e, sum, st) : launch_umma<16, 4, 32, false>(img, c, e, sum, st);
 }

@@ -38,6 +38,8 @@ def _run_radius(x, y, r, batch_x, batch_y, max_num_neighbors, mode, inv_scale=No
     nb = _num_examples(batch_x, batch_y)
     px, py = _ptr_from_batch(batch_x, x.shape[0], nb, dev), _ptr_from_batch(batch_y, y.shape[0], nb, dev)
     n_y = y.shape[0]
+    if n_y == 0 or x.shape[0] == 0:
+        return torch.zeros(2, 0, dtype=torch.long, device=dev)
     seg = int((px[1:] - px[:-1]).max().item()) if x.shape[0] else 0
     slab_w = max(min(int(max_num_neighbors), seg), 1)
     slab = torch.empty(max(n_y, 1) * slab_w, dtype=torch.int32, device=dev)
@@ -59,7 +61,7 @@ def radius(x, y, r, batch_x=None, batch_y=None, max_num_neighbors=32, inv_scale=
 
 def radius_graph(x, r, batch=None, loop=False, max_num_neighbors=32, flow='source_to_target'):
     assert not loop and flow == 'source_to_target'
-    return _run_radius(x, x, r, batch, batch, max_num_neighbors + 1, _lib.lib() and 1)
+    return _run_radius(x, x, r, batch, batch, max_num_neighbors + 1, 1)
 
 
 def knn_graph(x, k, batch=None, loop=False, flow='source_to_target'):
@@ -69,6 +71,8 @@ def knn_graph(x, k, batch=None, loop=False, flow='source_to_target'):
         raise RuntimeError('ddp_b200 graph ops run on CUDA only (no CPU fallback)')
     x = x.float().contiguous()
     n = x.shape[0]
+    if n == 0:
+        return torch.zeros(2, 0, dtype=torch.long, device=dev)
     nb = _num_examples(batch, batch)
     p = _ptr_from_batch(batch, n, nb, dev)
     slab = torch.empty(max(n, 1) * (k + 1), dtype=torch.int32, device=dev)

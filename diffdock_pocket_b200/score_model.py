@@ -177,17 +177,18 @@ class PackedConv:
     def umma_image(self, layer, mode, device):
         if mode not in self.umma:
             L = _lib.lib()
-            size = L.ddp_tpconv_pack_size(C.byref(self.cdesc), mode)
-            if size <= 0:
-                raise RuntimeError(f'ddp_tpconv_pack_size failed ({size}): conv is not tensor-core eligible')
-            host = torch.empty(size, dtype=torch.uint8)
             fc0, fc3 = layer.fc[0], layer.fc[3]
             w1 = fc0.weight.detach().cpu().float().contiguous()
             b1 = fc0.bias.detach().cpu().float().contiguous()
             w2 = fc3.weight.detach().cpu().float().contiguous()
             b2 = fc3.bias.detach().cpu().float().contiguous()
-            _lib.check(L.ddp_tpconv_pack(C.byref(self.cdesc), self.groups_host, ptr(w1), ptr(b1), ptr(w2), ptr(b2), mode,
-                                         ptr(host)), 'ddp_tpconv_pack')
+            ctab = torch.tensor(self.spec.ctab, dtype=torch.float32)
+            args = (C.byref(self.cdesc), self.groups_host, ptr(ctab), ptr(w1), ptr(b1), ptr(w2), ptr(b2), mode)
+            size = L.ddp_tpconv_pack(*args, None)
+            if size <= 0:
+                raise RuntimeError(f'ddp_tpconv_pack failed ({size}): conv is not tensor-core eligible')
+            host = torch.empty(size, dtype=torch.uint8)
+            _lib.check(L.ddp_tpconv_pack(*args, ptr(host)), 'ddp_tpconv_pack')
             self.umma[mode] = host.to(device)
         return self.umma[mode]
 
@@ -213,6 +214,7 @@ class TensorProductConvLayer(nn.Module):
                                 nn.Linear(hidden_features, spec.weight_numel))
         self.batch_norm = BatchNorm(out_irreps) if batch_norm else None
         self._packed = None
+        self.conv_mode = 'fp32'      # stand-alone operator calls: 'fp32' | 'bf16' | 'bf16x3'
 
     def _load_from_state_dict(self, *a, **k):
         self._packed = None
@@ -232,7 +234,6 @@ class TensorProductConvLayer(nn.Module):
         if dev.type != 'cuda':
             raise RuntimeError('TensorProductConvLayer runs on CUDA only (no CPU fallback)')
         L = _lib.lib()
-        pk = self.packed(dev, self.fc[0].in_features, 0)
         E = edge_index.shape[1]
         out_nodes = int(out_nodes or node_attr.shape[0])
         ei = edge_index.to(torch.int32).contiguous()
@@ -242,11 +243,28 @@ class TensorProductConvLayer(nn.Module):
         if torch.is_tensor(edge_weight):
             ew = edge_weight.float().reshape(-1).contiguous()
         n_dev = torch.tensor([E], dtype=torch.int32, device=dev)
+        k1 = self.fc[0].in_features
+        use_tc = self.conv_mode != 'fp32' and self.tp.spec.faster and k1 % 3 == 0 and ew is None
+        if use_tc:
+            ns = k1 // 3
+            pk = self.packed(dev, ns, ns)
+            parts = [ea[:, i * ns:(i + 1) * ns].contiguous() for i in range(3)]
+            ident = torch.arange(E, dtype=torch.int32, device=dev)
+            ed = _lib.TpEdges(emb=ptr(parts[0]), p1=ptr(parts[1]), i1=ptr(ident), ld1=ns, p2=ptr(parts[2]), i2=ptr(ident), ld2=ns,
+                              x=ptr(x), gather=ei[1].data_ptr(), ldx=x.shape[1], sh=ptr(sh), agg=ei[0].data_ptr(), ew=None,
+                              n_edges_dev=ptr(n_dev), edge_cap=E)
+        else:
+            pk = self.packed(dev, k1, 0)
+            ed = _lib.TpEdges(emb=ptr(ea), p1=None, i1=None, ld1=0, p2=None, i2=None, ld2=0, x=ptr(x), gather=ei[1].data_ptr(),
+                              ldx=x.shape[1], sh=ptr(sh), agg=ei[0].data_ptr(), ew=ptr(ew), n_edges_dev=ptr(n_dev), edge_cap=E)
         f_out = pk.spec.f_out
         s = torch.zeros(out_nodes, f_out, device=dev)
-        ed = _lib.TpEdges(emb=ptr(ea), p1=None, i1=None, ld1=0, p2=None, i2=None, ld2=0, x=ptr(x), gather=ei[1].data_ptr(),
-                          ldx=x.shape[1], sh=ptr(sh), agg=ei[0].data_ptr(), ew=ptr(ew), n_edges_dev=ptr(n_dev), edge_cap=E)
-        _lib.check(L.ddp_tpconv_fp32(C.byref(pk.cdesc), C.byref(ed), ptr(s), _lib.stream_ptr()), 'ddp_tpconv_fp32')
+        if use_tc:
+            mode = 0 if self.conv_mode == 'bf16' else 1
+            img = pk.umma_image(self, mode, dev)
+            _lib.check(L.ddp_tpconv_umma(C.byref(pk.cdesc), ptr(img), mode, C.byref(ed), ptr(s), _lib.stream_ptr()), 'ddp_tpconv_umma')
+        else:
+            _lib.check(L.ddp_tpconv_fp32(C.byref(pk.cdesc), C.byref(ed), ptr(s), _lib.stream_ptr()), 'ddp_tpconv_fp32')
         deg = torch.zeros(out_nodes, dtype=torch.int32, device=dev)
         _lib.check(L.ddp_degree(ei[0].data_ptr(), ptr(n_dev), E, ptr(deg), _lib.stream_ptr()), 'ddp_degree')
         up = _lib.Update(sum=ptr(s), deg=ptr(deg), scale=ptr(pk.bn_scale), shift=ptr(pk.bn_shift), n_edges_dev=ptr(n_dev))

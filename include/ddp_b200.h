@@ -159,13 +159,18 @@ typedef struct {
  * specialise (lmax = 2, torsion FCTP).  sum: [n_out][f_out], zeroed by the caller. */
 int ddp_tpconv_fp32(const ddp_tpconv_t *conv, const ddp_tpconv_edges_t *edges, float *sum, void *stream);
 
-/* Tensor-core path (tcgen05 / TMEM, bf16 operands, fp32 accumulate).  `packed` is the weight image
- * produced by ddp_tpconv_pack_size / ddp_tpconv_pack.  mode: 0 = bf16 single pass, 1 = bf16x3 split
- * (fp32-grade products).  Only FasterTensorProduct-shaped convs (l <= 1 row groups). */
-int64_t ddp_tpconv_pack_size(const ddp_tpconv_t *conv_host_view, int32_t mode);
-int ddp_tpconv_pack(const ddp_tpconv_t *conv_host_view, const ddp_tp_group_t *groups_host,
-                    const float *w1_host, const float *b1_host, const float *w2_host, const float *b2_host,
-                    int32_t mode, void *packed_host);
+/* Tensor-core path (tcgen05 / TMEM, bf16 operands, fp32 accumulate), for FasterTensorProduct-shaped
+ * convs (l <= 1 row groups, k1 == hid == 3*ns).  mode: 0 = bf16 single pass, 1 = bf16x3 split
+ * (hi*hi + lo*hi + hi*lo: fp32-grade products).
+ * ddp_tpconv_pack builds the weight image the kernel streams with TMA bulk copies: UMMA core-matrix order,
+ * consumption order, biases folded into a constant-one K slot, path normalisation folded into the weights.
+ * All its pointers are HOST pointers (groups_host / ctab_host mirror conv->groups / conv->ctab; w1 [hid][k1],
+ * b1 [hid], w2 [w_numel][hid], b2 [w_numel] in nn.Linear layout).  packed_host == NULL returns the image size
+ * in bytes; otherwise 0 on success; negative DDP_E_* (DDP_E_UNSUPPORTED: not tensor-core eligible). */
+int64_t ddp_tpconv_pack(const ddp_tpconv_t *conv, const ddp_tp_group_t *groups_host, const float *ctab_host,
+                        const float *w1_host, const float *b1_host, const float *w2_host, const float *b2_host,
+                        int32_t mode, void *packed_host);
+/* `packed` is the device copy of that image.  Requires p1 and p2 (three 'ns'-wide edge-attribute parts). */
 int ddp_tpconv_umma(const ddp_tpconv_t *conv, const void *packed, int32_t mode,
                     const ddp_tpconv_edges_t *edges, float *sum, void *stream);
 
