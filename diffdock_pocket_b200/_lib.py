@@ -78,6 +78,7 @@ _SIGS = {
     'ddp_row_mlp': (i32, [vp, i32, i32, C.POINTER(MlpLayer), i32, vp, vp, i32, vp]),
     'ddp_tr_rot_head': (i32, [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
     'ddp_pose_update': (i32, [C.POINTER(Pose), C.POINTER(StepCoef), vp]),
+    'ddp_pose_update_dev': (i32, [C.POINTER(Pose), vp, vp]),
 }
 EXPORTS = sorted(_SIGS)
 _LIB = None

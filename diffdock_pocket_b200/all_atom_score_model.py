@@ -261,7 +261,7 @@ class TensorProductScoreModel(nn.Module):
         return P
 
     # ------------------------------------------------------------------------------------------ plan
-    def make_plan(self, data):
+    def make_plan(self, data, extra_step_floats=0):
         """Upload one collated batch and allocate all workspaces (no per-step allocation afterwards)."""
         P = self.packed()
         dev = P['device']
@@ -347,7 +347,8 @@ class TensorProductScoreModel(nn.Module):
             S = int(data['flexResidues'].edge_idx.shape[0])
         pl.S = S
         pl.n_scal = 4 * B + T + S
-        pl.scal = torch.zeros(pl.n_scal, **f32)
+        pl.step_in = torch.zeros(pl.n_scal + extra_step_floats, **f32)      # [per-graph scalars | caller's step inputs]
+        pl.scal = pl.step_in[:pl.n_scal]
         if not self.confidence_mode:
             ce = torch.stack([lb, torch.arange(pl.NL)])
             es['center'] = _EdgeSet(pl.NL, ns, sh_dim, dev)
@@ -402,7 +403,7 @@ class TensorProductScoreModel(nn.Module):
         return h
 
     # ------------------------------------------------------------------------------------------ scalars
-    def _host_scalars(self, pl, complex_t):
+    def _host_scalars(self, pl, complex_t, out=None):
         """t, sigma, score norms and cutoffs per graph, computed on the host exactly like the reference
         (all_atom_score_model.py:243-245, 263, 383-384, 405-407, 432-433) and staged in one pinned buffer."""
         B, T, S = pl.B, pl.T, pl.S
@@ -411,8 +412,7 @@ class TensorProductScoreModel(nn.Module):
             tr_s, rot_s, tor_s, sc_s = ct
         else:
             tr_s, rot_s, tor_s, sc_s = self.t_to_sigma(*ct)
-        # fresh pinned staging buffer per call: the caching host allocator keeps it alive until the async copy ran
-        h = torch.zeros(pl.n_scal, dtype=torch.float32).pin_memory()
+        h = torch.zeros(pl.n_scal, dtype=torch.float32) if out is None else out
         h[0:B] = ct[0]
         h[B:2 * B] = tr_s
         if not self.confidence_mode:
@@ -424,7 +424,10 @@ class TensorProductScoreModel(nn.Module):
         if S > 0 and not self.confidence_mode:
             es = sc_s[pl.sc_batch_h]
             h[4 * B + T:4 * B + T + S] = torch.sqrt(torch.tensor(torus.score_norm(es.numpy()))).float()
-        pl.scal.copy_(h, non_blocking=True)
+        if out is None:
+            # fresh pinned staging buffer per call: the caching host allocator keeps it alive until the async copy ran
+            pl.scal.copy_(h.pin_memory(), non_blocking=True)
+        return h
 
     # ------------------------------------------------------------------------------------------ forward
     def _conv(self, L, st, layer, pk, es, flip, x, p1, i1_row, p2, i2_row, sum_buf, ew=None):
@@ -453,12 +456,16 @@ class TensorProductScoreModel(nn.Module):
 
     def run_plan(self, pl, complex_t, return_layers=False):
         """Forward on a resident plan.  Returns device tensors; performs no host synchronisation."""
+        self._host_scalars(pl, complex_t)
+        return self.launch_plan(pl, return_layers)
+
+    def launch_plan(self, pl, return_layers=False):
+        """Kernel launches only (per-graph scalars already staged in ``pl.scal``): CUDA-graph capturable."""
         P = self.packed()
         L = _lib.lib()
         st = _lib.stream_ptr()
         B, ns, F = pl.B, self.ns, pl.F
         es = pl.es
-        self._host_scalars(pl, complex_t)
         t_dev, tr_sigma, so3n, cutoff = pl.scal[0:B], pl.scal[B:2 * B], pl.scal[2 * B:3 * B], pl.scal[3 * B:4 * B]
         chk = _lib.check
         names = P['proj_names']

@@ -90,7 +90,8 @@ constexpr int kPoseThreads = 64;
 constexpr int kMaxLigAtoms = 512;
 
 __global__ void __launch_bounds__(kPoseThreads)
-pose_update_kernel(ddp_pose_t P, ddp_step_coef_t C) {
+pose_update_kernel(ddp_pose_t P, ddp_step_coef_t C_host, const ddp_step_coef_t *__restrict__ C_dev) {
+    const ddp_step_coef_t C = C_dev ? *C_dev : C_host;
     __shared__ float s_flex[kMaxLigAtoms * 3];
     __shared__ float s_rigid[kMaxLigAtoms * 3];
     __shared__ double s_R[9];
@@ -218,7 +219,20 @@ extern "C" int ddp_pose_update(const ddp_pose_t *pose, const ddp_step_coef_t *co
     if (P.tor_ptr && (!P.tor_bonds || !P.mask_rotate || !P.mask_ptr || !P.tor_score)) return DDP_E_ARG;
     if (P.sc_ptr && (!P.sc_bonds || !P.sc_sub_ptr || !P.sc_sub || !P.sc_score || !P.atom_pos)) return DDP_E_ARG;
     if (P.n_samples <= 0) return 0;
-    pose_update_kernel<<<P.n_samples, kPoseThreads, 0, (cudaStream_t)stream>>>(P, *coef);
+    pose_update_kernel<<<P.n_samples, kPoseThreads, 0, (cudaStream_t)stream>>>(P, *coef, nullptr);
+    DDP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ddp_pose_update_dev(const ddp_pose_t *pose, const ddp_step_coef_t *coef_dev, void *stream) {
+    if (!pose || !coef_dev) return DDP_E_ARG;
+    const ddp_pose_t &P = *pose;
+    if (!P.lig_pos || !P.lig_ptr || !P.tr_score || !P.rot_score) return DDP_E_ARG;
+    if (P.tor_ptr && (!P.tor_bonds || !P.mask_rotate || !P.mask_ptr || !P.tor_score)) return DDP_E_ARG;
+    if (P.sc_ptr && (!P.sc_bonds || !P.sc_sub_ptr || !P.sc_sub || !P.sc_score || !P.atom_pos)) return DDP_E_ARG;
+    if (P.n_samples <= 0) return 0;
+    ddp_step_coef_t dummy = {0, 0, 0, 0, 0, 0, 0, 0};
+    pose_update_kernel<<<P.n_samples, kPoseThreads, 0, (cudaStream_t)stream>>>(P, dummy, coef_dev);
     DDP_LAUNCH_CHECK();
     return 0;
 }

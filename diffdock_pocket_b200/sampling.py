@@ -94,13 +94,75 @@ def step_coefficients(t_idx, inference_steps, schedules, t_to_sigma, model_args,
     return t, coef
 
 
+class StepRunner:
+    """One resident mini-batch: plan + pose state + (optionally) the captured CUDA graph of one whole
+    reverse-diffusion step (score-model forward + fused pose update).  Per step the host stages ONE pinned row
+    [per-graph scalars | 8 step coefficients | tr_z | rot_z | tor_z | sc_z], copies it to the device with one
+    async H2D and replays the graph: no other host work, no synchronisation."""
+
+    def __init__(self, model, data_sub, flexible_sidechains, no_torsion, use_graph=True):
+        b = len(data_sub)
+        self.model, self.b = model, b
+        n_tor = 0 if no_torsion else sum(int(g['ligand'].edge_mask.sum()) for g in data_sub)
+        n_sc = sum(int(g['flexResidues'].edge_idx.shape[0]) for g in data_sub
+                   if flexible_sidechains and 'flexResidues' in g and 'edge_idx' in g['flexResidues'])
+        self.n_extra = 8 + 6 * b + n_tor + n_sc
+        self.pl = model.make_plan(Batch.from_data_list(data_sub), extra_step_floats=self.n_extra)
+        pl = self.pl
+        self.ps = PoseState(data_sub, pl.device, lig_pos=pl.lig_pos, atom_pos=pl.atom_pos,
+                            flexible_sidechains=flexible_sidechains, no_torsion=no_torsion)
+        self.T, self.S = self.ps.T, self.ps.S
+        o = pl.n_scal
+        x = pl.step_in
+        self.coef_dev = x[o:o + 8]
+        o += 8
+        self.z = (x[o:o + 3 * b], x[o + 3 * b:o + 6 * b], x[o + 6 * b:o + 6 * b + self.T],
+                  x[o + 6 * b + self.T:o + 6 * b + self.T + self.S])
+        self.use_sc = flexible_sidechains and self.ps.has_sc
+        assert (self.T, self.S) == (n_tor, n_sc)
+        self.graph = None
+        self.use_graph = use_graph
+        self.out = None
+        self.calls = 0
+
+    def _launch(self):
+        tr, rot, tor, sc = self.model.launch_plan(self.pl)
+        self.out = (tr, rot, tor, sc)
+        self.ps.update(self.coef_dev, tr, rot, tor if self.ps.has_tor else None, sc if self.use_sc else None,
+                       tr_z=self.z[0], rot_z=self.z[1], tor_z=self.z[2] if self.ps.has_tor else None,
+                       sc_z=self.z[3] if self.use_sc else None)
+
+    def stage(self, t4, coef, noise_row=None):
+        """Host side of one step: scalars + coefficients + this batch's noise -> one pinned row -> one H2D."""
+        pl, b = self.pl, self.b
+        row = torch.zeros(pl.n_scal + self.n_extra, dtype=torch.float32).pin_memory()
+        ct = {k: torch.full((b,), float(v)) for k, v in zip(('tr', 'rot', 'tor', 'sc_tor'), t4)}
+        self.model._host_scalars(pl, ct, out=row[:pl.n_scal])
+        row[pl.n_scal:pl.n_scal + 8] = torch.tensor([float(c) for c in coef])
+        if noise_row is not None:
+            row[pl.n_scal + 8:] = noise_row
+        pl.step_in.copy_(row, non_blocking=True)
+
+    def step(self, t4, coef, noise_row=None):
+        self.stage(t4, coef, noise_row)
+        self.calls += 1
+        if not self.use_graph or self.calls == 1:
+            return self._launch()                # first step runs eagerly (lazy kernel attributes, allocator warm-up)
+        if self.graph is None:                   # second step: capture (does not execute), then replay from here on
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._launch()
+        self.graph.replay()
+
+
 def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_schedule, sidechain_tor_schedule, device,
              t_to_sigma, model_args, no_random=False, ode=False, visualization_list=None, sidechain_visualization_list=None,
              confidence_model=None, filtering_data_list=None, filtering_model_args=None, asyncronous_noise_schedule=False,
              t_schedule=None, batch_size=32, no_final_step_noise=False, pivot=None, return_full_trajectory=False,
              svgd_weight=0.0, svgd_repulsive_weight=1.0, svgd_only=False, svgd_rot_rel_weight=1.0, svgd_tor_rel_weight=1.0,
              svgd_sidechain_tor_rel_weight=1.0, temp_sampling=1.0, temp_psi=0.0, temp_sigma_data=0.5,
-             flexible_sidechains=None, max_steps=None, trace=None):
+             flexible_sidechains=None, max_steps=None, trace=None, use_graph=True):
     if svgd_weight > 0 or pivot is not None or asyncronous_noise_schedule:
         raise NotImplementedError('SVGD / pivot / asynchronous schedules are outside the accelerated path')
     flexible_sidechains = model_args.flexible_sidechains if flexible_sidechains is None else flexible_sidechains
@@ -117,24 +179,19 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
     trajectory, sidechain_trajectory = [], []
     schedules = (tr_schedule, rot_schedule, tor_schedule, sidechain_tor_schedule)
 
-    # one resident plan + pose state per mini-batch
+    # one resident plan + pose state (+ captured step graph) per mini-batch
     chunks = [list(range(i, min(i + batch_size, N))) for i in range(0, N, batch_size)]
-    plans, poses = [], []
     with torch.no_grad():
-        for idx in chunks:
-            sub = [data_list[i] for i in idx]
-            pl = model.make_plan(Batch.from_data_list(sub))
-            plans.append(pl)
-            poses.append(PoseState(sub, pl.device, lig_pos=pl.lig_pos, atom_pos=pl.atom_pos,
-                                   flexible_sidechains=flexible_sidechains, no_torsion=ma.no_torsion))
+        runners = [StepRunner(model, [data_list[i] for i in idx], flexible_sidechains, ma.no_torsion, use_graph=use_graph and trace is None)
+                   for idx in chunks]
+    poses = [r.ps for r in runners]
     T_tot = sum(p.T for p in poses)
     S_tot = sum(p.S for p in poses)
-    use_sc = flexible_sidechains and S_tot > 0
     n_steps = inference_steps if max_steps is None else min(max_steps, inference_steps)
     M = 6 * N + T_tot + S_tot
     # Noise for all steps is drawn up front, in the reference's order (per step: tr_z, rot_z, tor_z,
-    # sidechain_tor_z; utils/sampling.py:136-163) -- nothing else consumes the CPU generator in between, so
-    # the stream is identical -- and uploaded with a single H2D copy.
+    # sidechain_tor_z; utils/sampling.py:136-163) -- nothing else consumes the CPU generator in between, so the
+    # stream is identical; each step's slice travels to the device inside that step's single H2D copy.
     noise_host = torch.zeros(max(n_steps, 1), M)
     if not ode:
         for t_idx in range(n_steps):
@@ -146,7 +203,6 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
                 noise_host[t_idx, 6 * N:6 * N + T_tot] = draw((T_tot,))
             if flexible_sidechains:
                 noise_host[t_idx, 6 * N + T_tot:] = draw((S_tot,))
-    noise_all = noise_host.pin_memory().to(plans[0].device, non_blocking=True)
 
     with torch.no_grad():
         for t_idx in range(n_steps):
@@ -158,23 +214,17 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
                 trajectory.append(np.asarray([g['ligand'].pos.cpu().numpy() for g in data_list]))
                 sidechain_trajectory.append(np.asarray([]) if no_sidechains_in_batch or not flexible_sidechains else np.asarray(
                     [g['atom'].pos.cpu().numpy()[g['flexResidues'].subcomponents.unique().cpu().numpy()] for g in data_list]))
-            noise_dev = noise_all[t_idx]
+            z = noise_host[t_idx]
             s0 = t0 = c0 = 0
             step_scores = []
-            for idx, pl, ps in zip(chunks, plans, poses):
+            for idx, r in zip(chunks, runners):
                 b = len(idx)
-                ct = {'tr': torch.full((b,), float(t[0])), 'rot': torch.full((b,), float(t[1])),
-                      'tor': torch.full((b,), float(t[2])), 'sc_tor': torch.full((b,), float(t[3]))}
-                tr_score, rot_score, tor_score, sc_score = model.run_plan(pl, ct)
+                row = torch.cat([z[3 * s0:3 * (s0 + b)], z[3 * N + 3 * s0:3 * N + 3 * (s0 + b)], z[6 * N + t0:6 * N + t0 + r.T],
+                                 z[6 * N + T_tot + c0:6 * N + T_tot + c0 + r.S]])
+                r.step(t, coef, row)
                 if trace is not None:
-                    step_scores.append((tr_score.clone(), rot_score.clone(), tor_score.clone(), sc_score.clone()))
-                z = None if ode else noise_dev
-                ps.update(coef, tr_score, rot_score, tor_score if ps.has_tor else None, sc_score if (ps.has_sc and use_sc) else None,
-                          tr_z=z[3 * s0:3 * (s0 + b)] if z is not None else None,
-                          rot_z=z[3 * N + 3 * s0:3 * N + 3 * (s0 + b)] if z is not None else None,
-                          tor_z=z[6 * N + t0:6 * N + t0 + ps.T] if z is not None and ps.has_tor else None,
-                          sc_z=z[6 * N + T_tot + c0:6 * N + T_tot + c0 + ps.S] if z is not None and ps.has_sc and use_sc else None)
-                s0, t0, c0 = s0 + b, t0 + ps.T, c0 + ps.S
+                    step_scores.append(tuple(o.clone() for o in r.out))
+                s0, t0, c0 = s0 + b, t0 + r.T, c0 + r.S
             if trace is not None:
                 trace.append(tuple(torch.cat([s[k] for s in step_scores]).cpu() for k in range(4)))
             if visualization_list is not None or sidechain_visualization_list is not None:

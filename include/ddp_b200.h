@@ -241,6 +241,9 @@ typedef struct {
     const float *tr_z, *rot_z, *tor_z, *sc_z;
 } ddp_pose_t;
 int ddp_pose_update(const ddp_pose_t *pose, const ddp_step_coef_t *coef, void *stream);
+/* Same, with the step coefficients read from DEVICE memory (8 floats): lets the whole step be replayed as a
+ * CUDA graph while the per-step scalars change. */
+int ddp_pose_update_dev(const ddp_pose_t *pose, const ddp_step_coef_t *coef_dev, void *stream);
 
 #ifdef __cplusplus
 }

@@ -138,13 +138,14 @@ def test_forward_drop_in_call_and_confidence():
         conf = c(copy.deepcopy(b))
         want = oc(copy.deepcopy(b))
     assert T.rel_err(conf, want) < 1e-4 and T.rel_err(conf, gold['confidence']) < 1e-4
-    b = T.batch_at(dl[:1], 0.3)                                        # single un-batched graph goes through forward()
+    b = T.batch_at(dl[:1], 0.3)                                        # single graph goes through forward()
+    b2 = copy.deepcopy(b)
     with torch.no_grad():
-        got = m(copy.deepcopy(b))
+        got = m(b2)
         want = om(copy.deepcopy(b))
     for g_, w_ in zip(got, want):
         assert T.rel_err(g_, w_) < 1e-4
-    assert b['atom', 'atom'].edge_index is not None
+    assert torch.equal(b2['atom', 'atom'].edge_index.cpu(), om._debug['aa'])      # side effect of all_atom_score_model.py:530
 
 
 def test_forward_apo_graph_and_empty_cross_edges():
