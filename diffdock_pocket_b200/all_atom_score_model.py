@@ -161,9 +161,10 @@ class TensorProductScoreModel(nn.Module):
     def _tor_conv(last, tor_sh, ns, dropout, batch_norm):
         conv = TensorProductConvLayer(last, tor_sh, f'{ns}x0o + {ns}x0e', 3 * ns, residual=False, dropout=dropout,
                                       batch_norm=batch_norm)
-        # only the 1o part of sh_tor is materialised (ddp_tor_edge_sh); valid while node irreps have l <= 1
-        spec = tpmod.fctp_spec(last, tor_sh, f'{ns}x0o + {ns}x0e', sh_keep=[0])
+        # only the 1o part of sh_tor is materialised, as [1 | 1o] (ddp_tor_edge_sh); valid while node irreps have l <= 1
+        spec = tpmod.fctp_spec(last, tor_sh, f'{ns}x0o + {ns}x0e', sh_keep=[0], sh_base=1)
         assert spec.weight_numel == conv.tp.weight_numel
+        spec.tc_eligible = all(l <= 1 for _, l, _ in tpmod.parse_irreps(last))
         conv.tp = _TP(spec)
         return conv
 
@@ -396,7 +397,7 @@ class TensorProductScoreModel(nn.Module):
         h.batch = bond_batch.to(**i32)
         h.mid, h.y2, h.attr = torch.zeros(n, 3, **f32), torch.zeros(n, 5, **f32), torch.zeros(n, self.ns, **f32)
         h.es = _EdgeSet(n * min(32, max_seg), self.ns, self.sh_dim, dev, with_slab=(n, min(32, max_seg)))
-        h.sh_tor = torch.zeros(h.es.cap, 3, **f32)
+        h.sh_tor = torch.zeros(h.es.cap, 4, **f32)
         h.deg = torch.zeros(n, **i32)
         h.sum = torch.zeros(n, 2 * self.ns, **f32)
         h.feat = torch.zeros(n, 2 * self.ns, **f32)
@@ -443,7 +444,7 @@ class TensorProductScoreModel(nn.Module):
         if prof is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        if self.conv_mode != 'fp32' and pk.spec.faster and p1 is not None and p2 is not None:
+        if self.conv_mode != 'fp32' and pk.spec.tc_eligible and p1 is not None and p2 is not None:
             mode = 0 if self.conv_mode == 'bf16' else 1
             img = pk.umma_image(layer, mode, x.device)
             _lib.check(L.ddp_tpconv_umma(C.byref(pk.cdesc), ptr(img), mode, C.byref(ed), ptr(sum_buf), st), 'ddp_tpconv_umma')
@@ -451,7 +452,7 @@ class TensorProductScoreModel(nn.Module):
             _lib.check(L.ddp_tpconv_fp32(C.byref(pk.cdesc), C.byref(ed), ptr(sum_buf), st), 'ddp_tpconv_fp32')
         if prof is not None:
             ev1.record()
-            if p1 is not None and p2 is not None and pk.spec.faster:
+            if p1 is not None and p2 is not None and pk.spec.tc_eligible:
                 prof.append((ev0, ev1, pk.spec.weight_numel, es, self.ns))
 
     def run_plan(self, pl, complex_t, return_layers=False):

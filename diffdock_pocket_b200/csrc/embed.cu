@@ -226,7 +226,7 @@ __global__ void tor_edge_sh_kernel(const float *__restrict__ sh, int sh_dim, con
 #pragma unroll
                 for (int k = 0; k < 3; ++k) o[k] = fmaf(sc[(i * 5 + j) * 3 + k], ab, o[k]);
             }
-        sh_tor[3 * (size_t)e] = o[0]; sh_tor[3 * (size_t)e + 1] = o[1]; sh_tor[3 * (size_t)e + 2] = o[2];
+        *reinterpret_cast<float4 *>(sh_tor + 4 * (size_t)e) = make_float4(1.f, o[0], o[1], o[2]);
     }
 }
 

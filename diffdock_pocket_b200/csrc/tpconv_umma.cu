@@ -35,7 +35,8 @@ struct TileDesc {
     uint8_t type;         // 0 scalar block (NS outputs), 1 vector block (NV x 3 outputs)
     uint8_t n_rows;       // basis rows covered (rest is zero padding)
     uint16_t out_off;     // first output feature of the block
-    uint8_t first, last;  // first / last tile of its block
+    uint8_t first;        // first tile of its block (bit 0); bit 1: swap the last input irrep into slot 0 first
+    uint8_t last;         // last tile of its block
     uint8_t row_kind[MAX_ROWS];  // 0 x*s0, 1 dot(xv,s1), 2 x*s1, 3 xv*s0, 4 cross(xv,s1), 255 padding
     uint8_t row_x[MAX_ROWS];     // offset of the row's input feature(s)
 };
@@ -144,11 +145,14 @@ struct Cfg {
     static constexpr int NCOL_V = ROWS_V * NV;
     static constexpr int NCOL_MAX = (NCOL_S > N1 ? NCOL_S : N1);
     static constexpr int STAGE_K = SPLIT ? 16 : 32;
-    static constexpr int STAGES = SPLIT ? 2 : (KS == 64 ? 5 : 6);
+    static constexpr int STAGES = SPLIT ? 4 : (KS == 64 ? 7 : 10);
     static constexpr int STAGE_BYTES = NCOL_MAX * STAGE_K * 2 * (SPLIT ? 2 : 1);
     static constexpr int A_BYTES = TILE_M * KP * 2;         // one bf16 A image
     static constexpr int F_MAX = 2 * NS + 6 * NV;
-    static constexpr int XLD = F_MAX + 1;                   // odd row stride: conflict-free per-thread rows
+    // Only NS + 6 NV gathered features are resident at a time: blocks 0e / 1o read (x0e, x1o, x1e), blocks
+    // 1e / 0o read (x1o, x1e, x0o); x0o is swapped into x0e's slots at the first tile that needs it.
+    static constexpr int X_SLOTS = NS + 6 * NV;
+    static constexpr int XLD = X_SLOTS + 1;                 // odd row stride: conflict-free per-thread rows
     static constexpr int X_BYTES = TILE_M * XLD * 4;
     static constexpr int MAX_TILES = 64;
     static constexpr size_t SMEM = 1024 + (size_t)A_BYTES * (SPLIT ? 2 : 1) + X_BYTES + (size_t)STAGES * STAGE_BYTES +
@@ -277,6 +281,7 @@ tpconv_umma_kernel(const uint8_t *__restrict__ image, ddp_tpconv_edges_t ed, int
             float s0 = 0.f, s1x = 0.f, s1y = 0.f, s1z = 0.f;
             // ---- stage the A operand [emb | p1 | p2] (bf16, constant one in slot NS of source 0) and x ----
             const float *srcs[3] = {nullptr, nullptr, nullptr};
+            const float *xg = nullptr;
             if (valid) {
                 agg = ed.agg[e];
                 const float4 sh4 = *reinterpret_cast<const float4 *>(ed.sh + (size_t)e * 4);
@@ -284,18 +289,34 @@ tpconv_umma_kernel(const uint8_t *__restrict__ image, ddp_tpconv_edges_t ed, int
                 srcs[0] = ed.emb + (size_t)e * NS;
                 if (ed.p1) srcs[1] = ed.p1 + (size_t)ed.i1[e] * ed.ld1;
                 if (ed.p2) srcs[2] = ed.p2 + (size_t)ed.i2[e] * ed.ld2;
+                xg = ed.x + (size_t)ed.gather[e] * ed.ldx;
             }
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
+                const float *sp = srcs[s];
+                const bool v4 = (s == 0) ? (NS % 4 == 0) : (((s == 1 ? ed.ld1 : ed.ld2) & 3) == 0);
 #pragma unroll
                 for (int c8 = 0; c8 < KS / 8; ++c8) {
                     float v[8];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int j = c8 * 8 + q;
-                        v[q] = (srcs[s] != nullptr && j < NS) ? __ldg(srcs[s] + j) : 0.f;
-                        if (s == 0 && j == NS) v[q] = 1.f;
+                    for (int q = 0; q < 8; ++q) v[q] = 0.f;
+                    if (sp != nullptr) {
+                        if (v4 && NS % 4 == 0) {
+                            if (c8 * 8 < NS) {
+                                const float4 f = __ldg(reinterpret_cast<const float4 *>(sp + c8 * 8));
+                                v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+                            }
+                            if (c8 * 8 + 4 < NS) {
+                                const float4 f = __ldg(reinterpret_cast<const float4 *>(sp + c8 * 8 + 4));
+                                v[4] = f.x; v[5] = f.y; v[6] = f.z; v[7] = f.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q)
+                                if (c8 * 8 + q < NS) v[q] = __ldg(sp + c8 * 8 + q);
+                        }
                     }
+                    if (s == 0 && NS / 8 == c8) v[NS % 8] = 1.f;
                     uint4 hi;
                     hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
                     hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
@@ -313,8 +334,18 @@ tpconv_umma_kernel(const uint8_t *__restrict__ image, ddp_tpconv_edges_t ed, int
                 }
             }
             {
-                const float *xg = valid ? ed.x + (size_t)ed.gather[e] * ed.ldx : nullptr;
-                for (int c = 0; c < f_in; ++c) xrow[c] = valid ? __ldg(xg + c) : 0.f;
+                // first X_SLOTS gathered features (the rest is swapped in later, see TileDesc::first bit 1)
+                const int n0 = f_in < C::X_SLOTS ? f_in : C::X_SLOTS;
+                if (valid && (ed.ldx & 3) == 0) {
+                    int c = 0;
+                    for (; c + 4 <= n0; c += 4) {
+                        const float4 f = __ldg(reinterpret_cast<const float4 *>(xg + c));
+                        xrow[c] = f.x; xrow[c + 1] = f.y; xrow[c + 2] = f.z; xrow[c + 3] = f.w;
+                    }
+                    for (; c < n0; ++c) xrow[c] = __ldg(xg + c);
+                } else {
+                    for (int c = 0; c < n0; ++c) xrow[c] = valid ? __ldg(xg + c) : 0.f;
+                }
             }
             fence_proxy_async();
             mbar_arrive(a_ready);
@@ -359,9 +390,12 @@ tpconv_umma_kernel(const uint8_t *__restrict__ image, ddp_tpconv_edges_t ed, int
                 const TileDesc &td = tiles[t];
                 const int buf = (t + 1) & 1;
                 const uint32_t taddr = tmem_base + lane_base + (uint32_t)buf * 256u;
-                if (td.first) {
+                if (td.first & 1) {
 #pragma unroll
                     for (int o = 0; o < NS; ++o) acc[o] = 0.f;
+                }
+                if (td.first & 2) {      // swap x[X_SLOTS..f_in) into the slots of the no longer needed first irrep
+                    for (int c = C::X_SLOTS; c < f_in; ++c) xrow[c - C::X_SLOTS] = valid ? __ldg(xg + c) : 0.f;
                 }
                 if (td.type == 0) {
                     float b[C::ROWS_S];
@@ -527,6 +561,25 @@ static int build_plan(const ddp_tpconv_t &c, const ddp_tp_group_t *groups, const
     }
     h.n_tiles = (int)P.tiles.size();
     if (h.n_tiles > 64) return DDP_E_UNSUPPORTED;
+    // Only x_slots gathered features are resident in shared memory; features [x_slots, f_in) replace the first
+    // f_in - x_slots ones from the first tile that reads them (kernel: TileDesc::first bit 1).
+    const int x_slots = ns + 6 * nv;
+    if (c.f_in > x_slots) {
+        const int lost = c.f_in - x_slots;
+        bool swapped = false;
+        for (auto &td : P.tiles) {
+            const int per = td.type ? rows_v : rows_s;
+            bool needs = false;
+            for (int rr = 0; rr < per; ++rr)
+                if (td.row_kind[rr] != 255 && td.row_x[rr] >= x_slots) needs = true;
+            if (needs && !swapped) { td.first |= 2; swapped = true; }
+            for (int rr = 0; rr < per; ++rr) {
+                if (td.row_kind[rr] == 255) continue;
+                if (td.row_x[rr] >= x_slots) td.row_x[rr] = (uint8_t)(td.row_x[rr] - x_slots);
+                else if (swapped && td.row_x[rr] < lost) return DDP_E_UNSUPPORTED;   // would read an overwritten slot
+            }
+        }
+    }
     int64_t off = (sizeof(Header) + 127) / 128 * 128;
     h.tiles_off = off;
     off += (int64_t)((h.n_tiles * sizeof(TileDesc) + 127) / 128 * 128);

@@ -94,7 +94,8 @@ class TpSpec:
         self.groups = []          # dicts with the ddp_tp_group_t fields
         self.ctab = []            # flat float list
         self.weight_numel = 0
-        self.faster = False       # FasterTensorProduct-shaped (tensor-core kernel eligible)
+        self.faster = False       # FasterTensorProduct-shaped
+        self.tc_eligible = False  # candidate for the tensor-core kernel (l <= 1 scalar / vector row groups)
 
     def add(self, C, x_off, mul_in, sh_off, w_off, out_off, mul_out):
         d1, d2, do = C.shape
@@ -140,6 +141,7 @@ def faster_tp_spec(in_irreps, out_irreps):
             '0o': [('1e', dot, 1), ('0o', one, 0)]}
     spec = TpSpec(in_irreps, 4, out_irreps)
     spec.faster = True
+    spec.tc_eligible = True
     w = 0
     for key in ('0e', '1o', '1e', '0o'):                         # layers.py:26-31
         in_k = sum(im[r[0]] for r in rows[key])
@@ -156,7 +158,7 @@ def faster_tp_spec(in_irreps, out_irreps):
     return spec
 
 
-def fctp_spec(in_irreps, sh_irreps, out_irreps, sh_keep=None):
+def fctp_spec(in_irreps, sh_irreps, out_irreps, sh_keep=None, sh_base=0):
     """e3nn FullyConnectedTensorProduct (mode uvw, mul2 == 1).  ``sh_keep``: optional list of sh irrep
     indices whose components are actually supplied (others must be unused by every instruction)."""
     in_irreps, sh_irreps, out_irreps = parse_irreps(in_irreps), parse_irreps(sh_irreps), parse_irreps(out_irreps)
@@ -170,7 +172,7 @@ def fctp_spec(in_irreps, sh_irreps, out_irreps, sh_keep=None):
     if sh_keep is None:
         sh_off, sh_dim = sh_off_full, irreps_dim(sh_irreps)
     else:
-        sh_off, s = {}, 0
+        sh_off, s = {}, sh_base
         for k in sh_keep:
             sh_off[k] = s
             s += 2 * sh_irreps[k][1] + 1

@@ -197,7 +197,8 @@ int ddp_segment_mean(const float *src, const int32_t *idx, const int32_t *ptr, i
 int ddp_bond_geometry(const float *pos, const int32_t *bonds, int32_t n_bonds, const float *x, int32_t ldx, int32_t ns,
                       float *mid, float *y2, float *attr, void *stream);
 
-/* sh_tor[e][0:3] = 1o component of FullTensorProduct(sh_edge (1x0e+1x1o), Y2[bond])  (:395, :419). */
+/* sh_tor[e] = [1, 1o component of FullTensorProduct(sh_edge (1x0e+1x1o), Y2[bond])]  (:395, :419); the leading 1
+ * pads the row to the [s0 | s1] layout of the conv kernels (4 floats per edge). */
 int ddp_tor_edge_sh(const float *sh, int32_t sh_dim, const float *y2, const float *c121 /* [3][5][3], sqrt(3) folded */,
                     const int32_t *edge, const int32_t *n_edges_dev, int32_t edge_cap, float *sh_tor, void *stream);
 

@@ -75,9 +75,13 @@ def test_packed_image_replays_conv(ns, nv, layer, mode):
     H = np.maximum(A.astype(np.float64) @ W1.astype(np.float64).T, 0)          # [n_e, n1]
     assert np.allclose(H[:, 3 * ns], 1.0) and np.all(H[:, 3 * ns + 1:] == 0)
     out = np.zeros((n_e, spec.f_out))
-    xs, s0, s1 = x.numpy().astype(np.float64), sh[:, 0].numpy().astype(np.float64), sh[:, 1:].numpy().astype(np.float64)
+    s0, s1 = sh[:, 0].numpy().astype(np.float64), sh[:, 1:].numpy().astype(np.float64)
+    x_slots = ns + 6 * nv
+    xs = x.numpy().astype(np.float64)[:, :x_slots].copy()              # resident slots of the kernel's x tile
     for t in range(n_tiles):
         n_cols, typ, n_rows, out_off, first, last = struct.unpack_from('<HBBHBB', buf, tiles_off + 40 * t)
+        if first & 2:                                                    # swap the last irrep into the first slots
+            xs[:, :spec.f_in - x_slots] = x.numpy().astype(np.float64)[:, x_slots:]
         kinds = np.frombuffer(buf, dtype=np.uint8, count=16, offset=tiles_off + 40 * t + 8)
         xo = np.frombuffer(buf, dtype=np.uint8, count=16, offset=tiles_off + 40 * t + 24)
         W2, off = _decode_operand(buf, off, n_cols, kp, stage_k, mode)
