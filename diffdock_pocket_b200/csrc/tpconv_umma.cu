@@ -20,6 +20,7 @@
 #include <cuda_bf16.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "ddp_common.cuh"
@@ -27,19 +28,20 @@
 namespace umma {
 
 constexpr int TILE_M = 128;
-constexpr int MAX_ROWS = 16;
 constexpr uint32_t MAGIC = 0x44445055u;  // "DDPU"
 
 struct TileDesc {
-    uint16_t n_cols;      // UMMA N of this weight tile (multiple of 16)
-    uint8_t type;         // 0 scalar block (NS outputs), 1 vector block (NV x 3 outputs)
-    uint8_t n_rows;       // basis rows covered (rest is zero padding)
+    uint16_t n_cols;      // UMMA N of this weight tile (multiple of 16): n_rows * mul_out rounded up, rest zero padding
+    uint8_t kind;         // basis of every row of the tile: 0 x*s0, 1 dot(xv,s1), 2 x*s1, 3 xv*s0, 4 cross(xv,s1)
+    uint8_t n_rows;       // basis rows covered
     uint16_t out_off;     // first output feature of the block
-    uint8_t first;        // first tile of its block (bit 0); bit 1: swap the last input irrep into slot 0 first
-    uint8_t last;         // last tile of its block
-    uint8_t row_kind[MAX_ROWS];  // 0 x*s0, 1 dot(xv,s1), 2 x*s1, 3 xv*s0, 4 cross(xv,s1), 255 padding
-    uint8_t row_x[MAX_ROWS];     // offset of the row's input feature(s)
+    uint8_t flags;        // bit 0: first tile of its block; bit 1: swap the last input irrep into slot 0 first; bit 2: last tile
+    uint8_t pad0;
+    uint16_t x_off;       // slot of the first input feature of row 0 (row rr reads x_off + rr * (kind 0/2 ? 1 : 3))
+    uint16_t pad1;
+    uint32_t pad2;
 };
+static_assert(sizeof(TileDesc) == 16, "TileDesc is read as one 16-byte word");
 
 struct Header {
     uint32_t magic;
@@ -126,7 +128,43 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ void red_add(float *p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+// Asynchronous TMEM load of 16 columns (this thread's lane): the registers are valid only after tmem_wait16(v).
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+// tcgen05.wait::ld with the destination registers as in/out operands, so no consumer can be scheduled above it
+__device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ void red_add_v2(float *p, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// sum[0..N) += acc[0..N): 16-byte vector reductions when the row is 16-byte aligned, 8-byte ones otherwise (N even,
+// rows always 8-byte aligned: f_out and every block offset are even)
+template <int N, int NA>
+__device__ __forceinline__ void red_row(float *dst, const float (&acc)[NA]) {
+    static_assert(N % 2 == 0 && N <= NA, "even block widths only");
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+        for (int o = 0; o + 4 <= N; o += 4) red_add_v4(dst + o, acc[o], acc[o + 1], acc[o + 2], acc[o + 3]);
+        if (N % 4) red_add_v2(dst + N - 2, acc[N - 2], acc[N - 1]);
+    } else {
+#pragma unroll
+        for (int o = 0; o < N; o += 2) red_add_v2(dst + o, acc[o], acc[o + 1]);
+    }
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
@@ -384,86 +422,100 @@ tpconv_umma_kernel(const uint8_t *__restrict__ image, ddp_tpconv_edges_t ed, int
             mbar_arrive(&tmem_empty[0]);
 
             // ---- weight tiles: TMEM accumulator x tensor-product basis -> per-edge output registers ----
+            // Every tile has one basis kind, so the basis rows are straight-line shared-memory reads; the accumulator
+            // is read 16 columns at a time with the next tcgen05.ld in flight under the FMAs of the current chunk.
             float acc[NS];
 #pragma unroll 1
             for (int t = 0; t < n_tiles; ++t) {
-                const TileDesc &td = tiles[t];
+                const uint4 tdw = *reinterpret_cast<const uint4 *>(&tiles[t]);
+                const int n_cols = (int)(tdw.x & 0xffffu), kind = (int)((tdw.x >> 16) & 0xffu), n_rows = (int)(tdw.x >> 24);
+                const int out_off = (int)(tdw.y & 0xffffu), flags = (int)((tdw.y >> 16) & 0xffu);
+                const float *xt = xrow + (tdw.z & 0xffffu);
+                const int n_chunks = n_cols >> 4;
                 const int buf = (t + 1) & 1;
                 const uint32_t taddr = tmem_base + lane_base + (uint32_t)buf * 256u;
-                if (td.first & 1) {
+                if (flags & 1) {
 #pragma unroll
                     for (int o = 0; o < NS; ++o) acc[o] = 0.f;
                 }
-                if (td.first & 2) {      // swap x[X_SLOTS..f_in) into the slots of the no longer needed first irrep
+                if (flags & 2) {         // swap x[X_SLOTS..f_in) into the slots of the no longer needed first irrep
                     for (int c = C::X_SLOTS; c < f_in; ++c) xrow[c - C::X_SLOTS] = valid ? __ldg(xg + c) : 0.f;
                 }
-                if (td.type == 0) {
+                uint32_t w[2][16];
+                if (kind < 2) {
                     float b[C::ROWS_S];
+                    if (kind == 0) {
 #pragma unroll
-                    for (int rr = 0; rr < C::ROWS_S; ++rr) {
-                        const int kind = td.row_kind[rr], xo = td.row_x[rr];
-                        float bv = 0.f;
-                        if (kind == 0) bv = xrow[xo] * s0;
-                        else if (kind == 1) bv = xrow[xo] * s1x + xrow[xo + 1] * s1y + xrow[xo + 2] * s1z;
-                        b[rr] = bv;
+                        for (int rr = 0; rr < C::ROWS_S; ++rr) b[rr] = rr < n_rows ? xt[rr] * s0 : 0.f;
+                    } else {
+#pragma unroll
+                        for (int rr = 0; rr < C::ROWS_S; ++rr)
+                            b[rr] = rr < n_rows ? xt[3 * rr] * s1x + xt[3 * rr + 1] * s1y + xt[3 * rr + 2] * s1z : 0.f;
                     }
                     mbar_wait(&tmem_full[buf], tf_phase[buf]);
                     tf_phase[buf] ^= 1;
                     tc_fence_after();
+                    tmem_ld16_async(taddr, w[0]);
 #pragma unroll
                     for (int c16 = 0; c16 < C::NCOL_S / 16; ++c16) {
-                        float w[16];
-                        tmem_ld16(taddr + (uint32_t)(c16 * 16), w);
+                        if (c16 < n_chunks) {
+                            tmem_wait16(w[c16 & 1]);
+                            if (c16 + 1 < C::NCOL_S / 16 && c16 + 1 < n_chunks) tmem_ld16_async(taddr + (uint32_t)((c16 + 1) * 16), w[(c16 + 1) & 1]);
 #pragma unroll
-                        for (int q = 0; q < 16; ++q) {
-                            const int c = c16 * 16 + q;
-                            acc[c % NS] = fmaf(w[q], b[c / NS], acc[c % NS]);
+                            for (int q = 0; q < 16; ++q) {
+                                const int c = c16 * 16 + q;
+                                acc[c % NS] = fmaf(__uint_as_float(w[c16 & 1][q]), b[c / NS], acc[c % NS]);
+                            }
                         }
                     }
                     tc_fence_before();
                     mbar_arrive(&tmem_empty[buf]);
-                    if (td.last && valid) {
-                        float *dst = sum + (size_t)agg * f_out + td.out_off;
-#pragma unroll
-                        for (int o = 0; o < NS; ++o) red_add(dst + o, acc[o]);
-                    }
+                    if ((flags & 4) && valid) red_row<NS>(sum + (size_t)agg * f_out + out_off, acc);
                 } else {
                     float bx[C::ROWS_V], by[C::ROWS_V], bz[C::ROWS_V];
+                    if (kind == 2) {
 #pragma unroll
-                    for (int rr = 0; rr < C::ROWS_V; ++rr) {
-                        const int kind = td.row_kind[rr], xo = td.row_x[rr];
-                        float vx = 0.f, vy = 0.f, vz = 0.f;
-                        if (kind == 2) { const float x0 = xrow[xo]; vx = x0 * s1x; vy = x0 * s1y; vz = x0 * s1z; }
-                        else if (kind == 3) { vx = xrow[xo] * s0; vy = xrow[xo + 1] * s0; vz = xrow[xo + 2] * s0; }
-                        else if (kind == 4) {
-                            const float ax = xrow[xo], ay = xrow[xo + 1], az = xrow[xo + 2];
-                            vx = ay * s1z - az * s1y; vy = az * s1x - ax * s1z; vz = ax * s1y - ay * s1x;
+                        for (int rr = 0; rr < C::ROWS_V; ++rr) {
+                            const float x0 = rr < n_rows ? xt[rr] : 0.f;
+                            bx[rr] = x0 * s1x; by[rr] = x0 * s1y; bz[rr] = x0 * s1z;
                         }
-                        bx[rr] = vx; by[rr] = vy; bz[rr] = vz;
+                    } else if (kind == 3) {
+#pragma unroll
+                        for (int rr = 0; rr < C::ROWS_V; ++rr) {
+                            const float m = rr < n_rows ? s0 : 0.f;
+                            bx[rr] = xt[3 * rr] * m; by[rr] = xt[3 * rr + 1] * m; bz[rr] = xt[3 * rr + 2] * m;
+                        }
+                    } else {
+#pragma unroll
+                        for (int rr = 0; rr < C::ROWS_V; ++rr) {
+                            const bool on = rr < n_rows;
+                            const float ax = on ? xt[3 * rr] : 0.f, ay = on ? xt[3 * rr + 1] : 0.f, az = on ? xt[3 * rr + 2] : 0.f;
+                            bx[rr] = ay * s1z - az * s1y; by[rr] = az * s1x - ax * s1z; bz[rr] = ax * s1y - ay * s1x;
+                        }
                     }
                     mbar_wait(&tmem_full[buf], tf_phase[buf]);
                     tf_phase[buf] ^= 1;
                     tc_fence_after();
+                    tmem_ld16_async(taddr, w[0]);
 #pragma unroll
                     for (int c16 = 0; c16 < C::NCOL_V / 16; ++c16) {
-                        float w[16];
-                        tmem_ld16(taddr + (uint32_t)(c16 * 16), w);
+                        if (c16 < n_chunks) {
+                            tmem_wait16(w[c16 & 1]);
+                            if (c16 + 1 < C::NCOL_V / 16 && c16 + 1 < n_chunks) tmem_ld16_async(taddr + (uint32_t)((c16 + 1) * 16), w[(c16 + 1) & 1]);
 #pragma unroll
-                        for (int q = 0; q < 16; ++q) {
-                            const int c = c16 * 16 + q;
-                            const int rr = c / NV, o = c % NV;
-                            acc[3 * o] = fmaf(w[q], bx[rr], acc[3 * o]);
-                            acc[3 * o + 1] = fmaf(w[q], by[rr], acc[3 * o + 1]);
-                            acc[3 * o + 2] = fmaf(w[q], bz[rr], acc[3 * o + 2]);
+                            for (int q = 0; q < 16; ++q) {
+                                const int c = c16 * 16 + q;
+                                const int rr = c / NV, o = c % NV;
+                                const float wv = __uint_as_float(w[c16 & 1][q]);
+                                acc[3 * o] = fmaf(wv, bx[rr], acc[3 * o]);
+                                acc[3 * o + 1] = fmaf(wv, by[rr], acc[3 * o + 1]);
+                                acc[3 * o + 2] = fmaf(wv, bz[rr], acc[3 * o + 2]);
+                            }
                         }
                     }
                     tc_fence_before();
                     mbar_arrive(&tmem_empty[buf]);
-                    if (td.last && valid) {
-                        float *dst = sum + (size_t)agg * f_out + td.out_off;
-#pragma unroll
-                        for (int o = 0; o < 3 * NV; ++o) red_add(dst + o, acc[o]);
-                    }
+                    if ((flags & 4) && valid) red_row<3 * NV>(sum + (size_t)agg * f_out + out_off, acc);
                 }
             }
         }
@@ -515,7 +567,11 @@ static int build_plan(const ddp_tpconv_t &c, const ddp_tp_group_t *groups, const
     memset(&h, 0, sizeof(h));
     h.magic = MAGIC; h.mode = mode; h.ns = ns; h.nv = nv; h.ks = ks; h.kp = 3 * ks; h.n1 = 3 * ks;
     h.stage_k = mode ? 16 : 32; h.f_in = c.f_in; h.f_out = c.f_out;
-    // groups sharing (out_off, d_out) form one weight block; they are contiguous in w_off order
+    // groups sharing (out_off, d_out) form one weight block (one accumulation of the kernel); they are contiguous in
+    // w_off order.  Every tile covers rows of ONE group, so its basis kind and x stride are uniform.
+    const int x_slots = ns + 6 * nv;
+    const int lost = c.f_in > x_slots ? c.f_in - x_slots : 0;
+    bool swapped = false;
     int g = 0;
     while (g < c.n_groups) {
         int g_end = g;
@@ -523,63 +579,47 @@ static int build_plan(const ddp_tpconv_t &c, const ddp_tp_group_t *groups, const
         const bool vec = groups[g].d_out == 3;
         const int mul_out = groups[g].mul_out;
         if (mul_out != (vec ? nv : ns)) return DDP_E_UNSUPPORTED;
-        struct Row { int kind, xo, wcol; float scale; };
-        std::vector<Row> rows;
+        const int per = vec ? rows_v : rows_s;
+        const size_t first_tile = P.tiles.size();
         for (int q = g; q < g_end; ++q) {
             float sc;
             const int kind = group_kind(groups[q], ctab_host, sc);
             if (kind < 0 || (vec != (kind >= 2))) return DDP_E_UNSUPPORTED;
             if (groups[q].sh_off != ((kind == 0 || kind == 3) ? 0 : 1)) return DDP_E_UNSUPPORTED;
-            for (int u = 0; u < groups[q].mul_in; ++u)
-                rows.push_back({kind, groups[q].x_off + u * groups[q].d1, groups[q].w_off + u * mul_out, sc});
-        }
-        const int per = vec ? rows_v : rows_s;
-        const int n_t = ((int)rows.size() + per - 1) / per;
-        for (int t = 0; t < n_t; ++t) {
-            TileDesc td;
-            memset(&td, 0, sizeof(td));
-            td.n_cols = (uint16_t)(per * mul_out);
-            td.type = vec ? 1 : 0;
-            td.out_off = (uint16_t)groups[g].out_off;
-            td.first = t == 0; td.last = t == n_t - 1;
-            std::vector<std::pair<int, float>> cols(td.n_cols, {-1, 0.f});
-            int nr = 0;
-            for (int rr = 0; rr < per; ++rr) {
-                const int ri = t * per + rr;
-                if (ri < (int)rows.size()) {
-                    td.row_kind[rr] = (uint8_t)rows[ri].kind; td.row_x[rr] = (uint8_t)rows[ri].xo; ++nr;
-                    for (int o = 0; o < mul_out; ++o) cols[rr * mul_out + o] = {rows[ri].wcol + o, rows[ri].scale};
-                } else {
-                    td.row_kind[rr] = 255;
+            const int d1 = groups[q].d1;
+            for (int r0 = 0; r0 < groups[q].mul_in; r0 += per) {
+                const int nr = std::min(per, groups[q].mul_in - r0);
+                TileDesc td;
+                memset(&td, 0, sizeof(td));
+                td.n_cols = (uint16_t)((nr * mul_out + 15) / 16 * 16);
+                td.kind = (uint8_t)kind;
+                td.n_rows = (uint8_t)nr;
+                td.out_off = (uint16_t)groups[g].out_off;
+                // Only x_slots gathered features are resident in shared memory; features [x_slots, f_in) replace the
+                // first f_in - x_slots ones from the first tile that reads them (flags bit 1).
+                int xo = groups[q].x_off + r0 * d1;
+                const int x_end = xo + nr * d1;
+                if (xo >= x_slots) {
+                    if (!swapped) { td.flags |= 2; swapped = true; }
+                    xo -= x_slots;
+                } else if (x_end > x_slots || (swapped && xo < lost)) {
+                    return DDP_E_UNSUPPORTED;                          // straddles the swap or reads an overwritten slot
                 }
+                td.x_off = (uint16_t)xo;
+                std::vector<std::pair<int, float>> cols(td.n_cols, {-1, 0.f});
+                for (int rr = 0; rr < nr; ++rr)
+                    for (int o = 0; o < mul_out; ++o) cols[rr * mul_out + o] = {groups[q].w_off + (r0 + rr) * mul_out + o, sc};
+                P.tiles.push_back(td);
+                P.tile_cols.push_back(cols);
             }
-            td.n_rows = (uint8_t)nr;
-            P.tiles.push_back(td);
-            P.tile_cols.push_back(cols);
         }
+        if (P.tiles.size() == first_tile) return DDP_E_UNSUPPORTED;
+        P.tiles[first_tile].flags |= 1;
+        P.tiles.back().flags |= 4;
         g = g_end;
     }
     h.n_tiles = (int)P.tiles.size();
     if (h.n_tiles > 64) return DDP_E_UNSUPPORTED;
-    // Only x_slots gathered features are resident in shared memory; features [x_slots, f_in) replace the first
-    // f_in - x_slots ones from the first tile that reads them (kernel: TileDesc::first bit 1).
-    const int x_slots = ns + 6 * nv;
-    if (c.f_in > x_slots) {
-        const int lost = c.f_in - x_slots;
-        bool swapped = false;
-        for (auto &td : P.tiles) {
-            const int per = td.type ? rows_v : rows_s;
-            bool needs = false;
-            for (int rr = 0; rr < per; ++rr)
-                if (td.row_kind[rr] != 255 && td.row_x[rr] >= x_slots) needs = true;
-            if (needs && !swapped) { td.first |= 2; swapped = true; }
-            for (int rr = 0; rr < per; ++rr) {
-                if (td.row_kind[rr] == 255) continue;
-                if (td.row_x[rr] >= x_slots) td.row_x[rr] = (uint8_t)(td.row_x[rr] - x_slots);
-                else if (swapped && td.row_x[rr] < lost) return DDP_E_UNSUPPORTED;   // would read an overwritten slot
-            }
-        }
-    }
     int64_t off = (sizeof(Header) + 127) / 128 * 128;
     h.tiles_off = off;
     off += (int64_t)((h.n_tiles * sizeof(TileDesc) + 127) / 128 * 128);

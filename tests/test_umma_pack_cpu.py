@@ -78,28 +78,30 @@ def test_packed_image_replays_conv(ns, nv, layer, mode):
     s0, s1 = sh[:, 0].numpy().astype(np.float64), sh[:, 1:].numpy().astype(np.float64)
     x_slots = ns + 6 * nv
     xs = x.numpy().astype(np.float64)[:, :x_slots].copy()              # resident slots of the kernel's x tile
+    x_full = x.numpy().astype(np.float64)
+    seen_first = set()
     for t in range(n_tiles):
-        n_cols, typ, n_rows, out_off, first, last = struct.unpack_from('<HBBHBB', buf, tiles_off + 40 * t)
-        if first & 2:                                                    # swap the last irrep into the first slots
-            xs[:, :spec.f_in - x_slots] = x.numpy().astype(np.float64)[:, x_slots:]
-        kinds = np.frombuffer(buf, dtype=np.uint8, count=16, offset=tiles_off + 40 * t + 8)
-        xo = np.frombuffer(buf, dtype=np.uint8, count=16, offset=tiles_off + 40 * t + 24)
+        n_cols, kind, n_rows, out_off, flags, _, x_off = struct.unpack_from('<HBBHBBH', buf, tiles_off + 16 * t)
+        if flags & 2:                                                    # swap the last irrep into the first slots
+            xs[:, :spec.f_in - x_slots] = x_full[:, x_slots:]
+        if flags & 1:
+            assert out_off not in seen_first                             # one accumulation per output block
+            seen_first.add(out_off)
         W2, off = _decode_operand(buf, off, n_cols, kp, stage_k, mode)
         w = H @ W2.astype(np.float64).T                                        # [n_e, n_cols]
-        mul = ns if typ == 0 else nv
-        for rr in range(n_cols // mul):
-            k = kinds[rr]
-            if k == 255:
-                assert np.all(W2[rr * mul:(rr + 1) * mul] == 0)
-                continue
-            xv = xs[:, xo[rr]:xo[rr] + 3]
-            if k == 0: b = xs[:, xo[rr]] * s0
-            elif k == 1: b = (xv * s1).sum(-1)
-            elif k == 2: b = xs[:, xo[rr], None] * s1
-            elif k == 3: b = xv * s0[:, None]
+        mul = ns if kind < 2 else nv
+        assert n_cols % 16 == 0 and n_rows * mul <= n_cols < n_rows * mul + 16
+        assert np.all(W2[n_rows * mul:] == 0)                            # zero padding columns
+        for rr in range(n_rows):
+            xo = x_off + rr * (1 if kind in (0, 2) else 3)
+            xv = xs[:, xo:xo + 3]
+            if kind == 0: b = xs[:, xo] * s0
+            elif kind == 1: b = (xv * s1).sum(-1)
+            elif kind == 2: b = xs[:, xo, None] * s1
+            elif kind == 3: b = xv * s0[:, None]
             else: b = np.cross(xv, s1)
             for o in range(mul):
-                if typ == 0:
+                if kind < 2:
                     out[:, out_off + o] += w[:, rr * mul + o] * b
                 else:
                     out[:, out_off + 3 * o:out_off + 3 * o + 3] += w[:, rr * mul + o, None] * b
