@@ -292,10 +292,9 @@ def main():
             model.run_plan(pl, ct)
         torch.cuda.synchronize()
         tot_ms, tot_fl, n_l = 0.0, 0.0, 0
-        for (e0, e1, w_numel, es, ns) in model.profile:
-            n_e = int(es.n_dev.item())
+        for (e0, e1, convs) in model.profile:
             tot_ms += e0.elapsed_time(e1)
-            tot_fl += conv_flops(ns, w_numel) * n_e
+            tot_fl += sum(conv_flops(ns, w_numel) * int(es.n_dev.item()) for (w_numel, es, ns) in convs)
             n_l += 1
         model.profile = None
         ach = tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0

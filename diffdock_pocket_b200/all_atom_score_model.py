@@ -335,7 +335,7 @@ class TensorProductScoreModel(nn.Module):
             es[nm].deg[r] = pl.deg_arena[o:o + n]
             o += n
         # scatter-sum arena: three updates per node type
-        pl.sum_arena = torch.zeros(3 * (pl.NL + pl.NA + pl.NR) * F, **f32)
+        pl.sum_arena = torch.zeros(3 * (pl.NL + pl.NA + pl.NR) * F + 64, **f32)
         pl.sig = torch.zeros(B, self.sigma_embed_dim, **f32)
         pl.U = torch.zeros(len(P['proj_names']), B, ns, **f32)
         # ---- per-forward host scalars -> one pinned staging buffer ------------------------------
@@ -431,29 +431,46 @@ class TensorProductScoreModel(nn.Module):
         return h
 
     # ------------------------------------------------------------------------------------------ forward
-    def _conv(self, L, st, layer, pk, es, flip, x, p1, i1_row, p2, i2_row, sum_buf, ew=None):
-        """One fused tensor-product convolution: agg / gather rows follow ``flip`` (torch.flip of edge_index)."""
+    @staticmethod
+    def _edges_desc(es, flip, x, p1, i1_row, p2, i2_row):
+        """ddp_tpconv_edges_t of one conv: agg / gather rows follow ``flip`` (torch.flip of edge_index)."""
         agg_r, gat_r = (1, 0) if flip else (0, 1)
-        ed = _lib.TpEdges(emb=ptr(es.emb), p1=ptr(p1) if p1 is not None else None,
-                          i1=es.row(i1_row) if p1 is not None else None, ld1=p1.shape[1] if p1 is not None else 0,
-                          p2=ptr(p2) if p2 is not None else None, i2=es.row(i2_row) if p2 is not None else None,
-                          ld2=p2.shape[1] if p2 is not None else 0, x=ptr(x), gather=es.row(gat_r), ldx=x.shape[1],
-                          sh=ptr(es.sh_conv if hasattr(es, 'sh_conv') else es.sh), agg=es.row(agg_r), ew=None,
-                          n_edges_dev=ptr(es.n_dev), edge_cap=es.cap)
+        return _lib.TpEdges(emb=ptr(es.emb), p1=ptr(p1) if p1 is not None else None,
+                            i1=es.row(i1_row) if p1 is not None else None, ld1=p1.shape[1] if p1 is not None else 0,
+                            p2=ptr(p2) if p2 is not None else None, i2=es.row(i2_row) if p2 is not None else None,
+                            ld2=p2.shape[1] if p2 is not None else 0, x=ptr(x), gather=es.row(gat_r), ldx=x.shape[1],
+                            sh=ptr(es.sh_conv if hasattr(es, 'sh_conv') else es.sh), agg=es.row(agg_r), ew=None,
+                            n_edges_dev=ptr(es.n_dev), edge_cap=es.cap)
+
+    def _conv_group(self, L, st, items):
+        """Fused tensor-product convolutions that share irreps (the convs of one interaction layer, or a single
+        head conv).  items: (layer, packed, edge set, flip, x, p1, i1_row, p2, i2_row, sum_buf).  On the tensor-core
+        path they run as ONE persistent kernel over the union of their edge tiles (ddp_tpconv_umma_group)."""
+        if len(items) > 1 and not getattr(self, 'group_convs', True):      # one launch per conv (per-conv timing)
+            for it in items:
+                self._conv_group(L, st, [it])
+            return
         prof = getattr(self, 'profile', None)
         if prof is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        if self.conv_mode != 'fp32' and pk.spec.tc_eligible and p1 is not None and p2 is not None:
+        tc = self.conv_mode != 'fp32' and all(it[1].spec.tc_eligible and it[5] is not None and it[7] is not None for it in items)
+        eds = [self._edges_desc(*it[2:9]) for it in items]
+        if tc:
             mode = 0 if self.conv_mode == 'bf16' else 1
-            img = pk.umma_image(layer, mode, x.device)
-            _lib.check(L.ddp_tpconv_umma(C.byref(pk.cdesc), ptr(img), mode, C.byref(ed), ptr(sum_buf), st), 'ddp_tpconv_umma')
+            n = len(items)
+            convs = (C.c_void_p * n)(*[C.addressof(it[1].cdesc) for it in items])
+            imgs = (C.c_void_p * n)(*[ptr(it[1].umma_image(it[0], mode, it[4].device)) for it in items])
+            edp = (C.c_void_p * n)(*[C.addressof(e) for e in eds])
+            sums = (C.c_void_p * n)(*[ptr(it[9]) for it in items])
+            _lib.check(L.ddp_tpconv_umma_group(convs, imgs, mode, edp, sums, n, st), 'ddp_tpconv_umma_group')
         else:
-            _lib.check(L.ddp_tpconv_fp32(C.byref(pk.cdesc), C.byref(ed), ptr(sum_buf), st), 'ddp_tpconv_fp32')
+            for it, e in zip(items, eds):
+                _lib.check(L.ddp_tpconv_fp32(C.byref(it[1].cdesc), C.byref(e), ptr(it[9]), st), 'ddp_tpconv_fp32')
         if prof is not None:
             ev1.record()
-            if p1 is not None and p2 is not None and pk.spec.tc_eligible:
-                prof.append((ev0, ev1, pk.spec.weight_numel, es, self.ns))
+            if tc:
+                prof.append((ev0, ev1, [(it[1].spec.weight_numel, it[2], self.ns) for it in items]))
 
     def run_plan(self, pl, complex_t, return_layers=False):
         """Forward on a resident plan.  Returns device tensors; performs no host synchronisation."""
@@ -526,23 +543,26 @@ class TensorProductScoreModel(nn.Module):
             def take(n):
                 nonlocal o
                 v = pl.sum_arena[o:o + n * f_new].view(n, f_new)
-                o += n * f_new
+                o += (n * f_new + 3) // 4 * 4                                # keep every slice 16-byte aligned
                 return v
             s_ll, s_lr, s_la = take(pl.NL), take(pl.NL), take(pl.NL)
-            self._conv(L, st, Cv[9 * l], Pk[9 * l], es['ll'], False, xl, xl, 0, xl, 1, s_ll)
-            self._conv(L, st, Cv[9 * l + 1], Pk[9 * l + 1], es['lr'], False, xr, xl, 0, xr, 1, s_lr)
-            self._conv(L, st, Cv[9 * l + 2], Pk[9 * l + 2], es['la'], False, xa, xl, 0, xa, 1, s_la)
+            grp = [(Cv[9 * l], Pk[9 * l], es['ll'], False, xl, xl, 0, xl, 1, s_ll),
+                   (Cv[9 * l + 1], Pk[9 * l + 1], es['lr'], False, xr, xl, 0, xr, 1, s_lr),
+                   (Cv[9 * l + 2], Pk[9 * l + 2], es['la'], False, xa, xl, 0, xa, 1, s_la)]
             do_atom = self.flexible_sidechains or not last
             if do_atom:
                 s_aa, s_al, s_ar = take(pl.NA), take(pl.NA), take(pl.NA)
-                self._conv(L, st, Cv[9 * l + 3], Pk[9 * l + 3], es['aa'], False, xa, xa, 0, xa, 1, s_aa)
-                self._conv(L, st, Cv[9 * l + 4], Pk[9 * l + 4], es['la'], True, xl, xa, 1, xl, 0, s_al)
-                self._conv(L, st, Cv[9 * l + 5], Pk[9 * l + 5], es['ar'], False, xr, xa, 0, xr, 1, s_ar)
+                grp += [(Cv[9 * l + 3], Pk[9 * l + 3], es['aa'], False, xa, xa, 0, xa, 1, s_aa),
+                        (Cv[9 * l + 4], Pk[9 * l + 4], es['la'], True, xl, xa, 1, xl, 0, s_al),
+                        (Cv[9 * l + 5], Pk[9 * l + 5], es['ar'], False, xr, xa, 0, xr, 1, s_ar)]
                 if not last:
                     s_rr, s_rl, s_ra = take(pl.NR), take(pl.NR), take(pl.NR)
-                    self._conv(L, st, Cv[9 * l + 6], Pk[9 * l + 6], es['rr'], False, xr, xr, 0, xr, 1, s_rr)
-                    self._conv(L, st, Cv[9 * l + 7], Pk[9 * l + 7], es['lr'], True, xl, xr, 1, xl, 0, s_rl)
-                    self._conv(L, st, Cv[9 * l + 8], Pk[9 * l + 8], es['ar'], True, xa, xr, 1, xa, 0, s_ra)
+                    grp += [(Cv[9 * l + 6], Pk[9 * l + 6], es['rr'], False, xr, xr, 0, xr, 1, s_rr),
+                            (Cv[9 * l + 7], Pk[9 * l + 7], es['lr'], True, xl, xr, 1, xl, 0, s_rl),
+                            (Cv[9 * l + 8], Pk[9 * l + 8], es['ar'], True, xa, xr, 1, xa, 0, s_ra)]
+            # largest edge sets first: the round-robin tile walk then ends on the small ones
+            grp.sort(key=lambda it: -it[2].cap)
+            self._conv_group(L, st, grp)
 
             def update(key, x_old, n, items):
                 ups = (_lib.Update * len(items))(*[
@@ -591,7 +611,7 @@ class TensorProductScoreModel(nn.Module):
         chk(L.ddp_edge_embed(ptr(pl.center), ptr(pl.lig_pos), ptr(ec.edge), ec.cap, ptr(ec.n_dev), None, None, 0, ptr(U['center']),
                              C.byref(em['center']['desc']), ptr(ec.sh), ptr(ec.emb), st), 'ddp_edge_embed(center)')
         pl.g_sum.zero_()
-        self._conv(L, st, self.final_conv, P['final_conv'], ec, False, xl, xl, 1 if self.fixed_center_conv else 0, None, 0, pl.g_sum)
+        self._conv_group(L, st, [(self.final_conv, P['final_conv'], ec, False, xl, xl, 1 if self.fixed_center_conv else 0, None, 0, pl.g_sum)])
         fc = P['final_conv']
         up = _lib.Update(sum=ptr(pl.g_sum), deg=ptr(pl.center_deg), scale=ptr(fc.bn_scale), shift=ptr(fc.bn_shift), n_edges_dev=ptr(ec.n_dev))
         chk(L.ddp_node_update(None, 0, 0, C.byref(up), 1, B, 12, ptr(pl.g), 12, st), 'ddp_node_update')
@@ -623,7 +643,7 @@ class TensorProductScoreModel(nn.Module):
             h.deg.zero_()
             chk(L.ddp_degree(e.row(0), ptr(e.n_dev), e.cap, ptr(h.deg), st), 'ddp_degree')
             pk = P[key + '_conv']
-            self._conv(L, st, conv, pk, e, False, xn, xn, 1, h.attr, 0, h.sum)
+            self._conv_group(L, st, [(conv, pk, e, False, xn, xn, 1, h.attr, 0, h.sum)])
             up = _lib.Update(sum=ptr(h.sum), deg=ptr(h.deg), scale=ptr(pk.bn_scale), shift=ptr(pk.bn_shift), n_edges_dev=ptr(e.n_dev))
             chk(L.ddp_node_update(None, 0, 0, C.byref(up), 1, n, 2 * ns, ptr(h.feat), 2 * ns, st), 'ddp_node_update')
             (w1, _), (w2, _) = P[mlp_key]

@@ -3,15 +3,18 @@
 // weight tiles consumed straight out of TMEM by the tensor-product epilogue.  The per-edge weight
 // vector (up to 10000 floats) never exists in shared or global memory.
 //
-// One CTA = one tile of 128 edges (TMEM lane = edge).  Warp roles:
-//   warps 0-3  gather + epilogue: stage [emb | node scalars] as the bf16 A operand and the gathered node
-//              features (fp32) in shared memory; after GEMM1 apply ReLU and write the hidden activations back
-//              as the A operand of GEMM2; then, per weight tile, tcgen05.ld the [128 x N] accumulator,
-//              multiply with the tensor-product basis and accumulate the edge's output in registers;
-//              red.global.add into the aggregation node at the end of each output block.
+// One CTA (persistent, one per SM) walks 128-edge tiles (TMEM lane = edge) of up to 9 convolutions that share
+// irreps (the convs of one interaction layer): tile g of the launch belongs to job j with pref[j] <= g < pref[j+1].
+// Warp roles:
+//   warps 0-3  epilogue: after GEMM1 apply ReLU and write the hidden activations back as the A operand of GEMM2;
+//              then, per weight tile, tcgen05.ld the [128 x N] accumulator, multiply with the tensor-product basis
+//              (node features fetched from global memory into registers one tile ahead) and accumulate the edge's
+//              output in registers; vector red.global.add into the aggregation node at the end of each output block.
 //   warp 4     TMA producer: streams the pre-packed weight image (already in UMMA core-matrix order and in
 //              consumption order) slab by slab.
 //   warp 5     MMA issuer (one elected lane) + TMEM allocator.
+//   warps 6-7  gather: stage [emb | node scalars] of the NEXT edge tile as the bf16 A operand (double buffered),
+//              so the gather latency hides under the current tile's GEMM2.
 //
 // Biases ride in the GEMMs: A has a constant-one column (padding slot of the first 64-wide source block)
 // and the images carry b1 / b2 in that K row; the hidden unit `hid` regenerates the one for GEMM2.
@@ -173,79 +176,132 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 
 // ------------------------------------------------------------------------------------------ kernel
 // NS scalar multiplicity, NV vector multiplicity, KS padded width of one A source block (>= NS + 1).
+__host__ __device__ constexpr int rows_scalar(int ns) { return 240 / ns; }                  // basis rows per scalar tile
+__host__ __device__ constexpr int rows_vector(int nv) { return nv == 10 ? 10 : 16; }        // basis rows per vector tile
+
+constexpr int MAX_JOBS = 9;
+constexpr int N_EPI = 128, N_GATHER = 64, N_THREADS = 256;
+
+// One fused convolution of a grouped launch.  All jobs of a launch share irreps (tile table, f_in, f_out).
+struct Job {
+    const uint8_t *image;
+    ddp_tpconv_edges_t ed;
+    float *sum;
+};
+struct Jobs {
+    int32_t n, f_in, f_out;
+    Job job[MAX_JOBS];
+};
+
 template <int NS, int NV, int KS, bool SPLIT>
 struct Cfg {
     static constexpr int KP = 3 * KS;                       // padded K of both GEMMs (and padded hidden width N1)
     static constexpr int N1 = KP;
-    static constexpr int ROWS_S = 240 / NS;                 // basis rows per scalar tile
+    static constexpr int ROWS_S = rows_scalar(NS);
     static constexpr int NCOL_S = ROWS_S * NS;
-    static constexpr int ROWS_V = 16;
-    static constexpr int NCOL_V = ROWS_V * NV;
+    static constexpr int ROWS_V = rows_vector(NV);
+    static constexpr int NVAL_V = ROWS_V * NV;              // weight columns of a full vector tile
+    static constexpr int NCOL_V = (NVAL_V + 15) / 16 * 16;  // ... padded to the UMMA N granularity
     static constexpr int NCOL_MAX = (NCOL_S > N1 ? NCOL_S : N1);
     static constexpr int STAGE_K = SPLIT ? 16 : 32;
-    static constexpr int STAGES = SPLIT ? 4 : (KS == 64 ? 7 : 10);
     static constexpr int STAGE_BYTES = NCOL_MAX * STAGE_K * 2 * (SPLIT ? 2 : 1);
     static constexpr int A_BYTES = TILE_M * KP * 2;         // one bf16 A image
-    static constexpr int F_MAX = 2 * NS + 6 * NV;
-    // Only NS + 6 NV gathered features are resident at a time: blocks 0e / 1o read (x0e, x1o, x1e), blocks
-    // 1e / 0o read (x1o, x1e, x0o); x0o is swapped into x0e's slots at the first tile that needs it.
-    static constexpr int X_SLOTS = NS + 6 * NV;
-    static constexpr int XLD = X_SLOTS + 1;                 // odd row stride: conflict-free per-thread rows
-    static constexpr int X_BYTES = TILE_M * XLD * 4;
+    static constexpr int NBUF = SPLIT ? 1 : 2;              // A operand buffers (next tile gathered under the current GEMM2)
+    static constexpr int A_TOTAL = A_BYTES * (SPLIT ? 2 : 1) * NBUF;
     static constexpr int MAX_TILES = 64;
-    static constexpr size_t SMEM = 1024 + (size_t)A_BYTES * (SPLIT ? 2 : 1) + X_BYTES + (size_t)STAGES * STAGE_BYTES +
-                                   MAX_TILES * sizeof(TileDesc) + 256;
-    static_assert(NCOL_S % 16 == 0 && NCOL_V % 16 == 0 && N1 % 16 == 0 && NCOL_MAX <= 256, "UMMA N constraints");
+    static constexpr int FIXED = 1024 + A_TOTAL + MAX_TILES * (int)sizeof(TileDesc) + 512;
+    static constexpr int STAGES_FIT = (220 * 1024 - FIXED) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_FIT > 12 ? 12 : STAGES_FIT;
+    static constexpr size_t SMEM = (size_t)FIXED + (size_t)STAGES * STAGE_BYTES;
+    static constexpr int XN = 3 * ROWS_V > ROWS_S * 3 ? 3 * ROWS_V : ROWS_S * 3;   // floats of x one tile can read
+    static_assert(NCOL_S % 16 == 0 && N1 % 16 == 0 && NCOL_MAX <= 256 && NCOL_V <= 256, "UMMA N constraints");
     static_assert(KS >= NS + 1 && KP % STAGE_K == 0, "K padding");
+    static_assert(STAGES >= 3, "weight ring too small");
+    static_assert(XN % 2 == 0, "x prefetch registers are loaded in pairs");
 };
 
+// Map the g-th 128-edge tile of the launch to (job, tile inside the job); pref = exclusive prefix of tile counts.
+__device__ __forceinline__ void locate(const int *pref, int n_jobs, int g, int &job, int &et) {
+    int j = 0;
+    while (j + 1 < n_jobs && g >= pref[j + 1]) ++j;
+    job = j;
+    et = g - pref[j];
+}
+
+// Issue the global loads of the gathered node features one weight tile reads (n_fl floats from xg): pairs when the
+// offset is even (rows are 8-byte aligned), single floats otherwise.  Predicated, branch-free.
+template <int XN>
+__device__ __forceinline__ void x_prefetch(const float *xg, int n_fl, float (&xn)[XN]) {
+    if ((reinterpret_cast<uintptr_t>(xg) & 7) == 0) {
+#pragma unroll
+        for (int j = 0; j < XN / 2; ++j)
+            if (2 * j < n_fl) {
+                const float2 v = __ldg(reinterpret_cast<const float2 *>(xg) + j);
+                xn[2 * j] = v.x; xn[2 * j + 1] = v.y;
+            }
+    } else {
+#pragma unroll
+        for (int j = 0; j < XN; ++j)
+            if (j < n_fl) xn[j] = __ldg(xg + j);
+    }
+}
+
 template <int NS, int NV, int KS, bool SPLIT>
-__global__ void __launch_bounds__(192, 1)
-tpconv_umma_kernel(const uint8_t *__restrict__ image, ddp_tpconv_edges_t ed, int f_in, int f_out, int n_parts,
-                   float *__restrict__ sum) {
+__global__ void __launch_bounds__(N_THREADS, 1)
+tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
     using C = Cfg<NS, NV, KS, SPLIT>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve (everything 128 B aligned)
     uint8_t *p = smem_raw;
-    uint8_t *a_hi = p;                     p += C::A_BYTES;
-    uint8_t *a_lo = p;                     p += SPLIT ? C::A_BYTES : 0;
-    float *xs = reinterpret_cast<float *>(p); p += (C::X_BYTES + 127) / 128 * 128;
+    uint8_t *a_base = p;                   p += C::A_TOTAL;            // [NBUF][hi (, lo)]
     uint8_t *ring = p;                     p += (size_t)C::STAGES * C::STAGE_BYTES;
     TileDesc *tiles = reinterpret_cast<TileDesc *>(p); p += C::MAX_TILES * sizeof(TileDesc);
     uint64_t *bars = reinterpret_cast<uint64_t *>(p);
     uint64_t *full = bars, *empty = bars + C::STAGES;
     uint64_t *tmem_full = bars + 2 * C::STAGES, *tmem_empty = tmem_full + 2;
-    uint64_t *a_ready = tmem_empty + 2, *h_ready = a_ready + 1;
+    uint64_t *a_ready = tmem_empty + 2, *a_free = a_ready + 2, *h_ready = a_free + 2;
     uint32_t *tmem_base_smem = reinterpret_cast<uint32_t *>(h_ready + 1);
+    int *pref = reinterpret_cast<int *>(tmem_base_smem + 2);            // [MAX_JOBS + 1]
 
-    const Header *hdr = reinterpret_cast<const Header *>(image);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_jobs = jobs.n, f_in = jobs.f_in, f_out = jobs.f_out;
+    const Header *hdr = reinterpret_cast<const Header *>(jobs.job[0].image);
     const int n_tiles = hdr->n_tiles;
-    const int n_edges = min(*ed.n_edges_dev, ed.edge_cap);
-    const int n_etiles = (n_edges + TILE_M - 1) / TILE_M;
 
     for (int i = threadIdx.x; i < n_tiles * (int)(sizeof(TileDesc) / 4); i += blockDim.x)
-        reinterpret_cast<uint32_t *>(tiles)[i] = reinterpret_cast<const uint32_t *>(image + hdr->tiles_off)[i];
+        reinterpret_cast<uint32_t *>(tiles)[i] = reinterpret_cast<const uint32_t *>(jobs.job[0].image + hdr->tiles_off)[i];
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], TILE_M); }
-        mbar_init(a_ready, TILE_M);
-        mbar_init(h_ready, TILE_M);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], N_EPI);
+            mbar_init(&a_ready[b], N_GATHER); mbar_init(&a_free[b], 1);
+        }
+        mbar_init(h_ready, N_EPI);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        int acc = 0;
+        for (int j = 0; j < n_jobs; ++j) {
+            pref[j] = acc;
+            const int ne = min(*jobs.job[j].ed.n_edges_dev, jobs.job[j].ed.edge_cap);
+            acc += (ne + TILE_M - 1) / TILE_M;
+        }
+        pref[n_jobs] = acc;
     }
     if (warp == 5) tmem_alloc(tmem_base_smem, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
+    const int n_etiles = pref[n_jobs];
+    const int slabs_off = (int)hdr->slabs_off;
 
     if (warp == 4) {
         // =============================== TMA producer ===========================================
         if (lane == 0) {
-            const uint8_t *slabs = image + hdr->slabs_off;
             uint32_t stage = 0, phase = 0;
-            for (int et = blockIdx.x; et < n_etiles; et += gridDim.x) {
-                const uint8_t *src = slabs;
+            for (int g = blockIdx.x; g < n_etiles; g += gridDim.x) {
+                int job, et;
+                locate(pref, n_jobs, g, job, et);
+                const uint8_t *src = jobs.job[job].image + slabs_off;
                 for (int t = -1; t < n_tiles; ++t) {
                     const int ncol = (t < 0) ? C::N1 : tiles[t].n_cols;
                     const uint32_t bytes = slab_bytes(ncol, C::STAGE_K, SPLIT);
@@ -264,13 +320,16 @@ tpconv_umma_kernel(const uint8_t *__restrict__ image, ddp_tpconv_edges_t ed, int
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             uint32_t te_phase[2] = {0, 0};       // parity to wait on tmem_empty[b]
-            uint32_t ar_phase = 0, hr_phase = 0;
-            const uint32_t a_hi_addr = smem_u32(a_hi), a_lo_addr = smem_u32(a_lo);
-            for (int et = blockIdx.x; et < n_etiles; et += gridDim.x) {
+            uint32_t hr_phase = 0;
+            int it = 0;
+            for (int g = blockIdx.x; g < n_etiles; g += gridDim.x, ++it) {
+                const int ab = it % C::NBUF;
+                const uint32_t a_hi_addr = smem_u32(a_base + (size_t)ab * C::A_BYTES * (SPLIT ? 2 : 1));
+                const uint32_t a_lo_addr = a_hi_addr + C::A_BYTES;
                 for (int t = -1; t < n_tiles; ++t) {
                     const int ncol = (t < 0) ? C::N1 : tiles[t].n_cols;
                     const int buf = (t + 1) & 1;
-                    if (t < 0) { mbar_wait(a_ready, ar_phase); ar_phase ^= 1; }
+                    if (t < 0) mbar_wait(&a_ready[ab], (uint32_t)(it / C::NBUF) & 1u);
                     if (t == 0) { mbar_wait(h_ready, hr_phase); hr_phase ^= 1; }
                     mbar_wait(&tmem_empty[buf], te_phase[buf] ^ 1);
                     te_phase[buf] ^= 1;
@@ -303,116 +362,148 @@ tpconv_umma_kernel(const uint8_t *__restrict__ image, ddp_tpconv_edges_t ed, int
                     }
                     umma_commit(&tmem_full[buf]);
                 }
+                umma_commit(&a_free[ab]);            // every MMA reading this A buffer has completed
             }
         }
-    } else {
-        // =============================== gather + epilogue warps ===================================
-        const int r = threadIdx.x;                       // edge row = TMEM lane
-        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-        uint32_t tf_phase[2] = {0, 0};
-        float *xrow = xs + (size_t)r * C::XLD;
-        const uint32_t a_row_off = (uint32_t)((r >> 3) * 128 + (r & 7) * 16);
-        for (int et = blockIdx.x; et < n_etiles; et += gridDim.x) {
-            const int e = et * TILE_M + r;
-            const bool valid = e < n_edges;
-            int agg = -1;
-            float s0 = 0.f, s1x = 0.f, s1y = 0.f, s1z = 0.f;
-            // ---- stage the A operand [emb | p1 | p2] (bf16, constant one in slot NS of source 0) and x ----
-            const float *srcs[3] = {nullptr, nullptr, nullptr};
-            const float *xg = nullptr;
-            if (valid) {
-                agg = ed.agg[e];
-                const float4 sh4 = *reinterpret_cast<const float4 *>(ed.sh + (size_t)e * 4);
-                s0 = sh4.x; s1x = sh4.y; s1y = sh4.z; s1z = sh4.w;
-                srcs[0] = ed.emb + (size_t)e * NS;
-                if (ed.p1) srcs[1] = ed.p1 + (size_t)ed.i1[e] * ed.ld1;
-                if (ed.p2) srcs[2] = ed.p2 + (size_t)ed.i2[e] * ed.ld2;
-                xg = ed.x + (size_t)ed.gather[e] * ed.ldx;
+    } else if (warp >= 6) {
+        // =============================== gather warps: A operand of the NEXT edge tile ==============
+        // [emb | p1 | p2] as bf16 (constant one in slot NS of source 0), two rows per thread, written in UMMA
+        // core-matrix order while the tensor cores still work on the previous tile.
+        const int gt = threadIdx.x - 6 * 32;
+        int it = 0;
+        for (int g = blockIdx.x; g < n_etiles; g += gridDim.x, ++it) {
+            int job, et;
+            locate(pref, n_jobs, g, job, et);
+            const ddp_tpconv_edges_t &ed = jobs.job[job].ed;
+            const int n_edges = min(*ed.n_edges_dev, ed.edge_cap);
+            const int ab = it % C::NBUF;
+            uint8_t *a_hi = a_base + (size_t)ab * C::A_BYTES * (SPLIT ? 2 : 1);
+            uint8_t *a_lo = a_hi + C::A_BYTES;
+            const float *srcs[2][3];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int e = et * TILE_M + gt + h * N_GATHER;
+                const bool valid = e < n_edges;
+                srcs[h][0] = valid ? ed.emb + (size_t)e * NS : nullptr;
+                srcs[h][1] = valid ? ed.p1 + (size_t)__ldg(ed.i1 + e) * ed.ld1 : nullptr;
+                srcs[h][2] = valid ? ed.p2 + (size_t)__ldg(ed.i2 + e) * ed.ld2 : nullptr;
             }
+            mbar_wait(&a_free[ab], ((uint32_t)(it / C::NBUF) & 1u) ^ 1u);
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {
-                const float *sp = srcs[s];
-                const bool v4 = (s == 0) ? (NS % 4 == 0) : (((s == 1 ? ed.ld1 : ed.ld2) & 3) == 0);
+            for (int h = 0; h < 2; ++h) {
+                const int r = gt + h * N_GATHER;
+                const uint32_t a_row_off = (uint32_t)((r >> 3) * 128 + (r & 7) * 16);
 #pragma unroll
-                for (int c8 = 0; c8 < KS / 8; ++c8) {
-                    float v[8];
+                for (int s = 0; s < 3; ++s) {
+                    const float *sp = srcs[h][s];
+                    const bool v4 = (s == 0) ? (NS % 4 == 0) : (((s == 1 ? ed.ld1 : ed.ld2) & 3) == 0);
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) v[q] = 0.f;
-                    if (sp != nullptr) {
-                        if (v4 && NS % 4 == 0) {
-                            if (c8 * 8 < NS) {
-                                const float4 f = __ldg(reinterpret_cast<const float4 *>(sp + c8 * 8));
-                                v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+                    for (int c8 = 0; c8 < KS / 8; ++c8) {
+                        float v[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] = 0.f;
+                        if (sp != nullptr) {
+                            if (v4 && NS % 4 == 0) {
+                                if (c8 * 8 < NS) {
+                                    const float4 f = __ldg(reinterpret_cast<const float4 *>(sp + c8 * 8));
+                                    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+                                }
+                                if (c8 * 8 + 4 < NS) {
+                                    const float4 f = __ldg(reinterpret_cast<const float4 *>(sp + c8 * 8 + 4));
+                                    v[4] = f.x; v[5] = f.y; v[6] = f.z; v[7] = f.w;
+                                }
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 8; ++q)
+                                    if (c8 * 8 + q < NS) v[q] = __ldg(sp + c8 * 8 + q);
                             }
-                            if (c8 * 8 + 4 < NS) {
-                                const float4 f = __ldg(reinterpret_cast<const float4 *>(sp + c8 * 8 + 4));
-                                v[4] = f.x; v[5] = f.y; v[6] = f.z; v[7] = f.w;
-                            }
-                        } else {
+                        }
+                        if (s == 0 && NS / 8 == c8) v[NS % 8] = 1.f;
+                        uint4 hi;
+                        hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
+                        hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
+                        const uint32_t off = (uint32_t)((s * (KS / 8) + c8) * (TILE_M * 16)) + a_row_off;
+                        *reinterpret_cast<uint4 *>(a_hi + off) = hi;
+                        if (SPLIT) {
+                            float w[8];
 #pragma unroll
-                            for (int q = 0; q < 8; ++q)
-                                if (c8 * 8 + q < NS) v[q] = __ldg(sp + c8 * 8 + q);
+                            for (int q = 0; q < 8; ++q) w[q] = v[q] - __bfloat162float(__float2bfloat16_rn(v[q]));
+                            uint4 lo;
+                            lo.x = pack_bf16x2(w[0], w[1]); lo.y = pack_bf16x2(w[2], w[3]);
+                            lo.z = pack_bf16x2(w[4], w[5]); lo.w = pack_bf16x2(w[6], w[7]);
+                            *reinterpret_cast<uint4 *>(a_lo + off) = lo;
                         }
                     }
-                    if (s == 0 && NS / 8 == c8) v[NS % 8] = 1.f;
-                    uint4 hi;
-                    hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
-                    hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
-                    const uint32_t off = (uint32_t)((s * (KS / 8) + c8) * (TILE_M * 16)) + a_row_off;
-                    *reinterpret_cast<uint4 *>(a_hi + off) = hi;
-                    if (SPLIT) {
-                        float w[8];
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) w[q] = v[q] - __bfloat162float(__float2bfloat16_rn(v[q]));
-                        uint4 lo;
-                        lo.x = pack_bf16x2(w[0], w[1]); lo.y = pack_bf16x2(w[2], w[3]);
-                        lo.z = pack_bf16x2(w[4], w[5]); lo.w = pack_bf16x2(w[6], w[7]);
-                        *reinterpret_cast<uint4 *>(a_lo + off) = lo;
-                    }
-                }
-            }
-            {
-                // first X_SLOTS gathered features (the rest is swapped in later, see TileDesc::first bit 1)
-                const int n0 = f_in < C::X_SLOTS ? f_in : C::X_SLOTS;
-                if (valid && (ed.ldx & 3) == 0) {
-                    int c = 0;
-                    for (; c + 4 <= n0; c += 4) {
-                        const float4 f = __ldg(reinterpret_cast<const float4 *>(xg + c));
-                        xrow[c] = f.x; xrow[c + 1] = f.y; xrow[c + 2] = f.z; xrow[c + 3] = f.w;
-                    }
-                    for (; c < n0; ++c) xrow[c] = __ldg(xg + c);
-                } else {
-                    for (int c = 0; c < n0; ++c) xrow[c] = valid ? __ldg(xg + c) : 0.f;
                 }
             }
             fence_proxy_async();
-            mbar_arrive(a_ready);
+            mbar_arrive(&a_ready[ab]);
+        }
+    } else {
+        // =============================== epilogue warps ============================================
+        const int r = threadIdx.x;                       // edge row = TMEM lane
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        uint32_t tf_phase[2] = {0, 0};
+        const uint32_t a_row_off = (uint32_t)((r >> 3) * 128 + (r & 7) * 16);
+        int it = 0;
+        for (int g = blockIdx.x; g < n_etiles; g += gridDim.x, ++it) {
+            int job, et;
+            locate(pref, n_jobs, g, job, et);
+            const ddp_tpconv_edges_t &ed = jobs.job[job].ed;
+            float *__restrict__ sum = jobs.job[job].sum;
+            const int n_edges = min(*ed.n_edges_dev, ed.edge_cap);
+            const int e = et * TILE_M + r;
+            const bool valid = e < n_edges;
+            const int ab = it % C::NBUF;
+            uint8_t *a_hi = a_base + (size_t)ab * C::A_BYTES * (SPLIT ? 2 : 1);
+            uint8_t *a_lo = a_hi + C::A_BYTES;
+            int agg = 0;
+            float s0 = 0.f, s1x = 0.f, s1y = 0.f, s1z = 0.f;
+            const float *xg = ed.x;                      // invalid rows read node 0 and are never written back
+            if (valid) {
+                agg = __ldg(ed.agg + e);
+                const float4 sh4 = __ldg(reinterpret_cast<const float4 *>(ed.sh + (size_t)e * 4));
+                s0 = sh4.x; s1x = sh4.y; s1y = sh4.z; s1z = sh4.w;
+                xg = ed.x + (size_t)__ldg(ed.gather + e) * ed.ldx;
+            }
+            // node features of weight tile 0 (registers; every tile prefetches the next one's)
+            float xn[C::XN];
+            uint4 tdw = *reinterpret_cast<const uint4 *>(&tiles[0]);
+            {
+                const int kind = (int)((tdw.x >> 16) & 0xffu), n_rows = (int)(tdw.x >> 24);
+                x_prefetch<C::XN>(xg + (tdw.z & 0xffffu), n_rows * ((kind == 0 || kind == 2) ? 1 : 3), xn);
+            }
 
             // ---- GEMM1 result -> ReLU -> hidden activations become the A operand of GEMM2 ----
             mbar_wait(&tmem_full[0], tf_phase[0]);
             tf_phase[0] ^= 1;
             tc_fence_after();
-#pragma unroll 1
-            for (int c16 = 0; c16 < C::N1 / 16; ++c16) {
-                float v[16];
-                tmem_ld16(tmem_base + lane_base + (uint32_t)(c16 * 16), v);
+            {
+                uint32_t w[2][16];
+                tmem_ld16_async(tmem_base + lane_base, w[0]);
 #pragma unroll
-                for (int q = 0; q < 16; ++q) v[q] = fmaxf(v[q], 0.f);
+                for (int c16 = 0; c16 < C::N1 / 16; ++c16) {
+                    tmem_wait16(w[c16 & 1]);
+                    if (c16 + 1 < C::N1 / 16) tmem_ld16_async(tmem_base + lane_base + (uint32_t)((c16 + 1) * 16), w[(c16 + 1) & 1]);
+                    float v[16];
 #pragma unroll
-                for (int h8 = 0; h8 < 2; ++h8) {
-                    uint4 hi;
-                    hi.x = pack_bf16x2(v[8 * h8 + 0], v[8 * h8 + 1]); hi.y = pack_bf16x2(v[8 * h8 + 2], v[8 * h8 + 3]);
-                    hi.z = pack_bf16x2(v[8 * h8 + 4], v[8 * h8 + 5]); hi.w = pack_bf16x2(v[8 * h8 + 6], v[8 * h8 + 7]);
-                    const uint32_t off = (uint32_t)((c16 * 2 + h8) * (TILE_M * 16)) + a_row_off;
-                    *reinterpret_cast<uint4 *>(a_hi + off) = hi;
-                    if (SPLIT) {
-                        float w[8];
+                    for (int q = 0; q < 16; ++q) v[q] = fmaxf(__uint_as_float(w[c16 & 1][q]), 0.f);
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) w[q] = v[8 * h8 + q] - __bfloat162float(__float2bfloat16_rn(v[8 * h8 + q]));
-                        uint4 lo;
-                        lo.x = pack_bf16x2(w[0], w[1]); lo.y = pack_bf16x2(w[2], w[3]);
-                        lo.z = pack_bf16x2(w[4], w[5]); lo.w = pack_bf16x2(w[6], w[7]);
-                        *reinterpret_cast<uint4 *>(a_lo + off) = lo;
+                    for (int h8 = 0; h8 < 2; ++h8) {
+                        uint4 hi;
+                        hi.x = pack_bf16x2(v[8 * h8 + 0], v[8 * h8 + 1]); hi.y = pack_bf16x2(v[8 * h8 + 2], v[8 * h8 + 3]);
+                        hi.z = pack_bf16x2(v[8 * h8 + 4], v[8 * h8 + 5]); hi.w = pack_bf16x2(v[8 * h8 + 6], v[8 * h8 + 7]);
+                        const uint32_t off = (uint32_t)((c16 * 2 + h8) * (TILE_M * 16)) + a_row_off;
+                        *reinterpret_cast<uint4 *>(a_hi + off) = hi;
+                        if (SPLIT) {
+                            float u[8];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) u[q] = v[8 * h8 + q] - __bfloat162float(__float2bfloat16_rn(v[8 * h8 + q]));
+                            uint4 lo;
+                            lo.x = pack_bf16x2(u[0], u[1]); lo.y = pack_bf16x2(u[2], u[3]);
+                            lo.z = pack_bf16x2(u[4], u[5]); lo.w = pack_bf16x2(u[6], u[7]);
+                            *reinterpret_cast<uint4 *>(a_lo + off) = lo;
+                        }
                     }
                 }
             }
@@ -422,15 +513,14 @@ tpconv_umma_kernel(const uint8_t *__restrict__ image, ddp_tpconv_edges_t ed, int
             mbar_arrive(&tmem_empty[0]);
 
             // ---- weight tiles: TMEM accumulator x tensor-product basis -> per-edge output registers ----
-            // Every tile has one basis kind, so the basis rows are straight-line shared-memory reads; the accumulator
-            // is read 16 columns at a time with the next tcgen05.ld in flight under the FMAs of the current chunk.
+            // Every tile has one basis kind; its node features arrive in registers (prefetched during the previous
+            // tile); the accumulator is read 16 columns at a time with the next tcgen05.ld in flight under the FMAs.
+            // Full tiles take a branch-free path.
             float acc[NS];
 #pragma unroll 1
             for (int t = 0; t < n_tiles; ++t) {
-                const uint4 tdw = *reinterpret_cast<const uint4 *>(&tiles[t]);
                 const int n_cols = (int)(tdw.x & 0xffffu), kind = (int)((tdw.x >> 16) & 0xffu), n_rows = (int)(tdw.x >> 24);
                 const int out_off = (int)(tdw.y & 0xffffu), flags = (int)((tdw.y >> 16) & 0xffu);
-                const float *xt = xrow + (tdw.z & 0xffffu);
                 const int n_chunks = n_cols >> 4;
                 const int buf = (t + 1) & 1;
                 const uint32_t taddr = tmem_base + lane_base + (uint32_t)buf * 256u;
@@ -438,33 +528,48 @@ tpconv_umma_kernel(const uint8_t *__restrict__ image, ddp_tpconv_edges_t ed, int
 #pragma unroll
                     for (int o = 0; o < NS; ++o) acc[o] = 0.f;
                 }
-                if (flags & 2) {         // swap x[X_SLOTS..f_in) into the slots of the no longer needed first irrep
-                    for (int c = C::X_SLOTS; c < f_in; ++c) xrow[c - C::X_SLOTS] = valid ? __ldg(xg + c) : 0.f;
-                }
                 uint32_t w[2][16];
                 if (kind < 2) {
                     float b[C::ROWS_S];
                     if (kind == 0) {
 #pragma unroll
-                        for (int rr = 0; rr < C::ROWS_S; ++rr) b[rr] = rr < n_rows ? xt[rr] * s0 : 0.f;
+                        for (int rr = 0; rr < C::ROWS_S; ++rr) b[rr] = rr < n_rows ? xn[rr] * s0 : 0.f;
                     } else {
 #pragma unroll
                         for (int rr = 0; rr < C::ROWS_S; ++rr)
-                            b[rr] = rr < n_rows ? xt[3 * rr] * s1x + xt[3 * rr + 1] * s1y + xt[3 * rr + 2] * s1z : 0.f;
+                            b[rr] = rr < n_rows ? xn[3 * rr] * s1x + xn[3 * rr + 1] * s1y + xn[3 * rr + 2] * s1z : 0.f;
+                    }
+                    if (t + 1 < n_tiles) {
+                        tdw = *reinterpret_cast<const uint4 *>(&tiles[t + 1]);
+                        const int k2 = (int)((tdw.x >> 16) & 0xffu), nr2 = (int)(tdw.x >> 24);
+                        x_prefetch<C::XN>(xg + (tdw.z & 0xffffu), nr2 * ((k2 == 0 || k2 == 2) ? 1 : 3), xn);
                     }
                     mbar_wait(&tmem_full[buf], tf_phase[buf]);
                     tf_phase[buf] ^= 1;
                     tc_fence_after();
                     tmem_ld16_async(taddr, w[0]);
+                    if (n_chunks == C::NCOL_S / 16) {
 #pragma unroll
-                    for (int c16 = 0; c16 < C::NCOL_S / 16; ++c16) {
-                        if (c16 < n_chunks) {
+                        for (int c16 = 0; c16 < C::NCOL_S / 16; ++c16) {
                             tmem_wait16(w[c16 & 1]);
-                            if (c16 + 1 < C::NCOL_S / 16 && c16 + 1 < n_chunks) tmem_ld16_async(taddr + (uint32_t)((c16 + 1) * 16), w[(c16 + 1) & 1]);
+                            if (c16 + 1 < C::NCOL_S / 16) tmem_ld16_async(taddr + (uint32_t)((c16 + 1) * 16), w[(c16 + 1) & 1]);
 #pragma unroll
                             for (int q = 0; q < 16; ++q) {
                                 const int c = c16 * 16 + q;
                                 acc[c % NS] = fmaf(__uint_as_float(w[c16 & 1][q]), b[c / NS], acc[c % NS]);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int c16 = 0; c16 < C::NCOL_S / 16; ++c16) {
+                            if (c16 < n_chunks) {
+                                tmem_wait16(w[c16 & 1]);
+                                if (c16 + 1 < C::NCOL_S / 16 && c16 + 1 < n_chunks) tmem_ld16_async(taddr + (uint32_t)((c16 + 1) * 16), w[(c16 + 1) & 1]);
+#pragma unroll
+                                for (int q = 0; q < 16; ++q) {
+                                    const int c = c16 * 16 + q;
+                                    acc[c % NS] = fmaf(__uint_as_float(w[c16 & 1][q]), b[c / NS], acc[c % NS]);
+                                }
                             }
                         }
                     }
@@ -476,40 +581,68 @@ tpconv_umma_kernel(const uint8_t *__restrict__ image, ddp_tpconv_edges_t ed, int
                     if (kind == 2) {
 #pragma unroll
                         for (int rr = 0; rr < C::ROWS_V; ++rr) {
-                            const float x0 = rr < n_rows ? xt[rr] : 0.f;
+                            const float x0 = rr < n_rows ? xn[rr] : 0.f;
                             bx[rr] = x0 * s1x; by[rr] = x0 * s1y; bz[rr] = x0 * s1z;
                         }
                     } else if (kind == 3) {
 #pragma unroll
                         for (int rr = 0; rr < C::ROWS_V; ++rr) {
                             const float m = rr < n_rows ? s0 : 0.f;
-                            bx[rr] = xt[3 * rr] * m; by[rr] = xt[3 * rr + 1] * m; bz[rr] = xt[3 * rr + 2] * m;
+                            bx[rr] = rr < n_rows ? xn[3 * rr] * m : 0.f;
+                            by[rr] = rr < n_rows ? xn[3 * rr + 1] * m : 0.f;
+                            bz[rr] = rr < n_rows ? xn[3 * rr + 2] * m : 0.f;
                         }
                     } else {
 #pragma unroll
                         for (int rr = 0; rr < C::ROWS_V; ++rr) {
                             const bool on = rr < n_rows;
-                            const float ax = on ? xt[3 * rr] : 0.f, ay = on ? xt[3 * rr + 1] : 0.f, az = on ? xt[3 * rr + 2] : 0.f;
+                            const float ax = on ? xn[3 * rr] : 0.f, ay = on ? xn[3 * rr + 1] : 0.f, az = on ? xn[3 * rr + 2] : 0.f;
                             bx[rr] = ay * s1z - az * s1y; by[rr] = az * s1x - ax * s1z; bz[rr] = ax * s1y - ay * s1x;
                         }
+                    }
+                    if (t + 1 < n_tiles) {
+                        tdw = *reinterpret_cast<const uint4 *>(&tiles[t + 1]);
+                        const int k2 = (int)((tdw.x >> 16) & 0xffu), nr2 = (int)(tdw.x >> 24);
+                        x_prefetch<C::XN>(xg + (tdw.z & 0xffffu), nr2 * ((k2 == 0 || k2 == 2) ? 1 : 3), xn);
                     }
                     mbar_wait(&tmem_full[buf], tf_phase[buf]);
                     tf_phase[buf] ^= 1;
                     tc_fence_after();
                     tmem_ld16_async(taddr, w[0]);
+                    if (n_chunks == C::NCOL_V / 16) {
 #pragma unroll
-                    for (int c16 = 0; c16 < C::NCOL_V / 16; ++c16) {
-                        if (c16 < n_chunks) {
+                        for (int c16 = 0; c16 < C::NCOL_V / 16; ++c16) {
                             tmem_wait16(w[c16 & 1]);
-                            if (c16 + 1 < C::NCOL_V / 16 && c16 + 1 < n_chunks) tmem_ld16_async(taddr + (uint32_t)((c16 + 1) * 16), w[(c16 + 1) & 1]);
+                            if (c16 + 1 < C::NCOL_V / 16) tmem_ld16_async(taddr + (uint32_t)((c16 + 1) * 16), w[(c16 + 1) & 1]);
 #pragma unroll
                             for (int q = 0; q < 16; ++q) {
                                 const int c = c16 * 16 + q;
-                                const int rr = c / NV, o = c % NV;
-                                const float wv = __uint_as_float(w[c16 & 1][q]);
-                                acc[3 * o] = fmaf(wv, bx[rr], acc[3 * o]);
-                                acc[3 * o + 1] = fmaf(wv, by[rr], acc[3 * o + 1]);
-                                acc[3 * o + 2] = fmaf(wv, bz[rr], acc[3 * o + 2]);
+                                if (c < C::NVAL_V) {
+                                    const int rr = c / NV, o = c % NV;
+                                    const float wv = __uint_as_float(w[c16 & 1][q]);
+                                    acc[3 * o] = fmaf(wv, bx[rr], acc[3 * o]);
+                                    acc[3 * o + 1] = fmaf(wv, by[rr], acc[3 * o + 1]);
+                                    acc[3 * o + 2] = fmaf(wv, bz[rr], acc[3 * o + 2]);
+                                }
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int c16 = 0; c16 < C::NCOL_V / 16; ++c16) {
+                            if (c16 < n_chunks) {
+                                tmem_wait16(w[c16 & 1]);
+                                if (c16 + 1 < C::NCOL_V / 16 && c16 + 1 < n_chunks) tmem_ld16_async(taddr + (uint32_t)((c16 + 1) * 16), w[(c16 + 1) & 1]);
+#pragma unroll
+                                for (int q = 0; q < 16; ++q) {
+                                    const int c = c16 * 16 + q;
+                                    if (c < C::NVAL_V) {
+                                        const int rr = c / NV, o = c % NV;
+                                        const float wv = __uint_as_float(w[c16 & 1][q]);
+                                        acc[3 * o] = fmaf(wv, bx[rr], acc[3 * o]);
+                                        acc[3 * o + 1] = fmaf(wv, by[rr], acc[3 * o + 1]);
+                                        acc[3 * o + 2] = fmaf(wv, bz[rr], acc[3 * o + 2]);
+                                    }
+                                }
                             }
                         }
                     }
@@ -561,17 +694,13 @@ static int build_plan(const ddp_tpconv_t &c, const ddp_tp_group_t *groups, const
     if (nv == 0) nv = (ns == 60) ? 10 : (ns == 24 ? 6 : 4);
     if (!pick_cfg(ns, nv, ks)) return DDP_E_UNSUPPORTED;
     if (c.k1 != 3 * ns || c.hid != 3 * ns || c.n_emb != ns || c.sh_dim != 4) return DDP_E_UNSUPPORTED;
-    if (c.f_in > 2 * ns + 6 * nv) return DDP_E_UNSUPPORTED;
-    const int rows_s = 240 / ns, rows_v = 16;
+    const int rows_s = rows_scalar(ns), rows_v = rows_vector(nv);
     Header &h = P.h;
     memset(&h, 0, sizeof(h));
     h.magic = MAGIC; h.mode = mode; h.ns = ns; h.nv = nv; h.ks = ks; h.kp = 3 * ks; h.n1 = 3 * ks;
     h.stage_k = mode ? 16 : 32; h.f_in = c.f_in; h.f_out = c.f_out;
     // groups sharing (out_off, d_out) form one weight block (one accumulation of the kernel); they are contiguous in
     // w_off order.  Every tile covers rows of ONE group, so its basis kind and x stride are uniform.
-    const int x_slots = ns + 6 * nv;
-    const int lost = c.f_in > x_slots ? c.f_in - x_slots : 0;
-    bool swapped = false;
     int g = 0;
     while (g < c.n_groups) {
         int g_end = g;
@@ -595,16 +724,7 @@ static int build_plan(const ddp_tpconv_t &c, const ddp_tp_group_t *groups, const
                 td.kind = (uint8_t)kind;
                 td.n_rows = (uint8_t)nr;
                 td.out_off = (uint16_t)groups[g].out_off;
-                // Only x_slots gathered features are resident in shared memory; features [x_slots, f_in) replace the
-                // first f_in - x_slots ones from the first tile that reads them (flags bit 1).
-                int xo = groups[q].x_off + r0 * d1;
-                const int x_end = xo + nr * d1;
-                if (xo >= x_slots) {
-                    if (!swapped) { td.flags |= 2; swapped = true; }
-                    xo -= x_slots;
-                } else if (x_end > x_slots || (swapped && xo < lost)) {
-                    return DDP_E_UNSUPPORTED;                          // straddles the swap or reads an overwritten slot
-                }
+                const int xo = groups[q].x_off + r0 * d1;   // first gathered feature the tile reads
                 td.x_off = (uint16_t)xo;
                 std::vector<std::pair<int, float>> cols(td.n_cols, {-1, 0.f});
                 for (int rr = 0; rr < nr; ++rr)
@@ -711,7 +831,7 @@ extern "C" int64_t ddp_tpconv_pack(const ddp_tpconv_t *conv, const ddp_tp_group_
 }
 
 template <int NS, int NV, int KS, bool SPLIT>
-static int launch_umma(const uint8_t *image, const ddp_tpconv_t &c, const ddp_tpconv_edges_t &e, float *sum, cudaStream_t st) {
+static int launch_umma(const umma::Jobs &jobs, int tiles_cap, cudaStream_t st) {
     using C = umma::Cfg<NS, NV, KS, SPLIT>;
     auto kern = umma::tpconv_umma_kernel<NS, NV, KS, SPLIT>;
     static bool configured = false;
@@ -720,28 +840,50 @@ static int launch_umma(const uint8_t *image, const ddp_tpconv_t &c, const ddp_tp
         if (err != cudaSuccess) return (int)err;
         configured = true;
     }
-    const int tiles = (e.edge_cap + umma::TILE_M - 1) / umma::TILE_M;
-    const int grid = tiles < ddp_num_sms() ? tiles : ddp_num_sms();
-    const int parts = (e.p1 != nullptr) + (e.p2 != nullptr);
-    kern<<<grid, 192, C::SMEM, st>>>(image, e, c.f_in, c.f_out, parts, sum);
+    const int grid = tiles_cap < ddp_num_sms() ? tiles_cap : ddp_num_sms();
+    kern<<<grid, umma::N_THREADS, C::SMEM, st>>>(jobs);
     DDP_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int ddp_tpconv_umma_group(const ddp_tpconv_t *const *convs, const void *const *packed, int32_t mode,
+                                     const ddp_tpconv_edges_t *const *edges, float *const *sums, int32_t n_jobs, void *stream) {
+    if (!convs || !packed || !edges || !sums) return DDP_E_ARG;
+    if (n_jobs <= 0) return 0;
+    if (n_jobs > umma::MAX_JOBS) return DDP_E_SHAPE;
+    umma::Jobs jobs;
+    memset(&jobs, 0, sizeof(jobs));
+    const ddp_tpconv_t &c0 = *convs[0];
+    jobs.f_in = c0.f_in;
+    jobs.f_out = c0.f_out;
+    int tiles_cap = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+        if (!convs[j] || !packed[j] || !edges[j] || !sums[j]) return DDP_E_ARG;
+        const ddp_tpconv_t &c = *convs[j];
+        const ddp_tpconv_edges_t &e = *edges[j];
+        // one tile table for the whole launch: same irreps / weight layout in every job
+        if (c.ns != c0.ns || c.f_in != c0.f_in || c.f_out != c0.f_out || c.w_numel != c0.w_numel || c.n_groups != c0.n_groups)
+            return DDP_E_SHAPE;
+        if (!e.emb || !e.x || !e.gather || !e.sh || !e.agg || !e.n_edges_dev || !e.p1 || !e.p2 || !e.i1 || !e.i2) return DDP_E_ARG;
+        if (e.ew != nullptr) return DDP_E_UNSUPPORTED;
+        if ((e.ldx & 1) || (c.f_out & 1)) return DDP_E_UNSUPPORTED;      // 8-byte aligned rows (vector loads / reductions)
+        if (e.edge_cap <= 0) continue;
+        umma::Job &jb = jobs.job[jobs.n++];
+        jb.image = static_cast<const uint8_t *>(packed[j]);
+        jb.ed = e;
+        jb.sum = sums[j];
+        tiles_cap += (e.edge_cap + umma::TILE_M - 1) / umma::TILE_M;
+    }
+    if (jobs.n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (c0.ns == 60) return mode ? launch_umma<60, 10, 64, true>(jobs, tiles_cap, st) : launch_umma<60, 10, 64, false>(jobs, tiles_cap, st);
+    if (c0.ns == 24) return mode ? launch_umma<24, 6, 32, true>(jobs, tiles_cap, st) : launch_umma<24, 6, 32, false>(jobs, tiles_cap, st);
+    if (c0.ns == 16) return mode ? launch_umma<16, 4, 32, true>(jobs, tiles_cap, st) : launch_umma<16, 4, 32, false>(jobs, tiles_cap, st);
+    return DDP_E_UNSUPPORTED;
 }
 
 extern "C" int ddp_tpconv_umma(const ddp_tpconv_t *conv, const void *packed, int32_t mode, const ddp_tpconv_edges_t *edges,
                                float *sum, void *stream) {
     if (!conv || !packed || !edges || !sum) return DDP_E_ARG;
-    const ddp_tpconv_t &c = *conv;
-    const ddp_tpconv_edges_t &e = *edges;
-    if (!e.emb || !e.x || !e.gather || !e.sh || !e.agg || !e.n_edges_dev || !e.p1 || !e.p2 || !e.i1 || !e.i2) return DDP_E_ARG;
-    if (e.ew != nullptr) return DDP_E_UNSUPPORTED;
-    if (e.edge_cap <= 0) return 0;
-    int nv = 0;
-    if (c.ns == 60) nv = 10; else if (c.ns == 24) nv = 6; else if (c.ns == 16) nv = 4; else return DDP_E_UNSUPPORTED;
-    const uint8_t *img = static_cast<const uint8_t *>(packed);
-    cudaStream_t st = (cudaStream_t)stream;
-    (void)nv;
-    if (c.ns == 60) return mode ? launch_umma<60, 10, 64, true>(img, c, e, sum, st) : launch_umma<60, 10, 64, false>(img, c, e, sum, st);
-    if (c.ns == 24) return mode ? launch_umma<24, 6, 32, true>(img, c, e, sum, st) : launch_umma<24, 6, 32, false>(img, c, e, sum, st);
-    return mode ? launch_umma<16, 4, 32, true>(img, c, e, sum, st) : launch_umma<16, 4, 32, false>(img, c, e, sum, st);
+    return ddp_tpconv_umma_group(&conv, &packed, mode, &edges, &sum, 1, stream);
 }

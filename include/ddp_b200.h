@@ -174,6 +174,12 @@ int64_t ddp_tpconv_pack(const ddp_tpconv_t *conv, const ddp_tp_group_t *groups_h
 int ddp_tpconv_umma(const ddp_tpconv_t *conv, const void *packed, int32_t mode,
                     const ddp_tpconv_edges_t *edges, float *sum, void *stream);
 
+/* Grouped launch: n_jobs (<= 9) convolutions that share irreps (same f_in / f_out / weight layout, e.g. the nine
+ * convs of one interaction layer, all_atom_score_model.py:274-312) run as ONE persistent kernel over the union of
+ * their 128-edge tiles, so small edge sets do not leave SMs idle.  Arrays of n_jobs HOST pointers. */
+int ddp_tpconv_umma_group(const ddp_tpconv_t *const *convs, const void *const *packed, int32_t mode,
+                          const ddp_tpconv_edges_t *const *edges, float *const *sums, int32_t n_jobs, void *stream);
+
 /* node update (all_atom_score_model.py:315-324 + scatter-mean + e3nn BatchNorm eval, score_model.py:117,123):
  *   new[n][c] = (c < f_old ? old[n][c] : 0) + sum_u live_u * (sum_u[n][c] / max(deg_u[n],1) * scale_u[c] + shift_u[c])
  * live_u = (*n_edges_u > 0) reproduces `return 0` for an empty edge set (score_model.py:109-111).

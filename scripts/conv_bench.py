@@ -19,6 +19,7 @@ reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 dev = torch.device('cuda:0')
 model, _, sa, _ = utils.build_models(dev, with_confidence=False)
 model.conv_mode = mode
+model.group_convs = os.environ.get('DDP_NO_GROUP', '0') != '1'
 g = inputs.load_graph_npz(os.path.join(ROOT, 'tests', 'golden', '3dpf_apo.npz'))
 np.random.seed(0)
 torch.manual_seed(0)
@@ -35,16 +36,17 @@ with torch.no_grad():
         model.profile = []
         model.run_plan(pl, ct)
         torch.cuda.synchronize()
-        for i, (e0, e1, w_numel, es, ns) in enumerate(model.profile):
-            ne = int(es.n_dev.item())
-            fl = 2.0 * (9 * ns * ns + 3 * ns * w_numel + w_numel) * ne
-            a = agg.setdefault(i, [0.0, fl, ne, w_numel])
+        for i, (e0, e1, convs) in enumerate(model.profile):
+            ne = sum(int(es.n_dev.item()) for (_, es, _) in convs)
+            nt = sum((int(es.n_dev.item()) + 127) // 128 for (_, es, _) in convs)
+            fl = sum(2.0 * (9 * ns * ns + 3 * ns * w + w) * int(es.n_dev.item()) for (w, es, ns) in convs)
+            a = agg.setdefault(i, [0.0, fl, ne, convs[0][0], nt, len(convs)])
             a[0] += e0.elapsed_time(e1) / reps
     model.profile = None
     tot_ms = sum(a[0] for a in agg.values())
     tot_fl = sum(a[1] for a in agg.values())
-    for i, (ms, fl, ne, w) in agg.items():
-        print(f'conv {i:2d}  W={w:5d} E={ne:7d} tiles={(ne + 127) // 128:5d}  {ms * 1e3:8.1f} us  {fl / ms / 1e9:7.1f} TFLOP/s')
+    for i, (ms, fl, ne, w, nt, nc) in agg.items():
+        print(f'launch {i:2d}  convs={nc} W={w:5d} E={ne:7d} tiles={nt:5d}  {ms * 1e3:8.1f} us  {fl / ms / 1e9:7.1f} TFLOP/s')
     print(f'TOTAL conv {tot_ms:.3f} ms  {tot_fl / tot_ms / 1e9:.1f} TFLOP/s')
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()

@@ -76,14 +76,11 @@ def test_packed_image_replays_conv(ns, nv, layer, mode):
     assert np.allclose(H[:, 3 * ns], 1.0) and np.all(H[:, 3 * ns + 1:] == 0)
     out = np.zeros((n_e, spec.f_out))
     s0, s1 = sh[:, 0].numpy().astype(np.float64), sh[:, 1:].numpy().astype(np.float64)
-    x_slots = ns + 6 * nv
-    xs = x.numpy().astype(np.float64)[:, :x_slots].copy()              # resident slots of the kernel's x tile
-    x_full = x.numpy().astype(np.float64)
+    xs = x.numpy().astype(np.float64)
     seen_first = set()
     for t in range(n_tiles):
         n_cols, kind, n_rows, out_off, flags, _, x_off = struct.unpack_from('<HBBHBBH', buf, tiles_off + 16 * t)
-        if flags & 2:                                                    # swap the last irrep into the first slots
-            xs[:, :spec.f_in - x_slots] = x_full[:, x_slots:]
+        assert not flags & 2
         if flags & 1:
             assert out_off not in seen_first                             # one accumulation per output block
             seen_first.add(out_off)
