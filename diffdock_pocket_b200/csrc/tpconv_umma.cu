@@ -105,6 +105,30 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same with the descriptors given as their low words (start address >> 4 | LBO >> 4 << 16); the high word is the
+// constant SBO = 128 B (8 x 16 B core-matrix rows) | descriptor version 1, so advancing along K is one 32-bit add.
+constexpr uint32_t DESC_HI = 8u | (1u << 14);
+__device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI)
+        : "memory");
+}
+// One lane of the (converged) warp: the tcgen05 / TMA issue paths run warp-uniform and only the instruction itself
+// is predicated, which keeps descriptors in uniform registers instead of per-lane broadcasts.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 // no-swizzle K-major shared-memory descriptor: 8x(16 B) core matrices, LBO = stride between the two
 // K-chunks of one MMA, SBO = stride between 8-row groups (cute::UMMA::SmemDescriptor, version 1)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -295,75 +319,81 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
     const int slabs_off = (int)hdr->slabs_off;
 
     if (warp == 4) {
-        // =============================== TMA producer ===========================================
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (int g = blockIdx.x; g < n_etiles; g += gridDim.x) {
-                int job, et;
-                locate(pref, n_jobs, g, job, et);
-                const uint8_t *src = jobs.job[job].image + slabs_off;
-                for (int t = -1; t < n_tiles; ++t) {
-                    const int ncol = (t < 0) ? C::N1 : tiles[t].n_cols;
-                    const uint32_t bytes = slab_bytes(ncol, C::STAGE_K, SPLIT);
-                    for (int ks = 0; ks < C::KP / C::STAGE_K; ++ks) {
-                        mbar_wait(&empty[stage], phase ^ 1);
+        // =============================== TMA producer (warp-uniform, one elected lane issues) =====
+        uint32_t stage = 0, phase = 0;
+        for (int g = blockIdx.x; g < n_etiles; g += gridDim.x) {
+            int job, et;
+            locate(pref, n_jobs, g, job, et);
+            const uint8_t *src = jobs.job[job].image + slabs_off;
+            for (int t = -1; t < n_tiles; ++t) {
+                const int ncol = (t < 0) ? C::N1 : tiles[t].n_cols;
+                const uint32_t bytes = slab_bytes(ncol, C::STAGE_K, SPLIT);
+#pragma unroll 1
+                for (int ks = 0; ks < C::KP / C::STAGE_K; ++ks) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    if (elect_one()) {
                         mbar_expect_tx(&full[stage], bytes);
                         bulk_g2s(ring + (size_t)stage * C::STAGE_BYTES, src, bytes, &full[stage]);
-                        src += bytes;
-                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                     }
+                    __syncwarp();
+                    src += bytes;
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 5) {
-        // =============================== MMA issuer =============================================
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            uint32_t te_phase[2] = {0, 0};       // parity to wait on tmem_empty[b]
-            uint32_t hr_phase = 0;
-            int it = 0;
-            for (int g = blockIdx.x; g < n_etiles; g += gridDim.x, ++it) {
-                const int ab = it % C::NBUF;
-                const uint32_t a_hi_addr = smem_u32(a_base + (size_t)ab * C::A_BYTES * (SPLIT ? 2 : 1));
-                const uint32_t a_lo_addr = a_hi_addr + C::A_BYTES;
-                for (int t = -1; t < n_tiles; ++t) {
-                    const int ncol = (t < 0) ? C::N1 : tiles[t].n_cols;
-                    const int buf = (t + 1) & 1;
-                    if (t < 0) mbar_wait(&a_ready[ab], (uint32_t)(it / C::NBUF) & 1u);
-                    if (t == 0) { mbar_wait(h_ready, hr_phase); hr_phase ^= 1; }
-                    mbar_wait(&tmem_empty[buf], te_phase[buf] ^ 1);
-                    te_phase[buf] ^= 1;
+        // =============================== MMA issuer (warp-uniform, one elected lane issues) =======
+        uint32_t stage = 0, phase = 0;
+        uint32_t te_phase = 0;               // bit b: parity to wait on tmem_empty[b]
+        uint32_t hr_phase = 0;
+        int it = 0;
+        for (int g = blockIdx.x; g < n_etiles; g += gridDim.x, ++it) {
+            const int ab = it % C::NBUF;
+            const uint32_t a_hi_addr = smem_u32(a_base + (size_t)ab * C::A_BYTES * (SPLIT ? 2 : 1));
+            // descriptor low words: A has LBO = 128 rows x 16 B between the two K chunks of one MMA
+            const uint32_t a_hi_lo = ((a_hi_addr >> 4) & 0x3FFFu) | ((uint32_t)(TILE_M * 16 >> 4) << 16);
+            const uint32_t a_lo_lo = (((a_hi_addr + C::A_BYTES) >> 4) & 0x3FFFu) | ((uint32_t)(TILE_M * 16 >> 4) << 16);
+            for (int t = -1; t < n_tiles; ++t) {
+                const uint32_t ncol = (t < 0) ? (uint32_t)C::N1 : (uint32_t)tiles[t].n_cols;
+                const uint32_t buf = (uint32_t)(t + 1) & 1u;
+                if (t < 0) mbar_wait(&a_ready[ab], (uint32_t)(it / C::NBUF) & 1u);
+                if (t == 0) { mbar_wait(h_ready, hr_phase); hr_phase ^= 1; }
+                mbar_wait(&tmem_empty[buf], ((te_phase >> buf) & 1u) ^ 1u);
+                te_phase ^= 1u << buf;
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * 256u;
+                const uint32_t idesc = instr_desc((int)ncol);
+                // B: LBO = ncol rows x 16 B; one K = 16 step advances the start address by 2 * LBO
+                const uint32_t b_lbo_word = ncol << 16;
+                const uint32_t b_step = 2u * ncol;                      // (2 * ncol * 16 B) >> 4
+#pragma unroll 1
+                for (int ks = 0; ks < C::KP / C::STAGE_K; ++ks) {
+                    mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u;
-                    const uint32_t idesc = instr_desc(ncol);
-                    const uint32_t b_lbo = (uint32_t)ncol * 16u;
-                    uint32_t acc = 0;
-                    for (int ks = 0; ks < C::KP / C::STAGE_K; ++ks) {
-                        mbar_wait(&full[stage], phase);
-                        tc_fence_after();
-                        const uint32_t b_addr = smem_u32(ring + (size_t)stage * C::STAGE_BYTES);
+                    const uint32_t b_addr = smem_u32(ring + (size_t)stage * C::STAGE_BYTES);
+                    const uint32_t b_lo0 = ((b_addr >> 4) & 0x3FFFu) | b_lbo_word;
+                    const uint32_t a_k = (uint32_t)(ks * (C::STAGE_K / 8)) * (uint32_t)(TILE_M * 16 >> 4);
+                    if (elect_one()) {
 #pragma unroll
                         for (int kk = 0; kk < C::STAGE_K / 16; ++kk) {
-                            const uint32_t a_off = (uint32_t)((ks * (C::STAGE_K / 8) + 2 * kk) * (TILE_M * 16));
-                            const uint32_t b_off = (uint32_t)(2 * kk) * b_lbo;
-                            const uint64_t ah = smem_desc(a_hi_addr + a_off, TILE_M * 16, 128);
-                            const uint64_t bh = smem_desc(b_addr + b_off, b_lbo, 128);
-                            umma_bf16(d_tmem, ah, bh, idesc, acc);
-                            acc = 1;
+                            const uint32_t a_off = a_k + (uint32_t)(2 * kk) * (uint32_t)(TILE_M * 16 >> 4);
+                            const uint32_t b_lo = b_lo0 + (uint32_t)kk * b_step;
+                            umma_bf16_lo(d_tmem, a_hi_lo + a_off, b_lo, idesc, (ks | kk) != 0);
                             if (SPLIT) {
-                                const uint64_t al = smem_desc(a_lo_addr + a_off, TILE_M * 16, 128);
-                                const uint64_t bl = smem_desc(b_addr + (uint32_t)(ncol * C::STAGE_K * 2) + b_off, b_lbo, 128);
-                                umma_bf16(d_tmem, al, bh, idesc, 1);
-                                umma_bf16(d_tmem, ah, bl, idesc, 1);
+                                const uint32_t bl_lo = b_lo + ((ncol * (uint32_t)C::STAGE_K * 2u) >> 4);
+                                umma_bf16_lo(d_tmem, a_lo_lo + a_off, b_lo, idesc, 1);
+                                umma_bf16_lo(d_tmem, a_hi_lo + a_off, bl_lo, idesc, 1);
                             }
                         }
                         umma_commit(&empty[stage]);
-                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                        if (ks == C::KP / C::STAGE_K - 1) umma_commit(&tmem_full[buf]);
                     }
-                    umma_commit(&tmem_full[buf]);
+                    __syncwarp();
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&a_free[ab]);            // every MMA reading this A buffer has completed
             }
+            if (elect_one()) umma_commit(&a_free[ab]);            // every MMA reading this A buffer has completed
+            __syncwarp();
         }
     } else if (warp >= 6) {
         // =============================== gather warps: A operand of the NEXT edge tile ==============
@@ -443,7 +473,7 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
         // =============================== epilogue warps ============================================
         const int r = threadIdx.x;                       // edge row = TMEM lane
         const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-        uint32_t tf_phase[2] = {0, 0};
+        uint32_t tf_phase = 0;                           // bit b: parity to wait on tmem_full[b]
         const uint32_t a_row_off = (uint32_t)((r >> 3) * 128 + (r & 7) * 16);
         int it = 0;
         for (int g = blockIdx.x; g < n_etiles; g += gridDim.x, ++it) {
@@ -475,8 +505,8 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
             }
 
             // ---- GEMM1 result -> ReLU -> hidden activations become the A operand of GEMM2 ----
-            mbar_wait(&tmem_full[0], tf_phase[0]);
-            tf_phase[0] ^= 1;
+            mbar_wait(&tmem_full[0], tf_phase & 1u);
+            tf_phase ^= 1u;
             tc_fence_after();
             {
                 uint32_t w[2][16];
@@ -544,8 +574,8 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                         const int k2 = (int)((tdw.x >> 16) & 0xffu), nr2 = (int)(tdw.x >> 24);
                         x_prefetch<C::XN>(xg + (tdw.z & 0xffffu), nr2 * ((k2 == 0 || k2 == 2) ? 1 : 3), xn);
                     }
-                    mbar_wait(&tmem_full[buf], tf_phase[buf]);
-                    tf_phase[buf] ^= 1;
+                    mbar_wait(&tmem_full[buf], (tf_phase >> buf) & 1u);
+                    tf_phase ^= 1u << buf;
                     tc_fence_after();
                     tmem_ld16_async(taddr, w[0]);
                     if (n_chunks == C::NCOL_S / 16) {
@@ -605,8 +635,8 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                         const int k2 = (int)((tdw.x >> 16) & 0xffu), nr2 = (int)(tdw.x >> 24);
                         x_prefetch<C::XN>(xg + (tdw.z & 0xffffu), nr2 * ((k2 == 0 || k2 == 2) ? 1 : 3), xn);
                     }
-                    mbar_wait(&tmem_full[buf], tf_phase[buf]);
-                    tf_phase[buf] ^= 1;
+                    mbar_wait(&tmem_full[buf], (tf_phase >> buf) & 1u);
+                    tf_phase ^= 1u << buf;
                     tc_fence_after();
                     tmem_ld16_async(taddr, w[0]);
                     if (n_chunks == C::NCOL_V / 16) {
