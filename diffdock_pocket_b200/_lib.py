@@ -72,6 +72,7 @@ _SIGS = {
     'ddp_tpconv_pack': (C.c_int64, [C.POINTER(TpConv), C.POINTER(TpGroup), vp, vp, vp, vp, vp, i32, vp]),
     'ddp_tpconv_umma': (i32, [C.POINTER(TpConv), vp, i32, C.POINTER(TpEdges), vp, vp]),
     'ddp_tpconv_umma_group': (i32, [vp, vp, i32, vp, vp, i32, vp]),
+    'ddp_tpconv_umma_set_trace': (i32, [vp]),
     'ddp_node_update': (i32, [vp, i32, i32, C.POINTER(Update), i32, i32, i32, vp, i32, vp]),
     'ddp_segment_mean': (i32, [vp, vp, vp, i32, i32, i32, vp, i32, vp]),
     'ddp_bond_geometry': (i32, [vp, vp, i32, vp, i32, i32, vp, vp, vp, vp]),
@@ -84,7 +85,7 @@ _SIGS = {
 EXPORTS = sorted(_SIGS)
 _LIB = None
 # kernels launched per C-ABI call (for the bench's gpu_launches claim)
-KERNELS_PER_CALL = {'ddp_radius': 3, 'ddp_knn_graph': 3, 'ddp_version': 0, 'ddp_tpconv_pack': 0}
+KERNELS_PER_CALL = {'ddp_radius': 3, 'ddp_knn_graph': 3, 'ddp_version': 0, 'ddp_tpconv_pack': 0, 'ddp_tpconv_umma_set_trace': 0}
 COUNTS = {}
 
 

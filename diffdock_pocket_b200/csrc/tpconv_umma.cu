@@ -200,6 +200,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 
 // ------------------------------------------------------------------------------------------ kernel
 // NS scalar multiplicity, NV vector multiplicity, KS padded width of one A source block (>= NS + 1).
+#ifndef DDP_UMMA_STAGE_K
+#define DDP_UMMA_STAGE_K 64
+#endif
+// K extent of one TMA slab / mbarrier round trip: more MMAs per barrier wait amortise the issue-side latencies.
+__host__ __device__ constexpr int stage_k_of(int ks, bool split) {
+    return ks == 64 ? (split ? DDP_UMMA_STAGE_K / 2 : DDP_UMMA_STAGE_K) : (split ? 16 : 32);
+}
 __host__ __device__ constexpr int rows_scalar(int ns) { return 240 / ns; }                  // basis rows per scalar tile
 __host__ __device__ constexpr int rows_vector(int nv) { return nv == 10 ? 10 : 16; }        // basis rows per vector tile
 
@@ -214,8 +221,14 @@ struct Job {
 };
 struct Jobs {
     int32_t n, f_in, f_out;
+    long long *trace;     // optional timing trace of CTA 0 (ddp_tpconv_umma_set_trace), NULL in production
     Job job[MAX_JOBS];
 };
+constexpr int TRACE_EVENTS = 8, TRACE_TILES = 256;
+// trace[(role * TRACE_TILES + tile iteration) * TRACE_EVENTS + event] = clock64 (CTA 0, one lane per role)
+__device__ __forceinline__ void trace_ev(long long *trace, int role, int iter, int ev) {
+    if (trace != nullptr && blockIdx.x == 0 && iter < TRACE_TILES) trace[(role * TRACE_TILES + iter) * TRACE_EVENTS + ev] = clock64();
+}
 
 template <int NS, int NV, int KS, bool SPLIT>
 struct Cfg {
@@ -227,7 +240,7 @@ struct Cfg {
     static constexpr int NVAL_V = ROWS_V * NV;              // weight columns of a full vector tile
     static constexpr int NCOL_V = (NVAL_V + 15) / 16 * 16;  // ... padded to the UMMA N granularity
     static constexpr int NCOL_MAX = (NCOL_S > N1 ? NCOL_S : N1);
-    static constexpr int STAGE_K = SPLIT ? 16 : 32;
+    static constexpr int STAGE_K = stage_k_of(KS, SPLIT);
     static constexpr int STAGE_BYTES = NCOL_MAX * STAGE_K * 2 * (SPLIT ? 2 : 1);
     static constexpr int A_BYTES = TILE_M * KP * 2;         // one bf16 A image
     static constexpr int NBUF = SPLIT ? 1 : 2;              // A operand buffers (next tile gathered under the current GEMM2)
@@ -240,7 +253,7 @@ struct Cfg {
     static constexpr int XN = 3 * ROWS_V > ROWS_S * 3 ? 3 * ROWS_V : ROWS_S * 3;   // floats of x one tile can read
     static_assert(NCOL_S % 16 == 0 && N1 % 16 == 0 && NCOL_MAX <= 256 && NCOL_V <= 256, "UMMA N constraints");
     static_assert(KS >= NS + 1 && KP % STAGE_K == 0, "K padding");
-    static_assert(STAGES >= 3, "weight ring too small");
+    static_assert(STAGES >= 2, "weight ring too small");
     static_assert(XN % 2 == 0, "x prefetch registers are loaded in pairs");
 };
 
@@ -358,9 +371,12 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                 const uint32_t buf = (uint32_t)(t + 1) & 1u;
                 if (t < 0) mbar_wait(&a_ready[ab], (uint32_t)(it / C::NBUF) & 1u);
                 if (t == 0) { mbar_wait(h_ready, hr_phase); hr_phase ^= 1; }
+                const int titer = it * (n_tiles + 1) + t + 1;
+                trace_ev(jobs.trace, 0, titer, 0);
                 mbar_wait(&tmem_empty[buf], ((te_phase >> buf) & 1u) ^ 1u);
                 te_phase ^= 1u << buf;
                 tc_fence_after();
+                trace_ev(jobs.trace, 0, titer, 1);
                 const uint32_t d_tmem = tmem_base + buf * 256u;
                 const uint32_t idesc = instr_desc((int)ncol);
                 // B: LBO = ncol rows x 16 B; one K = 16 step advances the start address by 2 * LBO
@@ -370,6 +386,7 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                 for (int ks = 0; ks < C::KP / C::STAGE_K; ++ks) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
+                    if (ks == 0) trace_ev(jobs.trace, 0, titer, 2);
                     const uint32_t b_addr = smem_u32(ring + (size_t)stage * C::STAGE_BYTES);
                     const uint32_t b_lo0 = ((b_addr >> 4) & 0x3FFFu) | b_lbo_word;
                     const uint32_t a_k = (uint32_t)(ks * (C::STAGE_K / 8)) * (uint32_t)(TILE_M * 16 >> 4);
@@ -391,6 +408,7 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                     __syncwarp();
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
+                trace_ev(jobs.trace, 0, titer, 3);
             }
             if (elect_one()) umma_commit(&a_free[ab]);            // every MMA reading this A buffer has completed
             __syncwarp();
@@ -505,9 +523,11 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
             }
 
             // ---- GEMM1 result -> ReLU -> hidden activations become the A operand of GEMM2 ----
+            if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1), 0);
             mbar_wait(&tmem_full[0], tf_phase & 1u);
             tf_phase ^= 1u;
             tc_fence_after();
+            if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1), 1);
             {
                 uint32_t w[2][16];
                 tmem_ld16_async(tmem_base + lane_base, w[0]);
@@ -541,6 +561,7 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
             fence_proxy_async();
             mbar_arrive(h_ready);
             mbar_arrive(&tmem_empty[0]);
+            if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1), 2);
 
             // ---- weight tiles: TMEM accumulator x tensor-product basis -> per-edge output registers ----
             // Every tile has one basis kind; its node features arrive in registers (prefetched during the previous
@@ -574,9 +595,11 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                         const int k2 = (int)((tdw.x >> 16) & 0xffu), nr2 = (int)(tdw.x >> 24);
                         x_prefetch<C::XN>(xg + (tdw.z & 0xffffu), nr2 * ((k2 == 0 || k2 == 2) ? 1 : 3), xn);
                     }
+                    if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1) + t + 1, 0);
                     mbar_wait(&tmem_full[buf], (tf_phase >> buf) & 1u);
                     tf_phase ^= 1u << buf;
                     tc_fence_after();
+                    if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1) + t + 1, 1);
                     tmem_ld16_async(taddr, w[0]);
                     if (n_chunks == C::NCOL_S / 16) {
 #pragma unroll
@@ -605,7 +628,9 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                     }
                     tc_fence_before();
                     mbar_arrive(&tmem_empty[buf]);
+                    if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1) + t + 1, 2);
                     if ((flags & 4) && valid) red_row<NS>(sum + (size_t)agg * f_out + out_off, acc);
+                    if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1) + t + 1, 3);
                 } else {
                     float bx[C::ROWS_V], by[C::ROWS_V], bz[C::ROWS_V];
                     if (kind == 2) {
@@ -635,9 +660,11 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                         const int k2 = (int)((tdw.x >> 16) & 0xffu), nr2 = (int)(tdw.x >> 24);
                         x_prefetch<C::XN>(xg + (tdw.z & 0xffffu), nr2 * ((k2 == 0 || k2 == 2) ? 1 : 3), xn);
                     }
+                    if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1) + t + 1, 0);
                     mbar_wait(&tmem_full[buf], (tf_phase >> buf) & 1u);
                     tf_phase ^= 1u << buf;
                     tc_fence_after();
+                    if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1) + t + 1, 1);
                     tmem_ld16_async(taddr, w[0]);
                     if (n_chunks == C::NCOL_V / 16) {
 #pragma unroll
@@ -678,7 +705,9 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                     }
                     tc_fence_before();
                     mbar_arrive(&tmem_empty[buf]);
+                    if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1) + t + 1, 2);
                     if ((flags & 4) && valid) red_row<3 * NV>(sum + (size_t)agg * f_out + out_off, acc);
+                    if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1) + t + 1, 3);
                 }
             }
         }
@@ -728,7 +757,7 @@ static int build_plan(const ddp_tpconv_t &c, const ddp_tp_group_t *groups, const
     Header &h = P.h;
     memset(&h, 0, sizeof(h));
     h.magic = MAGIC; h.mode = mode; h.ns = ns; h.nv = nv; h.ks = ks; h.kp = 3 * ks; h.n1 = 3 * ks;
-    h.stage_k = mode ? 16 : 32; h.f_in = c.f_in; h.f_out = c.f_out;
+    h.stage_k = stage_k_of(ks, mode != 0); h.f_in = c.f_in; h.f_out = c.f_out;
     // groups sharing (out_off, d_out) form one weight block (one accumulation of the kernel); they are contiguous in
     // w_off order.  Every tile covers rows of ONE group, so its basis kind and x stride are uniform.
     int g = 0;
@@ -876,6 +905,12 @@ static int launch_umma(const umma::Jobs &jobs, int tiles_cap, cudaStream_t st) {
     return 0;
 }
 
+static long long *g_umma_trace = nullptr;
+extern "C" int ddp_tpconv_umma_set_trace(void *trace_dev) {
+    g_umma_trace = static_cast<long long *>(trace_dev);
+    return 2 * umma::TRACE_TILES * umma::TRACE_EVENTS;      // int64 slots the buffer must hold
+}
+
 extern "C" int ddp_tpconv_umma_group(const ddp_tpconv_t *const *convs, const void *const *packed, int32_t mode,
                                      const ddp_tpconv_edges_t *const *edges, float *const *sums, int32_t n_jobs, void *stream) {
     if (!convs || !packed || !edges || !sums) return DDP_E_ARG;
@@ -886,6 +921,7 @@ extern "C" int ddp_tpconv_umma_group(const ddp_tpconv_t *const *convs, const voi
     const ddp_tpconv_t &c0 = *convs[0];
     jobs.f_in = c0.f_in;
     jobs.f_out = c0.f_out;
+    jobs.trace = g_umma_trace;
     int tiles_cap = 0;
     for (int j = 0; j < n_jobs; ++j) {
         if (!convs[j] || !packed[j] || !edges[j] || !sums[j]) return DDP_E_ARG;

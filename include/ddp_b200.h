@@ -180,6 +180,11 @@ int ddp_tpconv_umma(const ddp_tpconv_t *conv, const void *packed, int32_t mode,
 int ddp_tpconv_umma_group(const ddp_tpconv_t *const *convs, const void *const *packed, int32_t mode,
                           const ddp_tpconv_edges_t *const *edges, float *const *sums, int32_t n_jobs, void *stream);
 
+/* Developer aid: when trace_dev != NULL, CTA 0 of every following tensor-core conv launch records clock64()
+ * timestamps of its MMA-issue and epilogue roles per weight tile into trace_dev (device int64 buffer); NULL turns
+ * it off.  Returns the number of int64 slots the buffer must hold.  Not part of the reference surface. */
+int ddp_tpconv_umma_set_trace(void *trace_dev);
+
 /* node update (all_atom_score_model.py:315-324 + scatter-mean + e3nn BatchNorm eval, score_model.py:117,123):
  *   new[n][c] = (c < f_old ? old[n][c] : 0) + sum_u live_u * (sum_u[n][c] / max(deg_u[n],1) * scale_u[c] + shift_u[c])
  * live_u = (*n_edges_u > 0) reproduces `return 0` for an empty edge set (score_model.py:109-111).
