@@ -12,6 +12,10 @@ tr_z, rot_z, tor_z, sidechain_tor_z per step), but the loop body is restructured
   N x (n_sc + 1) CPU round trips per step (utils/sampling.py:245-251);
 * poses return to the host once, after the last step (and the confidence pass).
 
+``use_graph=True`` additionally captures each mini-batch's whole step as a CUDA graph (worth it only when the
+plans outlive many calls or the batch is so small that launches dominate: capture + instantiation cost ~40 ms per
+mini-batch, while at batch 20 the eager launch stream already runs ~4x ahead of the GPU).
+
 SVGD (svgd_weight > 0) and ``pivot`` are outside the accelerated path and raise NotImplementedError.
 """
 import copy
@@ -162,7 +166,7 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
              t_schedule=None, batch_size=32, no_final_step_noise=False, pivot=None, return_full_trajectory=False,
              svgd_weight=0.0, svgd_repulsive_weight=1.0, svgd_only=False, svgd_rot_rel_weight=1.0, svgd_tor_rel_weight=1.0,
              svgd_sidechain_tor_rel_weight=1.0, temp_sampling=1.0, temp_psi=0.0, temp_sigma_data=0.5,
-             flexible_sidechains=None, max_steps=None, trace=None, use_graph=True):
+             flexible_sidechains=None, max_steps=None, trace=None, use_graph=False):
     if svgd_weight > 0 or pivot is not None or asyncronous_noise_schedule:
         raise NotImplementedError('SVGD / pivot / asynchronous schedules are outside the accelerated path')
     flexible_sidechains = model_args.flexible_sidechains if flexible_sidechains is None else flexible_sidechains
@@ -179,14 +183,16 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
     trajectory, sidechain_trajectory = [], []
     schedules = (tr_schedule, rot_schedule, tor_schedule, sidechain_tor_schedule)
 
-    # one resident plan + pose state (+ captured step graph) per mini-batch
+    # one resident plan + pose state (+ optionally a captured step graph) per mini-batch; the plans are built lazily
+    # inside step 0 so that the GPU already works on mini-batch k while the host collates mini-batch k + 1
     chunks = [list(range(i, min(i + batch_size, N))) for i in range(0, N, batch_size)]
-    with torch.no_grad():
-        runners = [StepRunner(model, [data_list[i] for i in idx], flexible_sidechains, ma.no_torsion, use_graph=use_graph and trace is None)
-                   for idx in chunks]
-    poses = [r.ps for r in runners]
-    T_tot = sum(p.T for p in poses)
-    S_tot = sum(p.S for p in poses)
+    use_graph = bool(use_graph) and trace is None
+    runners = [None] * len(chunks)
+    n_tor = [0 if ma.no_torsion else sum(int(data_list[i]['ligand'].edge_mask.sum()) for i in idx) for idx in chunks]
+    n_sc = [sum(int(data_list[i]['flexResidues'].edge_idx.shape[0]) for i in idx
+                if flexible_sidechains and 'flexResidues' in data_list[i] and 'edge_idx' in data_list[i]['flexResidues'])
+            for idx in chunks]
+    T_tot, S_tot = sum(n_tor), sum(n_sc)
     n_steps = inference_steps if max_steps is None else min(max_steps, inference_steps)
     M = 6 * N + T_tot + S_tot
     # Noise for all steps is drawn up front, in the reference's order (per step: tr_z, rot_z, tor_z,
@@ -204,20 +210,30 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
             if flexible_sidechains:
                 noise_host[t_idx, 6 * N + T_tot:] = draw((S_tot,))
 
+    conf_plans = None
+
+    def write_back_all():
+        for idx, r in zip(chunks, runners):
+            if r is not None:
+                r.ps.write_back([data_list[i] for i in idx])
+
     with torch.no_grad():
         for t_idx in range(n_steps):
             t, coef = step_coefficients(t_idx, inference_steps, schedules, t_to_sigma, ma, ode, temp_sampling, temp_psi,
                                         temp_sigma_data, flexible_sidechains)
             if return_full_trajectory:
-                for idx, p in zip(chunks, poses):
-                    p.write_back([data_list[i] for i in idx])
+                write_back_all()
                 trajectory.append(np.asarray([g['ligand'].pos.cpu().numpy() for g in data_list]))
                 sidechain_trajectory.append(np.asarray([]) if no_sidechains_in_batch or not flexible_sidechains else np.asarray(
                     [g['atom'].pos.cpu().numpy()[g['flexResidues'].subcomponents.unique().cpu().numpy()] for g in data_list]))
             z = noise_host[t_idx]
             s0 = t0 = c0 = 0
             step_scores = []
-            for idx, r in zip(chunks, runners):
+            for k, idx in enumerate(chunks):
+                if runners[k] is None:
+                    runners[k] = StepRunner(model, [data_list[i] for i in idx], flexible_sidechains, ma.no_torsion, use_graph=use_graph)
+                    assert (runners[k].T, runners[k].S) == (n_tor[k], n_sc[k])
+                r = runners[k]
                 b = len(idx)
                 row = torch.cat([z[3 * s0:3 * (s0 + b)], z[3 * N + 3 * s0:3 * N + 3 * (s0 + b)], z[6 * N + t0:6 * N + t0 + r.T],
                                  z[6 * N + T_tot + c0:6 * N + T_tot + c0 + r.S]])
@@ -227,9 +243,13 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
                 s0, t0, c0 = s0 + b, t0 + r.T, c0 + r.S
             if trace is not None:
                 trace.append(tuple(torch.cat([s[k] for s in step_scores]).cpu() for k in range(4)))
+            if conf_plans is None and confidence_model is not None:
+                # confidence plans (static tensors, workspaces) are collated and uploaded while the GPU runs step 0;
+                # the final poses reach them by device-to-device copies after the last step
+                conf_plans = [confidence_model.make_plan(Batch.from_data_list(
+                    [(filtering_data_list if filtering_data_list is not None else data_list)[i] for i in idx])) for idx in chunks]
             if visualization_list is not None or sidechain_visualization_list is not None:
-                for idx, ps in zip(chunks, poses):
-                    ps.write_back([data_list[i] for i in idx])
+                write_back_all()
                 if visualization_list is not None:
                     for i, v in enumerate(visualization_list):
                         v.add((data_list[i]['ligand'].pos + data_list[i].original_center).detach().cpu(), part=1, order=t_idx + 2)
@@ -237,22 +257,24 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
                     for i, v in enumerate(sidechain_visualization_list):
                         v.append(data_list[i]['atom'].pos + data_list[i]['original_center'])
 
-        for idx, ps in zip(chunks, poses):
-            ps.write_back([data_list[i] for i in idx])
         confidence = None
         if confidence_model is not None:                              # utils/sampling.py:263-281
+            if conf_plans is None:                                    # n_steps == 0
+                conf_plans = [confidence_model.make_plan(Batch.from_data_list(
+                    [(filtering_data_list if filtering_data_list is not None else data_list)[i] for i in idx])) for idx in chunks]
             conf = []
-            for idx, ps in zip(chunks, poses):
-                if filtering_data_list is not None:
-                    sub = [filtering_data_list[i] for i in idx]
-                    for g, i in zip(sub, idx):
-                        g['ligand'].pos = data_list[i]['ligand'].pos
-                else:
-                    sub = [data_list[i] for i in idx]
-                cpl = confidence_model.make_plan(Batch.from_data_list(sub))
+            for idx, r, cpl in zip(chunks, runners, conf_plans):
+                if r is not None:
+                    cpl.lig_pos.copy_(r.pl.lig_pos)
+                    if filtering_data_list is None:                   # filtering graphs keep their own receptor atoms
+                        cpl.atom_pos.copy_(r.pl.atom_pos)
                 zt = torch.zeros(len(idx))
                 conf.append(confidence_model.run_plan(cpl, {'tr': zt, 'rot': zt, 'tor': zt, 'sc_tor': zt}).clone())
             confidence = torch.cat(conf, dim=0)
+        write_back_all()                                              # the one device->host read of the poses
+        if filtering_data_list is not None:
+            for i, g in enumerate(filtering_data_list):
+                g['ligand'].pos = data_list[i]['ligand'].pos
     if return_full_trajectory:
         return data_list, confidence, trajectory, sidechain_trajectory
     return data_list, confidence

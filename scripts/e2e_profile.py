@@ -1,0 +1,47 @@
+"""cProfile of one end-to-end sampling() call (host graphs in, host poses out) after a warm-up call."""
+import argparse
+import cProfile
+import copy
+import os
+import pstats
+import sys
+import time
+from functools import partial
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from diffdock_pocket_b200 import diffusion_utils as du, sampling as ps, utils  # noqa: E402
+
+args = argparse.Namespace(samples=40, batch_size=20, inference_steps=20, workload='3dpf_apo')
+dev = torch.device('cuda:0')
+model, conf, sa, ca = utils.build_models(dev, seed=0)
+model.conv_mode = conf.conv_mode = 'bf16'
+g, dl0 = bench.workload(args, 0)
+sch = du.get_t_schedule('expbeta', 20)
+t2s = partial(du.t_to_sigma, args=sa)
+kw = dict(confidence_model=conf, filtering_model_args=ca, batch_size=20, **bench.TEMP)
+
+
+def run(dl):
+    torch.manual_seed(7)
+    out, c = ps.sampling(dl, model, 20, sch, sch, sch, sch, dev, t2s, sa, **kw)
+    poses = torch.stack([o['ligand'].pos for o in out])
+    torch.cuda.synchronize()
+    return poses, c
+
+
+for _ in range(2):
+    run(copy.deepcopy(dl0))
+dl = copy.deepcopy(dl0)
+t0 = time.time()
+run(dl)
+print('e2e wall ms', (time.time() - t0) * 1e3)
+dl = copy.deepcopy(dl0)
+pr = cProfile.Profile()
+pr.enable()
+run(dl)
+pr.disable()
+pstats.Stats(pr).sort_stats('cumulative').print_stats(45)
