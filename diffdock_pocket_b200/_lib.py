@@ -114,7 +114,7 @@ def build(verbose=False):
                  + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cuh')])
     if os.path.exists(SO_PATH) and os.path.getmtime(SO_PATH) >= newest:
         return SO_PATH
-    cmd = ['nvcc'] + NVCC_FLAGS + srcs + ['-o', SO_PATH]
+    cmd = ['nvcc'] + NVCC_FLAGS + os.environ.get('DDP_NVCC_FLAGS', '').split() + srcs + ['-o', SO_PATH]
     if verbose:
         print(' '.join(cmd))
     subprocess.check_call(cmd)

@@ -77,6 +77,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// Split-phase barrier test for the MMA issue loop: mbar_test_pN starts a non-blocking phase test whose predicate
+// lives in a PTX register declared once per kernel (DDP_DECLARE_TEST_PREDS); mbar_finish_pN consumes it later (falling
+// back to the blocking wait), so the ~100-cycle shared-memory round trip overlaps the tcgen05.mma issue in between.
+#define DDP_DECLARE_TEST_PREDS() asm volatile(".reg .pred ddp_p0, ddp_p1, ddp_p2;")
+#define DDP_MBAR_SPLIT(N)                                                                                                   \
+    __device__ __forceinline__ void mbar_test_p##N(uint64_t *bar, uint32_t parity) {                                        \
+        asm volatile("mbarrier.test_wait.parity.shared::cta.b64 ddp_p" #N ", [%0], %1;" ::"r"(smem_u32(bar)), "r"(parity)   \
+                     : "memory");                                                                                           \
+    }                                                                                                                       \
+    __device__ __forceinline__ void mbar_finish_p##N(uint64_t *bar, uint32_t parity) {                                      \
+        asm volatile(                                                                                                       \
+            "{\n\t"                                                                                                         \
+            "@ddp_p" #N " bra D_%=;\n\t"                                                                                    \
+            "W_%=:\n\t"                                                                                                     \
+            "mbarrier.try_wait.parity.shared::cta.b64 ddp_p" #N ", [%0], %1;\n\t"                                           \
+            "@!ddp_p" #N " bra W_%=;\n\t"                                                                                   \
+            "D_%=:\n\t}\n" ::"r"(smem_u32(bar)),                                                                           \
+            "r"(parity)                                                                                                     \
+            : "memory");                                                                                                    \
+    }
+DDP_MBAR_SPLIT(0)
+DDP_MBAR_SPLIT(1)
+DDP_MBAR_SPLIT(2)
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
@@ -118,6 +141,23 @@ __device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uin
         "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI)
         : "memory");
 }
+// A operand from tensor memory (lane = row, column c = packed bf16 pair k = 2c, 2c + 1): no shared-memory read of A,
+// which in the SS form costs ~43 exposed cycles per MMA (profiles/r1_umma_microbench.txt)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // One lane of the (converged) warp: the tcgen05 / TMA issue paths run warp-uniform and only the instruction itself
 // is predicated, which keeps descriptors in uniform registers instead of per-lane broadcasts.
 __device__ __forceinline__ bool elect_one() {
@@ -172,6 +212,12 @@ __device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16]) {
                  :
                  : "memory");
 }
+__device__ __forceinline__ void tmem_ld4_async(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void red_add_v2(float *p, float a, float b) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
@@ -200,15 +246,27 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 
 // ------------------------------------------------------------------------------------------ kernel
 // NS scalar multiplicity, NV vector multiplicity, KS padded width of one A source block (>= NS + 1).
-#ifndef DDP_UMMA_STAGE_K
-#define DDP_UMMA_STAGE_K 64
+// K extent of one TMA slab / mbarrier round trip: 4 MMAs per wait amortise the issue-side latencies while the ring
+// still holds ~2 weight tiles in flight (whole-tile slabs with 2 slots measured slower: the first MMA of a tile then
+// waits for all of its 72 KB).
+__host__ __device__ constexpr int stage_k_of(int ks, bool split) { return ks == 64 ? (split ? 32 : 64) : (split ? 16 : 32); }
+// Tile shapes.  TS variant (hidden activations as a TMEM-resident A operand, single-pass bf16 only): a scalar tile
+// covers ROWS_S basis rows x NS outputs padded to N = 192; TMEM holds two such fp32 accumulators next to the bf16
+// hidden activations (2 x 208 + 96 columns = 512).  SS variant (A from shared memory; always used by the split mode):
+// N = 240 scalar tiles, two 256-column accumulators.  A vector tile covers up to 2 NV basis rows x NV outputs, which
+// the epilogue reads in two passes of NV rows.
+// Measured on B200 (3dpf batch of 20, W = 10000 layers): SS 1.24 PFLOP/s, TS 1.04 PFLOP/s.  TS issues faster MMAs
+// (106 vs 148 cycles) but its smaller tiles pay the per-tile hand-over (~500 cycles on both the issue and the epilogue
+// side) more often and leave the tensor pipe idle in between, whereas in SS mode the exposed A-operand read hides
+// those gaps.  TS stays selectable (-DDDP_UMMA_TS=1) for further work on the hand-over.
+#ifndef DDP_UMMA_TS
+#define DDP_UMMA_TS 0
 #endif
-// K extent of one TMA slab / mbarrier round trip: more MMAs per barrier wait amortise the issue-side latencies.
-__host__ __device__ constexpr int stage_k_of(int ks, bool split) {
-    return ks == 64 ? (split ? DDP_UMMA_STAGE_K / 2 : DDP_UMMA_STAGE_K) : (split ? 16 : 32);
-}
-__host__ __device__ constexpr int rows_scalar(int ns) { return 240 / ns; }                  // basis rows per scalar tile
-__host__ __device__ constexpr int rows_vector(int nv) { return nv == 10 ? 10 : 16; }        // basis rows per vector tile
+__host__ __device__ constexpr bool use_ts(bool split) { return DDP_UMMA_TS != 0 && !split; }
+__host__ __device__ constexpr int rows_scalar(int ns, bool ts) { return (ts ? 192 : 240) / ns; }
+__host__ __device__ constexpr int ncol_scalar(int ns, bool ts) { return (rows_scalar(ns, ts) * ns + 15) / 16 * 16; }
+__host__ __device__ constexpr int rows_vector(int nv) { return 2 * nv; }
+__host__ __device__ constexpr int ncol_vector(int nv, int n_rows) { return (n_rows * nv + 15) / 16 * 16; }
 
 constexpr int MAX_JOBS = 9;
 constexpr int N_EPI = 128, N_GATHER = 64, N_THREADS = 256;
@@ -234,24 +292,31 @@ template <int NS, int NV, int KS, bool SPLIT>
 struct Cfg {
     static constexpr int KP = 3 * KS;                       // padded K of both GEMMs (and padded hidden width N1)
     static constexpr int N1 = KP;
-    static constexpr int ROWS_S = rows_scalar(NS);
-    static constexpr int NCOL_S = ROWS_S * NS;
+    static constexpr bool TS = use_ts(SPLIT);               // hidden activations as a TMEM-resident A operand
+    static constexpr int ROWS_S = rows_scalar(NS, TS);
+    static constexpr int NVAL_S = ROWS_S * NS;              // weight columns of a scalar tile
+    static constexpr int NCOL_S = ncol_scalar(NS, TS);      // ... padded to the UMMA N granularity
     static constexpr int ROWS_V = rows_vector(NV);
-    static constexpr int NVAL_V = ROWS_V * NV;              // weight columns of a full vector tile
-    static constexpr int NCOL_V = (NVAL_V + 15) / 16 * 16;  // ... padded to the UMMA N granularity
-    static constexpr int NCOL_MAX = (NCOL_S > N1 ? NCOL_S : N1);
+    static constexpr int PASS_COLS = NV * NV;               // weight columns the epilogue handles per pass (NV rows)
+    static constexpr int NCOL_V = ncol_vector(NV, ROWS_V);
+    static constexpr int NCOL_MAX = (NCOL_S > N1 ? (NCOL_S > NCOL_V ? NCOL_S : NCOL_V) : (N1 > NCOL_V ? N1 : NCOL_V));
+    static constexpr int ACC_STRIDE = TS ? 208 : 256;       // TMEM columns between the two accumulators
+    static constexpr int H_COL = 2 * ACC_STRIDE;            // TS: first TMEM column of the hidden activations (KP / 2 columns)
     static constexpr int STAGE_K = stage_k_of(KS, SPLIT);
     static constexpr int STAGE_BYTES = NCOL_MAX * STAGE_K * 2 * (SPLIT ? 2 : 1);
     static constexpr int A_BYTES = TILE_M * KP * 2;         // one bf16 A image
-    static constexpr int NBUF = SPLIT ? 1 : 2;              // A operand buffers (next tile gathered under the current GEMM2)
+    // A operand buffers in shared memory.  TS: one (free again as soon as GEMM1 has run); SS: two, so that the next
+    // edge tile is gathered under the current GEMM2 (split mode: one, its hi + lo images are already 96 KB)
+    static constexpr int NBUF = (TS || SPLIT) ? 1 : 2;
     static constexpr int A_TOTAL = A_BYTES * (SPLIT ? 2 : 1) * NBUF;
     static constexpr int MAX_TILES = 64;
     static constexpr int FIXED = 1024 + A_TOTAL + MAX_TILES * (int)sizeof(TileDesc) + 512;
     static constexpr int STAGES_FIT = (220 * 1024 - FIXED) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_FIT > 12 ? 12 : STAGES_FIT;
     static constexpr size_t SMEM = (size_t)FIXED + (size_t)STAGES * STAGE_BYTES;
-    static constexpr int XN = 3 * ROWS_V > ROWS_S * 3 ? 3 * ROWS_V : ROWS_S * 3;   // floats of x one tile can read
-    static_assert(NCOL_S % 16 == 0 && N1 % 16 == 0 && NCOL_MAX <= 256 && NCOL_V <= 256, "UMMA N constraints");
+    static constexpr int XN_RAW = 3 * NV > 3 * ROWS_S ? 3 * NV : 3 * ROWS_S;   // floats of x one tile reads (x (x) s1 tiles: 2 NV,
+    static constexpr int XN = XN_RAW + (XN_RAW & 1);                              //  stride-3 kinds: NV or ROWS_S rows of 3)
+    static_assert(N1 % 16 == 0 && NCOL_MAX <= ACC_STRIDE && (TS ? H_COL + KP / 2 : H_COL) <= 512, "UMMA N / TMEM budget");
     static_assert(KS >= NS + 1 && KP % STAGE_K == 0, "K padding");
     static_assert(STAGES >= 2, "weight ring too small");
     static_assert(XN % 2 == 0, "x prefetch registers are loaded in pairs");
@@ -356,12 +421,20 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
         }
     } else if (warp == 5) {
         // =============================== MMA issuer (warp-uniform, one elected lane issues) =======
+        // The tensor pipe queues only ~1 MMA beyond the one executing and tcgen05.mma issue blocks while it is full, so
+        // anything between two issues longer than one MMA (~100 cycles) drains it.  Barrier round trips are therefore
+        // split-phase: the test for the NEXT K group's slab (p0), the next tile's accumulator (p1) and the next edge
+        // tile's A operand (p2) start before the current group is issued and are consumed after it.
+        DDP_DECLARE_TEST_PREDS();
         uint32_t stage = 0, phase = 0;
         uint32_t te_phase = 0;               // bit b: parity to wait on tmem_empty[b]
         uint32_t hr_phase = 0;
+        bool pre_a = false, pre_te = false, pre_full = false;   // waits of the upcoming tile / group already taken
         int it = 0;
+        constexpr int NG = C::KP / C::STAGE_K;
         for (int g = blockIdx.x; g < n_etiles; g += gridDim.x, ++it) {
             const int ab = it % C::NBUF;
+            const bool more = g + (int)gridDim.x < n_etiles;
             const uint32_t a_hi_addr = smem_u32(a_base + (size_t)ab * C::A_BYTES * (SPLIT ? 2 : 1));
             // descriptor low words: A has LBO = 128 rows x 16 B between the two K chunks of one MMA
             const uint32_t a_hi_lo = ((a_hi_addr >> 4) & 0x3FFFu) | ((uint32_t)(TILE_M * 16 >> 4) << 16);
@@ -369,33 +442,55 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
             for (int t = -1; t < n_tiles; ++t) {
                 const uint32_t ncol = (t < 0) ? (uint32_t)C::N1 : (uint32_t)tiles[t].n_cols;
                 const uint32_t buf = (uint32_t)(t + 1) & 1u;
-                if (t < 0) mbar_wait(&a_ready[ab], (uint32_t)(it / C::NBUF) & 1u);
-                if (t == 0) { mbar_wait(h_ready, hr_phase); hr_phase ^= 1; }
                 const int titer = it * (n_tiles + 1) + t + 1;
                 trace_ev(jobs.trace, 0, titer, 0);
-                mbar_wait(&tmem_empty[buf], ((te_phase >> buf) & 1u) ^ 1u);
-                te_phase ^= 1u << buf;
+                if (t < 0 && !pre_a) mbar_wait(&a_ready[ab], (uint32_t)(it / C::NBUF) & 1u);
+                if (t == 0) { mbar_wait(h_ready, hr_phase); hr_phase ^= 1; }
+                if (!pre_te) {
+                    mbar_wait(&tmem_empty[buf], ((te_phase >> buf) & 1u) ^ 1u);
+                    te_phase ^= 1u << buf;
+                }
+                if (!pre_full) mbar_wait(&full[stage], phase);
                 tc_fence_after();
                 trace_ev(jobs.trace, 0, titer, 1);
-                const uint32_t d_tmem = tmem_base + buf * 256u;
+                const uint32_t d_tmem = tmem_base + buf * (uint32_t)C::ACC_STRIDE;
                 const uint32_t idesc = instr_desc((int)ncol);
                 // B: LBO = ncol rows x 16 B; one K = 16 step advances the start address by 2 * LBO
                 const uint32_t b_lbo_word = ncol << 16;
                 const uint32_t b_step = 2u * ncol;                      // (2 * ncol * 16 B) >> 4
-#pragma unroll 1
-                for (int ks = 0; ks < C::KP / C::STAGE_K; ++ks) {
-                    mbar_wait(&full[stage], phase);
-                    tc_fence_after();
+                const bool ts = C::TS && t >= 0;                        // GEMM2 reads the hidden activations from TMEM
+                // what may be taken early for the tile after this one (never anything that needs THIS tile's MMAs to
+                // complete: tile 0's h_ready; the accumulator this tile writes; in SS mode the A buffer)
+                const bool wrap = t + 1 == n_tiles;
+                const bool nx_any = t != -1 && (!wrap || more);
+                const bool nx_a = nx_any && wrap && (C::TS || C::NBUF == 2);
+                const uint32_t nbuf = wrap ? 0u : (uint32_t)(t + 2) & 1u;
+                const bool nx_te = nx_any && nbuf != buf;
+                const uint32_t nte_par = ((te_phase >> nbuf) & 1u) ^ 1u;
+                const uint32_t na_par = (uint32_t)((it + 1) / C::NBUF) & 1u;
+#pragma unroll
+                for (int ks = 0; ks < NG; ++ks) {
+                    // the slab of this group has landed (blocking wait above, or the finish of the previous group)
+                    uint32_t ns_ = stage + 1, np_ = phase;
+                    if (ns_ == C::STAGES) { ns_ = 0; np_ ^= 1; }
+                    const bool nx_full = ks + 1 < NG || nx_any;          // is there a next group whose slab we may test?
+                    if (nx_full) mbar_test_p0(&full[ns_], np_);
+                    if (ks == NG - 1) {
+                        if (nx_te) mbar_test_p1(&tmem_empty[nbuf], nte_par);
+                        if (nx_a) mbar_test_p2(&a_ready[(it + 1) % C::NBUF], na_par);
+                    }
                     if (ks == 0) trace_ev(jobs.trace, 0, titer, 2);
                     const uint32_t b_addr = smem_u32(ring + (size_t)stage * C::STAGE_BYTES);
                     const uint32_t b_lo0 = ((b_addr >> 4) & 0x3FFFu) | b_lbo_word;
                     const uint32_t a_k = (uint32_t)(ks * (C::STAGE_K / 8)) * (uint32_t)(TILE_M * 16 >> 4);
+                    const uint32_t a_t = tmem_base + (uint32_t)C::H_COL + (uint32_t)(ks * (C::STAGE_K / 2));
                     if (elect_one()) {
 #pragma unroll
                         for (int kk = 0; kk < C::STAGE_K / 16; ++kk) {
                             const uint32_t a_off = a_k + (uint32_t)(2 * kk) * (uint32_t)(TILE_M * 16 >> 4);
                             const uint32_t b_lo = b_lo0 + (uint32_t)kk * b_step;
-                            umma_bf16_lo(d_tmem, a_hi_lo + a_off, b_lo, idesc, (ks | kk) != 0);
+                            if (ts) umma_bf16_ts(d_tmem, a_t + (uint32_t)(8 * kk), b_lo, idesc, (ks | kk) != 0);
+                            else umma_bf16_lo(d_tmem, a_hi_lo + a_off, b_lo, idesc, (ks | kk) != 0);
                             if (SPLIT) {
                                 const uint32_t bl_lo = b_lo + ((ncol * (uint32_t)C::STAGE_K * 2u) >> 4);
                                 umma_bf16_lo(d_tmem, a_lo_lo + a_off, b_lo, idesc, 1);
@@ -403,15 +498,29 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                             }
                         }
                         umma_commit(&empty[stage]);
-                        if (ks == C::KP / C::STAGE_K - 1) umma_commit(&tmem_full[buf]);
+                        if (ks == NG - 1) {
+                            umma_commit(&tmem_full[buf]);
+                            // the smem A buffer is free once its last reader has run: GEMM1 (TS) / the last GEMM2 tile (SS)
+                            if (C::TS ? t < 0 : t == n_tiles - 1) umma_commit(&a_free[ab]);
+                        }
                     }
                     __syncwarp();
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    if (nx_full) mbar_finish_p0(&full[ns_], np_);
+                    if (ks == NG - 1) {
+                        if (nx_te) { mbar_finish_p1(&tmem_empty[nbuf], nte_par); te_phase ^= 1u << nbuf; }
+                        if (nx_a) mbar_finish_p2(&a_ready[(it + 1) % C::NBUF], na_par);
+                        pre_full = nx_full; pre_te = nx_te; pre_a = nx_a;
+                    }
+                    tc_fence_after();
+                    stage = ns_; phase = np_;
                 }
                 trace_ev(jobs.trace, 0, titer, 3);
+                if (jobs.trace != nullptr && blockIdx.x == 0 && titer < TRACE_TILES) {
+                    unsigned long long ns_now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_now));
+                    jobs.trace[(0 * TRACE_TILES + titer) * TRACE_EVENTS + 4] = (long long)ns_now;
+                }
             }
-            if (elect_one()) umma_commit(&a_free[ab]);            // every MMA reading this A buffer has completed
-            __syncwarp();
         }
     } else if (warp >= 6) {
         // =============================== gather warps: A operand of the NEXT edge tile ==============
@@ -523,6 +632,8 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
             }
 
             // ---- GEMM1 result -> ReLU -> hidden activations become the A operand of GEMM2 ----
+            // TS: packed bf16 pairs into tensor memory (column c of the lane = k 2c, 2c + 1); SS (split mode): hi / lo
+            // images back into the shared-memory A buffer in core-matrix order.
             if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1), 0);
             mbar_wait(&tmem_full[0], tf_phase & 1u);
             tf_phase ^= 1u;
@@ -538,27 +649,35 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                     float v[16];
 #pragma unroll
                     for (int q = 0; q < 16; ++q) v[q] = fmaxf(__uint_as_float(w[c16 & 1][q]), 0.f);
+                    if (C::TS) {
+                        uint32_t pk[8];
 #pragma unroll
-                    for (int h8 = 0; h8 < 2; ++h8) {
-                        uint4 hi;
-                        hi.x = pack_bf16x2(v[8 * h8 + 0], v[8 * h8 + 1]); hi.y = pack_bf16x2(v[8 * h8 + 2], v[8 * h8 + 3]);
-                        hi.z = pack_bf16x2(v[8 * h8 + 4], v[8 * h8 + 5]); hi.w = pack_bf16x2(v[8 * h8 + 6], v[8 * h8 + 7]);
-                        const uint32_t off = (uint32_t)((c16 * 2 + h8) * (TILE_M * 16)) + a_row_off;
-                        *reinterpret_cast<uint4 *>(a_hi + off) = hi;
-                        if (SPLIT) {
-                            float u[8];
+                        for (int q = 0; q < 8; ++q) pk[q] = pack_bf16x2(v[2 * q], v[2 * q + 1]);
+                        tmem_st8(tmem_base + lane_base + (uint32_t)(C::H_COL + c16 * 8), pk);
+                    } else {
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) u[q] = v[8 * h8 + q] - __bfloat162float(__float2bfloat16_rn(v[8 * h8 + q]));
-                            uint4 lo;
-                            lo.x = pack_bf16x2(u[0], u[1]); lo.y = pack_bf16x2(u[2], u[3]);
-                            lo.z = pack_bf16x2(u[4], u[5]); lo.w = pack_bf16x2(u[6], u[7]);
-                            *reinterpret_cast<uint4 *>(a_lo + off) = lo;
+                        for (int h8 = 0; h8 < 2; ++h8) {
+                            uint4 hi;
+                            hi.x = pack_bf16x2(v[8 * h8 + 0], v[8 * h8 + 1]); hi.y = pack_bf16x2(v[8 * h8 + 2], v[8 * h8 + 3]);
+                            hi.z = pack_bf16x2(v[8 * h8 + 4], v[8 * h8 + 5]); hi.w = pack_bf16x2(v[8 * h8 + 6], v[8 * h8 + 7]);
+                            const uint32_t off = (uint32_t)((c16 * 2 + h8) * (TILE_M * 16)) + a_row_off;
+                            *reinterpret_cast<uint4 *>(a_hi + off) = hi;
+                            if (SPLIT) {
+                                float u[8];
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) u[q] = v[8 * h8 + q] - __bfloat162float(__float2bfloat16_rn(v[8 * h8 + q]));
+                                uint4 lo;
+                                lo.x = pack_bf16x2(u[0], u[1]); lo.y = pack_bf16x2(u[2], u[3]);
+                                lo.z = pack_bf16x2(u[4], u[5]); lo.w = pack_bf16x2(u[6], u[7]);
+                                *reinterpret_cast<uint4 *>(a_lo + off) = lo;
+                            }
                         }
                     }
                 }
             }
+            if (C::TS) tmem_wait_st();
             tc_fence_before();
-            fence_proxy_async();
+            if (!C::TS) fence_proxy_async();
             mbar_arrive(h_ready);
             mbar_arrive(&tmem_empty[0]);
             if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1), 2);
@@ -566,15 +685,14 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
             // ---- weight tiles: TMEM accumulator x tensor-product basis -> per-edge output registers ----
             // Every tile has one basis kind; its node features arrive in registers (prefetched during the previous
             // tile); the accumulator is read 16 columns at a time with the next tcgen05.ld in flight under the FMAs.
-            // Full tiles take a branch-free path.
+            // Scalar tiles: ROWS_S rows in one pass; vector tiles: up to 2 NV rows in two passes of NV rows.
             float acc[NS];
 #pragma unroll 1
             for (int t = 0; t < n_tiles; ++t) {
-                const int n_cols = (int)(tdw.x & 0xffffu), kind = (int)((tdw.x >> 16) & 0xffu), n_rows = (int)(tdw.x >> 24);
+                const int kind = (int)((tdw.x >> 16) & 0xffu), n_rows = (int)(tdw.x >> 24);
                 const int out_off = (int)(tdw.y & 0xffffu), flags = (int)((tdw.y >> 16) & 0xffu);
-                const int n_chunks = n_cols >> 4;
-                const int buf = (t + 1) & 1;
-                const uint32_t taddr = tmem_base + lane_base + (uint32_t)buf * 256u;
+                const uint32_t buf = (uint32_t)(t + 1) & 1u;
+                const uint32_t taddr = tmem_base + lane_base + buf * (uint32_t)C::ACC_STRIDE;
                 if (flags & 1) {
 #pragma unroll
                     for (int o = 0; o < NS; ++o) acc[o] = 0.f;
@@ -601,29 +719,15 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                     tc_fence_after();
                     if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1) + t + 1, 1);
                     tmem_ld16_async(taddr, w[0]);
-                    if (n_chunks == C::NCOL_S / 16) {
+                    constexpr int NCH = (C::NVAL_S + 15) / 16;
 #pragma unroll
-                        for (int c16 = 0; c16 < C::NCOL_S / 16; ++c16) {
-                            tmem_wait16(w[c16 & 1]);
-                            if (c16 + 1 < C::NCOL_S / 16) tmem_ld16_async(taddr + (uint32_t)((c16 + 1) * 16), w[(c16 + 1) & 1]);
+                    for (int c16 = 0; c16 < NCH; ++c16) {
+                        tmem_wait16(w[c16 & 1]);
+                        if (c16 + 1 < NCH) tmem_ld16_async(taddr + (uint32_t)((c16 + 1) * 16), w[(c16 + 1) & 1]);
 #pragma unroll
-                            for (int q = 0; q < 16; ++q) {
-                                const int c = c16 * 16 + q;
-                                acc[c % NS] = fmaf(__uint_as_float(w[c16 & 1][q]), b[c / NS], acc[c % NS]);
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int c16 = 0; c16 < C::NCOL_S / 16; ++c16) {
-                            if (c16 < n_chunks) {
-                                tmem_wait16(w[c16 & 1]);
-                                if (c16 + 1 < C::NCOL_S / 16 && c16 + 1 < n_chunks) tmem_ld16_async(taddr + (uint32_t)((c16 + 1) * 16), w[(c16 + 1) & 1]);
-#pragma unroll
-                                for (int q = 0; q < 16; ++q) {
-                                    const int c = c16 * 16 + q;
-                                    acc[c % NS] = fmaf(__uint_as_float(w[c16 & 1][q]), b[c / NS], acc[c % NS]);
-                                }
-                            }
+                        for (int q = 0; q < 16; ++q) {
+                            const int c = c16 * 16 + q;
+                            if (c < C::NVAL_S) acc[c % NS] = fmaf(__uint_as_float(w[c16 & 1][q]), b[c / NS], acc[c % NS]);
                         }
                     }
                     tc_fence_before();
@@ -632,73 +736,68 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                     if ((flags & 4) && valid) red_row<NS>(sum + (size_t)agg * f_out + out_off, acc);
                     if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1) + t + 1, 3);
                 } else {
-                    float bx[C::ROWS_V], by[C::ROWS_V], bz[C::ROWS_V];
-                    if (kind == 2) {
+                    // pass p covers basis rows [p NV, (p + 1) NV) = weight columns [p NV^2, (p + 1) NV^2)
+                    float bx[NV], by[NV], bz[NV];
+                    const int stride = kind == 2 ? 1 : 3;
+#pragma unroll 1
+                    for (int pass = 0; pass < 2; ++pass) {
+                        const int r0 = pass * NV;
+                        if (pass == 1 && n_rows <= NV) break;
+                        if (kind == 2) {
 #pragma unroll
-                        for (int rr = 0; rr < C::ROWS_V; ++rr) {
-                            const float x0 = rr < n_rows ? xn[rr] : 0.f;
-                            bx[rr] = x0 * s1x; by[rr] = x0 * s1y; bz[rr] = x0 * s1z;
+                            for (int rr = 0; rr < NV; ++rr) {
+                                // x (x) s1 tiles hold 2 NV scalars: pass 1 reads the upper half
+                                const float x0 = r0 + rr < n_rows ? (pass == 0 ? xn[rr] : xn[(NV + rr) % C::XN]) : 0.f;
+                                bx[rr] = x0 * s1x; by[rr] = x0 * s1y; bz[rr] = x0 * s1z;
+                            }
+                        } else if (kind == 3) {
+#pragma unroll
+                            for (int rr = 0; rr < NV; ++rr) {
+                                const bool on = rr < n_rows;
+                                bx[rr] = on ? xn[3 * rr] * s0 : 0.f; by[rr] = on ? xn[3 * rr + 1] * s0 : 0.f; bz[rr] = on ? xn[3 * rr + 2] * s0 : 0.f;
+                            }
+                        } else {
+#pragma unroll
+                            for (int rr = 0; rr < NV; ++rr) {
+                                const bool on = rr < n_rows;
+                                const float ax = on ? xn[3 * rr] : 0.f, ay = on ? xn[3 * rr + 1] : 0.f, az = on ? xn[3 * rr + 2] : 0.f;
+                                bx[rr] = ay * s1z - az * s1y; by[rr] = az * s1x - ax * s1z; bz[rr] = ax * s1y - ay * s1x;
+                            }
                         }
-                    } else if (kind == 3) {
-#pragma unroll
-                        for (int rr = 0; rr < C::ROWS_V; ++rr) {
-                            const float m = rr < n_rows ? s0 : 0.f;
-                            bx[rr] = rr < n_rows ? xn[3 * rr] * m : 0.f;
-                            by[rr] = rr < n_rows ? xn[3 * rr + 1] * m : 0.f;
-                            bz[rr] = rr < n_rows ? xn[3 * rr + 2] * m : 0.f;
+                        (void)stride;
+                        if (pass == 0) {
+                            if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1) + t + 1, 0);
+                            mbar_wait(&tmem_full[buf], (tf_phase >> buf) & 1u);
+                            tf_phase ^= 1u << buf;
+                            tc_fence_after();
+                            if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1) + t + 1, 1);
                         }
-                    } else {
-#pragma unroll
-                        for (int rr = 0; rr < C::ROWS_V; ++rr) {
-                            const bool on = rr < n_rows;
-                            const float ax = on ? xn[3 * rr] : 0.f, ay = on ? xn[3 * rr + 1] : 0.f, az = on ? xn[3 * rr + 2] : 0.f;
-                            bx[rr] = ay * s1z - az * s1y; by[rr] = az * s1x - ax * s1z; bz[rr] = ax * s1y - ay * s1x;
+                        if (pass == 1 || n_rows <= NV) {
+                            // the last basis rows are in registers: fetch the next tile's node features
+                            if (t + 1 < n_tiles) {
+                                tdw = *reinterpret_cast<const uint4 *>(&tiles[t + 1]);
+                                const int k2 = (int)((tdw.x >> 16) & 0xffu), nr2 = (int)(tdw.x >> 24);
+                                x_prefetch<C::XN>(xg + (tdw.z & 0xffffu), nr2 * ((k2 == 0 || k2 == 2) ? 1 : 3), xn);
+                            }
                         }
-                    }
-                    if (t + 1 < n_tiles) {
-                        tdw = *reinterpret_cast<const uint4 *>(&tiles[t + 1]);
-                        const int k2 = (int)((tdw.x >> 16) & 0xffu), nr2 = (int)(tdw.x >> 24);
-                        x_prefetch<C::XN>(xg + (tdw.z & 0xffffu), nr2 * ((k2 == 0 || k2 == 2) ? 1 : 3), xn);
-                    }
-                    if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1) + t + 1, 0);
-                    mbar_wait(&tmem_full[buf], (tf_phase >> buf) & 1u);
-                    tf_phase ^= 1u << buf;
-                    tc_fence_after();
-                    if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1) + t + 1, 1);
-                    tmem_ld16_async(taddr, w[0]);
-                    if (n_chunks == C::NCOL_V / 16) {
+                        const uint32_t tp = taddr + (uint32_t)(pass * C::PASS_COLS);
+                        constexpr int NCH = C::PASS_COLS / 16, REM = C::PASS_COLS % 16;
+                        static_assert(REM == 0 || REM == 4, "pass remainder is read with one x4 load");
+                        if (NCH > 0) tmem_ld16_async(tp, w[0]); else tmem_ld4_async(tp, w[0]);
 #pragma unroll
-                        for (int c16 = 0; c16 < C::NCOL_V / 16; ++c16) {
+                        for (int c16 = 0; c16 < NCH + (REM ? 1 : 0); ++c16) {
                             tmem_wait16(w[c16 & 1]);
-                            if (c16 + 1 < C::NCOL_V / 16) tmem_ld16_async(taddr + (uint32_t)((c16 + 1) * 16), w[(c16 + 1) & 1]);
+                            if (c16 + 1 < NCH) tmem_ld16_async(tp + (uint32_t)((c16 + 1) * 16), w[(c16 + 1) & 1]);
+                            else if (c16 + 1 == NCH && REM) tmem_ld4_async(tp + (uint32_t)((c16 + 1) * 16), w[(c16 + 1) & 1]);
 #pragma unroll
                             for (int q = 0; q < 16; ++q) {
                                 const int c = c16 * 16 + q;
-                                if (c < C::NVAL_V) {
+                                if (c < C::PASS_COLS) {
                                     const int rr = c / NV, o = c % NV;
                                     const float wv = __uint_as_float(w[c16 & 1][q]);
                                     acc[3 * o] = fmaf(wv, bx[rr], acc[3 * o]);
                                     acc[3 * o + 1] = fmaf(wv, by[rr], acc[3 * o + 1]);
                                     acc[3 * o + 2] = fmaf(wv, bz[rr], acc[3 * o + 2]);
-                                }
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int c16 = 0; c16 < C::NCOL_V / 16; ++c16) {
-                            if (c16 < n_chunks) {
-                                tmem_wait16(w[c16 & 1]);
-                                if (c16 + 1 < C::NCOL_V / 16 && c16 + 1 < n_chunks) tmem_ld16_async(taddr + (uint32_t)((c16 + 1) * 16), w[(c16 + 1) & 1]);
-#pragma unroll
-                                for (int q = 0; q < 16; ++q) {
-                                    const int c = c16 * 16 + q;
-                                    if (c < C::NVAL_V) {
-                                        const int rr = c / NV, o = c % NV;
-                                        const float wv = __uint_as_float(w[c16 & 1][q]);
-                                        acc[3 * o] = fmaf(wv, bx[rr], acc[3 * o]);
-                                        acc[3 * o + 1] = fmaf(wv, by[rr], acc[3 * o + 1]);
-                                        acc[3 * o + 2] = fmaf(wv, bz[rr], acc[3 * o + 2]);
-                                    }
                                 }
                             }
                         }
@@ -753,7 +852,8 @@ static int build_plan(const ddp_tpconv_t &c, const ddp_tp_group_t *groups, const
     if (nv == 0) nv = (ns == 60) ? 10 : (ns == 24 ? 6 : 4);
     if (!pick_cfg(ns, nv, ks)) return DDP_E_UNSUPPORTED;
     if (c.k1 != 3 * ns || c.hid != 3 * ns || c.n_emb != ns || c.sh_dim != 4) return DDP_E_UNSUPPORTED;
-    const int rows_s = rows_scalar(ns), rows_v = rows_vector(nv);
+    const bool ts = use_ts(mode != 0);
+    const int rows_s = rows_scalar(ns, ts), rows_v = rows_vector(nv);
     Header &h = P.h;
     memset(&h, 0, sizeof(h));
     h.magic = MAGIC; h.mode = mode; h.ns = ns; h.nv = nv; h.ks = ks; h.kp = 3 * ks; h.n1 = 3 * ks;
@@ -767,7 +867,6 @@ static int build_plan(const ddp_tpconv_t &c, const ddp_tp_group_t *groups, const
         const bool vec = groups[g].d_out == 3;
         const int mul_out = groups[g].mul_out;
         if (mul_out != (vec ? nv : ns)) return DDP_E_UNSUPPORTED;
-        const int per = vec ? rows_v : rows_s;
         const size_t first_tile = P.tiles.size();
         for (int q = g; q < g_end; ++q) {
             float sc;
@@ -775,11 +874,13 @@ static int build_plan(const ddp_tpconv_t &c, const ddp_tp_group_t *groups, const
             if (kind < 0 || (vec != (kind >= 2))) return DDP_E_UNSUPPORTED;
             if (groups[q].sh_off != ((kind == 0 || kind == 3) ? 0 : 1)) return DDP_E_UNSUPPORTED;
             const int d1 = groups[q].d1;
+            // rows per tile: scalar tiles ROWS_S; x (x) s1 tiles 2 NV (two epilogue passes); stride-3 vector kinds NV
+            const int per = !vec ? rows_s : (kind == 2 ? rows_v : nv);
             for (int r0 = 0; r0 < groups[q].mul_in; r0 += per) {
                 const int nr = std::min(per, groups[q].mul_in - r0);
                 TileDesc td;
                 memset(&td, 0, sizeof(td));
-                td.n_cols = (uint16_t)((nr * mul_out + 15) / 16 * 16);
+                td.n_cols = (uint16_t)(vec ? ncol_vector(nv, nr) : ncol_scalar(ns, ts));
                 td.kind = (uint8_t)kind;
                 td.n_rows = (uint8_t)nr;
                 td.out_off = (uint16_t)groups[g].out_off;
