@@ -187,7 +187,9 @@ class TensorProductScoreModel(nn.Module):
                   w_sig=cols['sig'].T.contiguous().to(**f32) if 'sig' in cols else None,
                   b1=b1.contiguous().to(**f32), w2=seq[3].weight.detach().T.contiguous().to(**f32),
                   b2=seq[3].bias.detach().contiguous().to(**f32), offset=rbf.offset.detach().contiguous().to(**f32))
-        pk['desc'] = _lib.EdgeMlp(w_pre=ptr(pk['w_pre']), w_rbf=ptr(pk['w_rbf']), w2=ptr(pk['w2']), b2=ptr(pk['b2']),
+        # the second Linear is folded into the W1 of every conv that consumes this embedding (PackedConv edge_fold)
+        pk['fold'] = (seq[3].weight, seq[3].bias)
+        pk['desc'] = _lib.EdgeMlp(w_pre=ptr(pk['w_pre']), w_rbf=ptr(pk['w_rbf']), w2=None, b2=ptr(pk['b2']),
                                   b1=ptr(pk['b1']), rbf_offset=ptr(pk['offset']), rbf_coeff=float(rbf.coeff),
                                   n_pre=cols['pre'].shape[1] if 'pre' in cols else 0, n_rbf=cols['rbf'].shape[1],
                                   ns=self.ns, sh_dim=self.sh_dim)
@@ -233,19 +235,20 @@ class TensorProductScoreModel(nn.Module):
         P['proj_w'], P['proj_b'] = torch.stack(ws).contiguous(), torch.stack(bs).contiguous()
         half = sd // 2
         P['freq'] = torch.exp(torch.arange(half, dtype=torch.float32) * -(np.log(10000) / (half - 1))).to(dev)
-        P['convs'] = [c.packed(dev, ns, ns) for c in self.conv_layers]
+        conv_edges = ('ll', 'lr', 'la', 'aa', 'la', 'ar', 'rr', 'lr', 'ar')       # edge embedding each of a layer's 9 convs reads
+        P['convs'] = [c.packed(dev, ns, ns, em[conv_edges[i % 9]]['fold']) for i, c in enumerate(self.conv_layers)]
         if not self.confidence_mode:
-            P['final_conv'] = self.final_conv.packed(dev, ns, ns)
+            P['final_conv'] = self.final_conv.packed(dev, ns, ns, em['center']['fold'])
             def lin(l):
                 return l.weight.detach().T.contiguous().to(**f32), (l.bias.detach().contiguous().to(**f32) if l.bias is not None else None)
             P['tr'] = lin(self.tr_final_layer[0]) + lin(self.tr_final_layer[3])
             P['rot'] = lin(self.rot_final_layer[0]) + lin(self.rot_final_layer[3])
             P['c121'] = torch.tensor((tpmod.wigner_3j(1, 2, 1) * np.sqrt(3.0)).reshape(-1), **f32)
             if not self.no_torsion:
-                P['tor_conv'] = self.tor_bond_conv.packed(dev, ns, ns)
+                P['tor_conv'] = self.tor_bond_conv.packed(dev, ns, ns, em['tor']['fold'])
                 P['tor_mlp'] = [lin(self.tor_final_layer[0]), lin(self.tor_final_layer[3])]
             if self.flexible_sidechains:
-                P['sc_conv'] = self.sc_tor_bond_conv.packed(dev, ns, ns)
+                P['sc_conv'] = self.sc_tor_bond_conv.packed(dev, ns, ns, em['sc']['fold'])
                 P['sc_mlp'] = [lin(self.sc_tor_final_layer[0]), lin(self.sc_tor_final_layer[3])]
         else:
             cp = self.confidence_predictor

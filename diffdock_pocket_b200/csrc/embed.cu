@@ -123,7 +123,16 @@ edge_embed_kernel(const float *__restrict__ pos_a, const float *__restrict__ pos
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) s_r[o * kEE + half * 16 + i] = fmaxf(acc[i], 0.f);
+        if (p.w2 == nullptr) {
+            // folded form: the second Linear lives in the consuming convolution's W1, emit the hidden activations
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int e = e0 + half * 16 + i;
+                if (e < n_edges) emb[(size_t)e * p.ns + o] = fmaxf(acc[i], 0.f);
+            }
+        }
     }
+    if (p.w2 == nullptr) return;
     __syncthreads();
     if (o < p.ns) {
 #pragma unroll

@@ -60,18 +60,37 @@ __device__ __forceinline__ void knn_insert(float (&bd)[KP], int (&bi)[KP], float
     }
 }
 
+// Same list, candidates in arbitrary order: lexicographic (distance, index) comparison reproduces the scan's
+// "ties keep the lower index" rule when partial lists are merged.
+template <int KP>
+__device__ __forceinline__ void knn_insert_lex(float (&bd)[KP], int (&bi)[KP], float d, int i) {
+    if (bd[KP - 1] > d || (bd[KP - 1] == d && bi[KP - 1] > i)) {
+        bd[KP - 1] = d; bi[KP - 1] = i;
+#pragma unroll
+        for (int e = KP - 1; e > 0; --e) {
+            if (bd[e - 1] > bd[e] || (bd[e - 1] == bd[e] && bi[e - 1] > bi[e])) {
+                float td = bd[e - 1]; bd[e - 1] = bd[e]; bd[e] = td;
+                int ti = bi[e - 1]; bi[e - 1] = bi[e]; bi[e] = ti;
+            }
+        }
+    }
+}
+
 constexpr int kKnnThreads = 128;
+constexpr int kKnnSub = 4;       // threads per centre (each scans a quarter of the staged points, lists merged by shuffles)
 constexpr int kKnnStage = 2048;  // points staged per pass (24 KB)
 
-// One thread per centre; the centre's example is staged through shared memory in chunks when the
+// kKnnSub threads per centre; the centre's example is staged through shared memory in chunks when the
 // whole block lies inside one example (the common case), otherwise threads read global memory.
 template <int KP>
 __global__ void knn_scan_kernel(const float *__restrict__ x, const int32_t *__restrict__ ptr, int num_examples, int n,
                                 int32_t *__restrict__ slab, int slab_w, int32_t *__restrict__ counts) {
     __shared__ float sx[kKnnStage * 3];
-    const int j = blockIdx.x * kKnnThreads + threadIdx.x;
-    const int j_first = blockIdx.x * kKnnThreads;
-    const int j_last = min(j_first + kKnnThreads, n) - 1;
+    constexpr int QPB = kKnnThreads / kKnnSub;      // centres per block
+    const int sub = threadIdx.x % kKnnSub;
+    const int j = blockIdx.x * QPB + threadIdx.x / kKnnSub;
+    const int j_first = blockIdx.x * QPB;
+    const int j_last = min(j_first + QPB, n) - 1;
     const int b_first = ddp_find_segment(ptr, num_examples, j_first);
     const int b_last = ddp_find_segment(ptr, num_examples, j_last);
     float bd[KP];
@@ -88,16 +107,34 @@ __global__ void knn_scan_kernel(const float *__restrict__ x, const int32_t *__re
             for (int t = threadIdx.x; t < 3 * m; t += kKnnThreads) sx[t] = x[3 * base + t];
             __syncthreads();
             if (j < n) {
-                for (int t = 0; t < m; ++t)
+                const int per = (m + kKnnSub - 1) / kKnnSub;
+                const int t1 = min(m, (sub + 1) * per);
+                for (int t = sub * per; t < t1; ++t)
                     knn_insert<KP>(bd, bi, ddp_sqdist(sx[3 * t], sx[3 * t + 1], sx[3 * t + 2], yx, yy, yz), base + t);
             }
         }
     } else if (j < n) {
         const int b = ddp_find_segment(ptr, num_examples, j);
-        for (int i = ptr[b]; i < ptr[b + 1]; ++i)
+        const int beg = ptr[b], m = ptr[b + 1] - beg;
+        const int per = (m + kKnnSub - 1) / kKnnSub;
+        const int t1 = min(m, (sub + 1) * per);
+        for (int t = sub * per; t < t1; ++t) {
+            const int i = beg + t;
             knn_insert<KP>(bd, bi, ddp_sqdist(x[3 * i], x[3 * i + 1], x[3 * i + 2], yx, yy, yz), i);
+        }
     }
-    if (j < n) {
+    // merge the partial lists into the group's first thread (all lanes take part in the shuffles)
+    const int lane = threadIdx.x & 31, lead = lane - sub;
+#pragma unroll
+    for (int s2 = 1; s2 < kKnnSub; ++s2) {
+#pragma unroll
+        for (int e = 0; e < KP; ++e) {
+            const float d = __shfl_sync(0xffffffffu, bd[e], lead + s2);
+            const int i = __shfl_sync(0xffffffffu, bi[e], lead + s2);
+            if (sub == 0 && i != -1) knn_insert_lex<KP>(bd, bi, d, i);
+        }
+    }
+    if (j < n && sub == 0) {
         int c = 0;
 #pragma unroll
         for (int e = 0; e < KP; ++e) {
@@ -229,10 +266,11 @@ extern "C" int ddp_knn_graph(const float *x, const int32_t *ptr, int32_t num_exa
     cudaStream_t st = (cudaStream_t)stream;
     const int kp = k + 1;
     if (n > 0) {
-        const int grid = (n + kKnnThreads - 1) / kKnnThreads;
-        if (kp == 9) knn_scan_kernel<9><<<grid, kKnnThreads, 0, st>>>(x, ptr, num_examples, n, slab, slab_w, counts);
-        else if (kp == 13) knn_scan_kernel<13><<<grid, kKnnThreads, 0, st>>>(x, ptr, num_examples, n, slab, slab_w, counts);
-        else if (kp == 33) knn_scan_kernel<33><<<grid, kKnnThreads, 0, st>>>(x, ptr, num_examples, n, slab, slab_w, counts);
+        const int qpb = kKnnThreads / kKnnSub;
+        const int grid_sub = (n + qpb - 1) / qpb, grid = (n + kKnnThreads - 1) / kKnnThreads;
+        if (kp == 9) knn_scan_kernel<9><<<grid_sub, kKnnThreads, 0, st>>>(x, ptr, num_examples, n, slab, slab_w, counts);
+        else if (kp == 13) knn_scan_kernel<13><<<grid_sub, kKnnThreads, 0, st>>>(x, ptr, num_examples, n, slab, slab_w, counts);
+        else if (kp == 33) knn_scan_kernel<33><<<grid_sub, kKnnThreads, 0, st>>>(x, ptr, num_examples, n, slab, slab_w, counts);
         else knn_scan_generic_kernel<<<grid, kKnnThreads, 0, st>>>(x, ptr, num_examples, n, kp, slab, slab_w, counts);
         DDP_LAUNCH_CHECK();
     }

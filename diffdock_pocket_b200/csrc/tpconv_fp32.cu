@@ -6,17 +6,19 @@
 
 namespace {
 
-constexpr int TE = 32;        // edges per tile
-constexpr int LDS_E = 36;     // padded edge stride (multiple of 4 for float4 reads)
 constexpr int NT = 256;
 constexpr int EG = 8;         // edges per register tile
+// TE edges per tile (32, or 8 for small edge sets so that a few hundred edges still spread over the SMs);
+// LDS_E = TE + 4: padded edge stride (multiple of 4 for float4 reads)
 
 struct Smem {
     float *a, *h, *x, *sh, *out, *ctab;
     int *agg;
 };
 
+template <int TE>
 __device__ __forceinline__ Smem carve(float *base, const ddp_tpconv_t &c, int ctab_len) {
+    constexpr int LDS_E = TE + 4;
     Smem s;
     s.a = base;
     s.h = s.a + c.k1 * LDS_E;
@@ -28,10 +30,14 @@ __device__ __forceinline__ Smem carve(float *base, const ddp_tpconv_t &c, int ct
     return s;
 }
 
+template <int TE>
 __global__ void __launch_bounds__(NT, 2)
 tpconv_fp32_kernel(ddp_tpconv_t c, ddp_tpconv_edges_t ed, int ctab_len, float *__restrict__ sum) {
+    constexpr int LDS_E = TE + 4;
+    constexpr int NEG = TE / EG;          // edge groups per tile
+    constexpr int TPG = NT / NEG;         // threads per edge group in the weight-column phase
     extern __shared__ __align__(16) float smem[];
-    Smem s = carve(smem, c, ctab_len);
+    Smem s = carve<TE>(smem, c, ctab_len);
     const int tid = threadIdx.x;
     const int n_edges = min(*ed.n_edges_dev, ed.edge_cap);
     for (int i = tid; i < ctab_len; i += NT) s.ctab[i] = c.ctab[i];
@@ -87,10 +93,13 @@ tpconv_fp32_kernel(ddp_tpconv_t c, ddp_tpconv_edges_t ed, int ctab_len, float *_
         }
         __syncthreads();
 
-        // ---- weight columns: 64 consecutive columns x 4 edge groups per pass -----------------------
-        const int eg = tid >> 6;
+        // ---- weight columns: TPG consecutive columns x NEG edge groups per pass ---------------------
+        const int eg = tid / TPG;
         const float *hp = s.h + eg * EG;
-        for (int col = tid & 63; col < c.w_numel; col += 64) {
+        // warp-uniform trip count (lanes past the last column idle but still take part in the shuffles below)
+        for (int cb = (tid % TPG) & ~31; cb < c.w_numel; cb += TPG) {
+            const bool active = cb + (tid & 31) < c.w_numel;
+            const int col = active ? cb + (tid & 31) : c.w_numel - 1;
             float acc[EG];
             const float bc = c.b2[col];
 #pragma unroll
@@ -105,7 +114,12 @@ tpconv_fp32_kernel(ddp_tpconv_t c, ddp_tpconv_edges_t ed, int ctab_len, float *_
                 acc[3] = fmaf(w, v0.w, acc[3]); acc[4] = fmaf(w, v1.x, acc[4]); acc[5] = fmaf(w, v1.y, acc[5]);
                 acc[6] = fmaf(w, v1.z, acc[6]); acc[7] = fmaf(w, v1.w, acc[7]);
             }
-            const ddp_tp_group_t g = c.groups[c.col_group[col]];
+            const int gi = c.col_group[col];
+            const ddp_tp_group_t g = c.groups[gi];
+            // warp-uniform: every lane active on a column of the same group, group start aligned to the warp's 32 columns
+            const int gi0 = __shfl_sync(0xffffffffu, gi, 0);
+            const bool same = __all_sync(0xffffffffu, active && gi == gi0);
+            const bool warp_reduce = same && (g.mul_out & (g.mul_out - 1)) == 0 && g.mul_out <= 16 && ((cb - g.w_off) % g.mul_out) == 0;
             const int u = (col - g.w_off) / g.mul_out, o = (col - g.w_off) % g.mul_out;
             const float *cg = s.ctab + g.c_off;
             const float *xp = s.x + (g.x_off + u * g.d1) * LDS_E + eg * EG;
@@ -123,8 +137,19 @@ tpconv_fp32_kernel(ddp_tpconv_t c, ddp_tpconv_edges_t ed, int ctab_len, float *_
                             for (int i = 0; i < EG; ++i) b[i] = fmaf(cc * xp[ii * LDS_E + i], sp[jj * LDS_E + i], b[i]);
                         }
                     }
+                if (warp_reduce) {
+                    // all 32 lanes hold columns of one group whose mul_out divides 32: lanes l, l + mul_out, ... feed
+                    // the same output channel, so they are summed by shuffles and only mul_out lanes touch shared memory
 #pragma unroll
-                for (int i = 0; i < EG; ++i) atomicAdd(op + kk * LDS_E + i, acc[i] * b[i]);
+                    for (int i = 0; i < EG; ++i) {
+                        float v = acc[i] * b[i];
+                        for (int off = 16; off >= g.mul_out; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                        if ((tid & 31) < g.mul_out) atomicAdd(op + kk * LDS_E + i, v);
+                    }
+                } else if (active) {
+#pragma unroll
+                    for (int i = 0; i < EG; ++i) atomicAdd(op + kk * LDS_E + i, acc[i] * b[i]);
+                }
             }
         }
         __syncthreads();
@@ -157,17 +182,21 @@ extern "C" int ddp_tpconv_fp32(const ddp_tpconv_t *conv, const ddp_tpconv_edges_
     if (e.edge_cap <= 0) return 0;
     const int ctab_len = c.ctab_len;
     if (ctab_len <= 0 || ctab_len > 64 * 125) return DDP_E_SHAPE;
-    const size_t smem = ((size_t)(c.k1 + c.hid + c.f_in + c.sh_dim + c.f_out) * LDS_E + ctab_len) * sizeof(float) + TE * sizeof(int);
+    const bool small = e.edge_cap <= 8 * 2 * ddp_num_sms();          // few edges: 8-edge tiles keep all SMs busy
+    const int TE = small ? 8 : 32;
+    const size_t smem = ((size_t)(c.k1 + c.hid + c.f_in + c.sh_dim + c.f_out) * (TE + 4) + ctab_len) * sizeof(float) + TE * sizeof(int);
     if (smem > 200 * 1024) return DDP_E_SHAPE;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t err = cudaFuncSetAttribute(tpconv_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static size_t configured[2] = {0, 0};
+    if (smem > configured[small]) {
+        cudaError_t err = small ? cudaFuncSetAttribute(tpconv_fp32_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                : cudaFuncSetAttribute(tpconv_fp32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;
-        configured = smem;
+        configured[small] = smem;
     }
     int tiles = (e.edge_cap + TE - 1) / TE;
     int grid = tiles < 2 * ddp_num_sms() ? tiles : 2 * ddp_num_sms();
-    tpconv_fp32_kernel<<<grid, NT, smem, (cudaStream_t)stream>>>(c, e, ctab_len, sum);
+    if (small) tpconv_fp32_kernel<8><<<grid, NT, smem, (cudaStream_t)stream>>>(c, e, ctab_len, sum);
+    else tpconv_fp32_kernel<32><<<grid, NT, smem, (cudaStream_t)stream>>>(c, e, ctab_len, sum);
     DDP_LAUNCH_CHECK();
     return 0;
 }

@@ -148,12 +148,21 @@ class _TP(nn.Module):
 class PackedConv:
     """Device-side, kernel-friendly image of one TensorProductConvLayer (built once per weight load)."""
 
-    def __init__(self, layer, device, n_emb, ns):
+    def __init__(self, layer, device, n_emb, ns, edge_fold=None):
+        """``edge_fold`` = (W2e [n_emb, h], b2e [n_emb]) of the edge-embedding MLP's second Linear: folded into the
+        first n_emb input columns of fc[0], so that the conv consumes the MLP's hidden activations directly."""
         spec = layer.tp.spec
         f32 = dict(dtype=torch.float32, device=device)
         fc0, fc3 = layer.fc[0], layer.fc[3]
-        self.w1t = fc0.weight.detach().T.contiguous().to(**f32)
-        self.b1 = fc0.bias.detach().contiguous().to(**f32)
+        W1, b1 = fc0.weight.detach().double().cpu(), fc0.bias.detach().double().cpu()
+        if edge_fold is not None:
+            W2e, b2e = (t.detach().double().cpu() for t in edge_fold)
+            assert W2e.shape[0] == n_emb and W2e.shape[1] == n_emb, 'fold keeps the edge-attribute width'
+            b1 = b1 + W1[:, :n_emb] @ b2e
+            W1 = torch.cat([W1[:, :n_emb] @ W2e, W1[:, n_emb:]], dim=1)
+        self.w1_host, self.b1_host = W1.float().contiguous(), b1.float().contiguous()       # nn.Linear layout, for the UMMA pack
+        self.w1t = self.w1_host.T.contiguous().to(**f32)
+        self.b1 = self.b1_host.to(**f32)
         self.w2t = fc3.weight.detach().T.contiguous().to(**f32)
         self.b2 = fc3.bias.detach().contiguous().to(**f32)
         self.k1, self.hid = fc0.in_features, fc0.out_features
@@ -177,9 +186,8 @@ class PackedConv:
     def umma_image(self, layer, mode, device):
         if mode not in self.umma:
             L = _lib.lib()
-            fc0, fc3 = layer.fc[0], layer.fc[3]
-            w1 = fc0.weight.detach().cpu().float().contiguous()
-            b1 = fc0.bias.detach().cpu().float().contiguous()
+            fc3 = layer.fc[3]
+            w1, b1 = self.w1_host, self.b1_host
             w2 = fc3.weight.detach().cpu().float().contiguous()
             b2 = fc3.bias.detach().cpu().float().contiguous()
             ctab = torch.tensor(self.spec.ctab, dtype=torch.float32)
@@ -220,9 +228,12 @@ class TensorProductConvLayer(nn.Module):
         self._packed = None
         return super()._load_from_state_dict(*a, **k)
 
-    def packed(self, device, n_emb, ns):
-        if self._packed is None or self._packed.w1t.device != torch.device(device) or self._packed.cdesc.n_emb != n_emb:
-            self._packed = PackedConv(self, device, n_emb, ns)
+    def packed(self, device, n_emb, ns, edge_fold=None):
+        key = None if edge_fold is None else tuple(id(t) for t in edge_fold)
+        if self._packed is None or self._packed.w1t.device != torch.device(device) or self._packed.cdesc.n_emb != n_emb \
+                or self._packed.fold_key != key:
+            self._packed = PackedConv(self, device, n_emb, ns, edge_fold)
+            self._packed.fold_key = key
         return self._packed
 
     def forward(self, node_attr, edge_index, edge_attr, edge_sh, out_nodes=None, reduce='mean', edge_weight=1.0):

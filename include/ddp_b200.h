@@ -72,6 +72,9 @@ int ddp_degree(const int32_t *idx, const int32_t *n_edges_dev, int32_t edge_cap,
  * Outputs: sh [cap,4], emb [cap,ns].  pre (n_pre columns, e.g. the 4 bond one-hots, zero for rows
  * >= n_pre_rows) may be NULL.  graph_of_a maps node index on side a -> graph (NULL => edge[0] is
  * already the graph index, used by the centre graph).  u may be NULL (torsion-bond embedding).
+ * Folded form (mlp->w2 == NULL): emb receives the hidden activations relu(...) instead; the caller has folded W2 / b2
+ * into the first Linear of every convolution that consumes this edge embedding (W1[:, :ns] W2, b1 + W1[:, :ns] b2),
+ * which halves the per-edge work of this kernel.
  */
 typedef struct {
     const float *w_pre;  /* [n_pre][ns]  (input-major) or NULL */
