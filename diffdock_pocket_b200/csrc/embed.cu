@@ -159,23 +159,37 @@ edge_embed_kernel(const float *__restrict__ pos_a, const float *__restrict__ pos
 constexpr int kMaxUpdates = 4;
 struct UpdatePack { ddp_update_t u[kMaxUpdates]; int n; };
 
+// One warp per node row: the per-node counts are read once, channels are covered by the lanes (coalesced rows).
 __global__ void node_update_kernel(const float *__restrict__ old_x, int f_old, int ld_old, UpdatePack up, int n,
                                    int f_new, float *__restrict__ new_x, int ld_new) {
-    const size_t total = (size_t)n * f_new;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int node = (int)(i / f_new), c = (int)(i % f_new);
-        float v = (old_x != nullptr && c < f_old) ? old_x[(size_t)node * ld_old + c] : 0.f;
-        for (int k = 0; k < up.n; ++k) {
-            if (*up.u[k].n_edges_dev > 0) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    bool live[kMaxUpdates];
+#pragma unroll
+    for (int k = 0; k < kMaxUpdates; ++k) live[k] = k < up.n && *up.u[k].n_edges_dev > 0;
+    for (int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; node < n; node += warps) {
+        float cnt[kMaxUpdates];
+#pragma unroll
+        for (int k = 0; k < kMaxUpdates; ++k) {
+            cnt[k] = 1.f;
+            if (live[k]) {
                 const int dg = up.u[k].deg[node];
-                const float cnt = (float)(dg < 1 ? 1 : dg);
-                const float m = up.u[k].sum[(size_t)node * f_new + c] / cnt;
-                const float sc = up.u[k].scale ? up.u[k].scale[c] : 1.f;
-                const float sf = up.u[k].shift ? up.u[k].shift[c] : 0.f;
-                v += fmaf(m, sc, sf);
+                cnt[k] = (float)(dg < 1 ? 1 : dg);
             }
         }
-        new_x[(size_t)node * ld_new + c] = v;
+        for (int c = lane; c < f_new; c += 32) {
+            float v = (old_x != nullptr && c < f_old) ? old_x[(size_t)node * ld_old + c] : 0.f;
+#pragma unroll
+            for (int k = 0; k < kMaxUpdates; ++k) {
+                if (live[k]) {
+                    const float m = __fdiv_rn(up.u[k].sum[(size_t)node * f_new + c], cnt[k]);
+                    const float sc = up.u[k].scale ? __ldg(up.u[k].scale + c) : 1.f;
+                    const float sf = up.u[k].shift ? __ldg(up.u[k].shift + c) : 0.f;
+                    v += fmaf(m, sc, sf);
+                }
+            }
+            new_x[(size_t)node * ld_new + c] = v;
+        }
     }
 }
 
@@ -246,6 +260,7 @@ struct MlpPack { ddp_mlp_layer_t l[kMaxLayers]; int n; };
 __global__ void row_mlp_kernel(const float *__restrict__ in, int n, int ld_in, MlpPack mp,
                                const float *__restrict__ row_scale, float *__restrict__ out, int ld_out) {
     __shared__ float buf[2][256];
+    __shared__ float red[8];
     const int row = blockIdx.x;
     if (row >= n) return;
     for (int k = threadIdx.x; k < mp.l[0].n_in; k += blockDim.x) buf[0][k] = in[(size_t)row * ld_in + k];
@@ -253,12 +268,30 @@ __global__ void row_mlp_kernel(const float *__restrict__ in, int n, int ld_in, M
     int cur = 0;
     for (int l = 0; l < mp.n; ++l) {
         const ddp_mlp_layer_t L = mp.l[l];
-        for (int o = threadIdx.x; o < L.n_out; o += blockDim.x) {
-            float acc = L.b ? L.b[o] : 0.f;
-            for (int k = 0; k < L.n_in; ++k) acc = fmaf(L.wt[(size_t)k * L.n_out + o], buf[cur][k], acc);
-            if (L.act == 1) acc = fmaxf(acc, 0.f);
-            else if (L.act == 2) acc = tanhf(acc);
-            buf[cur ^ 1][o] = acc;
+        if (L.n_out == 1) {
+            // single output: the threads split K and reduce (a lone thread would chain n_in dependent loads)
+            float part = 0.f;
+            for (int k = threadIdx.x; k < L.n_in; k += blockDim.x) part = fmaf(__ldg(L.wt + k), buf[cur][k], part);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                float acc = L.b ? L.b[0] : 0.f;
+                for (int w = 0; w < (int)(blockDim.x >> 5); ++w) acc += red[w];
+                if (L.act == 1) acc = fmaxf(acc, 0.f);
+                else if (L.act == 2) acc = tanhf(acc);
+                buf[cur ^ 1][0] = acc;
+            }
+        } else {
+            for (int o = threadIdx.x; o < L.n_out; o += blockDim.x) {
+                float acc = L.b ? L.b[o] : 0.f;
+#pragma unroll 8
+                for (int k = 0; k < L.n_in; ++k) acc = fmaf(__ldg(L.wt + (size_t)k * L.n_out + o), buf[cur][k], acc);
+                if (L.act == 1) acc = fmaxf(acc, 0.f);
+                else if (L.act == 2) acc = tanhf(acc);
+                buf[cur ^ 1][o] = acc;
+            }
         }
         __syncthreads();
         cur ^= 1;
@@ -352,8 +385,8 @@ extern "C" int ddp_node_update(const float *old_x, int32_t f_old, int32_t ld_old
     UpdatePack up;
     up.n = n_updates;
     for (int i = 0; i < n_updates; ++i) up.u[i] = updates[i];
-    node_update_kernel<<<grid_for((size_t)n * f_new, 256), 256, 0, (cudaStream_t)stream>>>(old_x, f_old, ld_old, up, n, f_new,
-                                                                                         new_x, ld_new);
+    node_update_kernel<<<grid_for((size_t)n * 32, 256), 256, 0, (cudaStream_t)stream>>>(old_x, f_old, ld_old, up, n, f_new,
+                                                                                      new_x, ld_new);
     DDP_LAUNCH_CHECK();
     return 0;
 }

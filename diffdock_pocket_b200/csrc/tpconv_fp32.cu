@@ -79,7 +79,7 @@ tpconv_fp32_kernel(ddp_tpconv_t c, ddp_tpconv_edges_t ed, int ctab_len, float *_
 #pragma unroll
             for (int i = 0; i < EG; ++i) acc[i] = bj;
             const float *ap = s.a + eg * EG;
-#pragma unroll 4
+#pragma unroll 8
             for (int k = 0; k < c.k1; ++k) {
                 const float w = __ldg(c.w1t + (size_t)k * c.hid + j);
                 const float4 v0 = *reinterpret_cast<const float4 *>(ap + k * LDS_E);
@@ -105,7 +105,7 @@ tpconv_fp32_kernel(ddp_tpconv_t c, ddp_tpconv_edges_t ed, int ctab_len, float *_
 #pragma unroll
             for (int i = 0; i < EG; ++i) acc[i] = bc;
             const float *wp = c.w2t + col;
-#pragma unroll 4
+#pragma unroll 8
             for (int k = 0; k < c.hid; ++k) {
                 const float w = __ldg(wp + (size_t)k * c.w_numel);
                 const float4 v0 = *reinterpret_cast<const float4 *>(hp + k * LDS_E);
