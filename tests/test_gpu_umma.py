@@ -92,3 +92,72 @@ def test_sampling_tensor_core_pose_rmsd(mode):
     for a, r in zip(got, ref):
         rmsd = float(((a['ligand'].pos.cpu() - r['ligand'].pos) ** 2).sum(-1).mean().sqrt())
         assert rmsd < 0.1, (mode, rmsd)
+
+
+def test_grouped_launch_equals_single_launches():
+    """ddp_tpconv_umma_group over three convs that share irreps (different weights, edge sets of 1000 / 0 live / 130
+    edges, one with spare capacity) == the same three convs launched one by one."""
+    import ctypes as C
+    from diffdock_pocket_b200 import _lib
+    from diffdock_pocket_b200._lib import ptr
+    ns, nv = 60, 10
+    seq = _seq(ns, nv)
+    L = _lib.lib()
+    n = 90
+    torch.manual_seed(3)
+    x = torch.randn(n, E.Irreps(seq[3]).dim, device=DEV)
+    jobs = []
+    for j, (n_live, cap) in enumerate([(1000, 1000), (0, 256), (130, 400)]):
+        conv = TensorProductConvLayer(seq[3], '1x0e+1x1o', seq[3], 3 * ns, residual=False, batch_norm=False, faster=True).to(DEV)
+        pk = conv.packed(DEV, ns, ns)
+        img = pk.umma_image(conv, 0, DEV)
+        ei = torch.randint(0, n, (2, cap), dtype=torch.int32, device=DEV)
+        emb = torch.randn(cap, ns, device=DEV)
+        sh = E.spherical_harmonics('1x0e+1x1o', torch.randn(cap, 3)).to(DEV).contiguous()
+        n_dev = torch.tensor([n_live], dtype=torch.int32, device=DEV)
+        ed = _lib.TpEdges(emb=ptr(emb), p1=ptr(x), i1=ei[0].data_ptr(), ld1=x.shape[1], p2=ptr(x), i2=ei[1].data_ptr(), ld2=x.shape[1],
+                          x=ptr(x), gather=ei[1].data_ptr(), ldx=x.shape[1], sh=ptr(sh), agg=ei[0].data_ptr(), ew=None,
+                          n_edges_dev=ptr(n_dev), edge_cap=cap)
+        jobs.append((conv, pk, img, ed, (ei, emb, sh, n_dev)))
+    st = _lib.stream_ptr()
+    single = []
+    for conv, pk, img, ed, _ in jobs:
+        s = torch.zeros(n, pk.spec.f_out, device=DEV)
+        _lib.check(L.ddp_tpconv_umma(C.byref(pk.cdesc), ptr(img), 0, C.byref(ed), ptr(s), st), 'single')
+        single.append(s)
+    grouped = [torch.zeros(n, jobs[0][1].spec.f_out, device=DEV) for _ in jobs]
+    k = len(jobs)
+    convs = (C.c_void_p * k)(*[C.addressof(j[1].cdesc) for j in jobs])
+    imgs = (C.c_void_p * k)(*[ptr(j[2]) for j in jobs])
+    eds = (C.c_void_p * k)(*[C.addressof(j[3]) for j in jobs])
+    sums = (C.c_void_p * k)(*[ptr(g) for g in grouped])
+    _lib.check(L.ddp_tpconv_umma_group(convs, imgs, 0, eds, sums, k, st), 'group')
+    torch.cuda.synchronize()
+    assert float(single[0].abs().max()) > 0 and float(single[1].abs().max()) == 0
+    for a, b in zip(grouped, single):
+        assert T.rel_err(a, b) < 1e-5 if float(b.abs().max()) > 0 else float(a.abs().max()) == 0      # atomics order only
+
+
+@pytest.mark.parametrize('mode,n,tol', [('bf16', 20, 3e-2), ('fp32', 3, 2e-3)])
+def test_forward_is_se3_equivariant_at_full_size(mode, n, tol):
+    """Size-independent property of the whole path on the full 3dpf apo batch (no oracle needed): a global rotation +
+    translation of every coordinate rotates tr / rot scores and leaves the torsion scores unchanged."""
+    from scipy.spatial.transform import Rotation
+    m, c, om, oc, sa, ca = T.models(DEV)
+    dl = T.randomized_list(T.graph('3dpf_apo'), n, sa, seed=4)
+    Rm = torch.from_numpy(Rotation.from_rotvec([0.3, -1.1, 0.7]).as_matrix()).float()
+    shift = torch.tensor([1.5, -2.0, 0.5])
+    dl2 = copy.deepcopy(dl)
+    for g in dl2:
+        for k in ('ligand', 'atom', 'receptor'):
+            g[k].pos = g[k].pos @ Rm.T + shift
+    m.conv_mode = mode
+    try:
+        with torch.no_grad():
+            a = [t.cpu() for t in m(T.batch_at(dl, 0.4))]
+            b = [t.cpu() for t in m(T.batch_at(dl2, 0.4))]
+    finally:
+        m.conv_mode = 'fp32'
+    assert T.rel_err(b[0], a[0] @ Rm.T) < tol and T.rel_err(b[1], a[1] @ Rm.T) < tol
+    assert T.rel_err(b[2], a[2]) < tol and T.rel_err(b[3], a[3]) < tol
+    assert a[2].numel() > 0 and a[3].numel() > 0
