@@ -380,13 +380,19 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
         }
         mbar_init(h_ready, N_EPI);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        int acc = 0;
-        for (int j = 0; j < n_jobs; ++j) {
-            pref[j] = acc;
-            const int ne = min(*jobs.job[j].ed.n_edges_dev, jobs.job[j].ed.edge_cap);
-            acc += (ne + TILE_M - 1) / TILE_M;
+    }
+    // tile counts of the jobs: one thread per job fetches its live edge count (independent loads), warp 7 scans them
+    if (warp == 7) {
+        int nt = 0;
+        if (lane < n_jobs) nt = (min(__ldg(jobs.job[lane].ed.n_edges_dev), jobs.job[lane].ed.edge_cap) + TILE_M - 1) / TILE_M;
+        int incl = nt;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
         }
-        pref[n_jobs] = acc;
+        if (lane < n_jobs) pref[lane] = incl - nt;
+        if (lane == n_jobs - 1) pref[n_jobs] = incl;
     }
     if (warp == 5) tmem_alloc(tmem_base_smem, 512);
     tc_fence_before();
