@@ -1,0 +1,114 @@
+"""Host mirror of the docking driver in ``inference.py`` (boundary only: no RDKit / Biopython file I/O).
+
+``infer_single_complex`` follows inference.py:106-291 up to the ranking step (:135 copy the complex graph
+``samples_per_complex`` times, :140 ``randomize_position``, :177 ``sampling``, :198-219 gather poses in the original
+frame and sort by confidence, descending); writing SDF / PDB files (:221-280) stays with the reference's own code,
+which consumes exactly the arrays returned here.  ``infer_multiple_complexes`` is the per-device loop (:294-304) with
+the reference's per-complex failure isolation (:282-287: a failing complex is reported and skipped).
+
+Multi-GPU: the reference splits the complex table with ``np.array_split`` over a spawn pool (inference.py:466-488).
+``infer_sharded`` does the same split over ``torch.distributed`` ranks (one process per GPU) and adds the path's single
+collective: an all-gather of every complex's best confidence so that all ranks hold the global ranking
+(virtual-screening use, BASELINE.json configs[4]).
+"""
+import copy
+import traceback
+from argparse import Namespace
+from functools import partial
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .diffusion_utils import get_t_schedule, t_to_sigma as t_to_sigma_compl
+from .parallel import shard_range
+from .sampling import randomize_position, sampling
+
+
+def default_args(**over):
+    """Sampler flags of inference.py's parser (:49-103) that reach the hot path."""
+    a = dict(samples_per_complex=10, batch_size=32, inference_steps=30, actual_steps=None, no_random=False, ode=False,
+             no_final_step_noise=False, rigid=False, inf_sched_alpha=1.0, inf_sched_beta=1.0,
+             temp_sampling_tr=0.9766350103728372, temp_psi_tr=1.5102572175711826,
+             temp_sampling_rot=6.077432837220868, temp_psi_rot=0.8141168207563049,
+             temp_sampling_tor=6.761568162335063, temp_psi_tor=0.7661845361370018,
+             temp_sampling_sc_tor=1.4487910576602347, temp_psi_sc_tor=1.339614553802453,
+             temp_sigma_data=0.48884149503636976)
+    a.update(over)
+    return Namespace(**a)
+
+
+def infer_single_complex(idx, protein_ligand_info_row, model, args, score_model_args, filtering_args=None,
+                         filtering_model=None, filtering_model_args=None, filtering_complex_dict=None, t_schedule=None,
+                         tr_schedule=None, device=None):
+    """-> dict(name, ligand_pos [spc, N_l, 3], atom_pos [spc, N_a, 3], confidence [spc] or None), poses in the original
+    frame and sorted by confidence (descending); ``None`` if the complex failed (the reference returns 0 and goes on)."""
+    orig = protein_ligand_info_row['complex_graph']
+    spc = args.samples_per_complex
+    t_to_sigma = partial(t_to_sigma_compl, args=score_model_args)
+    flex = False if args.rigid else score_model_args.flexible_sidechains
+    try:
+        data_list = [copy.deepcopy(orig) for _ in range(spc)]
+        randomize_position(data_list, score_model_args.no_torsion, args.no_random, score_model_args.tr_sigma_max,
+                           flexible_sidechains=flex)
+        filtering_data_list = None
+        if filtering_model is not None and filtering_complex_dict is not None and not (
+                getattr(filtering_args, 'use_original_model_cache', True) or getattr(filtering_args, 'transfer_weights', False)):
+            filtering_data_list = [copy.deepcopy(filtering_complex_dict[orig.name]) for _ in range(spc)]
+        steps = args.actual_steps if args.actual_steps is not None else args.inference_steps
+        data_list, confidence = sampling(
+            data_list=data_list, model=model, inference_steps=steps, tr_schedule=tr_schedule, rot_schedule=tr_schedule,
+            tor_schedule=tr_schedule, sidechain_tor_schedule=tr_schedule, t_schedule=t_schedule, t_to_sigma=t_to_sigma,
+            model_args=score_model_args, confidence_model=filtering_model, device=device, no_random=args.no_random,
+            ode=args.ode, filtering_data_list=filtering_data_list, filtering_model_args=filtering_model_args,
+            asyncronous_noise_schedule=getattr(score_model_args, 'asyncronous_noise_schedule', False),
+            batch_size=args.batch_size, no_final_step_noise=args.no_final_step_noise,
+            temp_sampling=[args.temp_sampling_tr, args.temp_sampling_rot, args.temp_sampling_tor, args.temp_sampling_sc_tor],
+            temp_psi=[args.temp_psi_tr, args.temp_psi_rot, args.temp_psi_tor, args.temp_psi_sc_tor],
+            flexible_sidechains=flex)     # reference quirk kept: --temp_sigma_data is parsed (:101) but never passed
+        #                                   to sampling() (:177-196), so its default 0.5 applies
+        center = np.asarray(orig.original_center.cpu().numpy() if torch.is_tensor(orig.original_center) else orig.original_center)
+        ligand_pos = np.asarray([g['ligand'].pos.cpu().numpy() + center for g in data_list])
+        atom_pos = np.asarray([g['atom'].pos.cpu().numpy() + center for g in data_list])
+        if confidence is not None:
+            if confidence.dim() == 2:                               # multi-cutoff confidence heads: first column ranks
+                confidence = confidence[:, 0]
+            confidence = confidence.cpu().numpy()
+            order = np.argsort(confidence)[::-1]
+            confidence, ligand_pos, atom_pos = confidence[order], ligand_pos[order], atom_pos[order]
+        return dict(name=orig.name, index=idx, ligand_pos=ligand_pos, atom_pos=atom_pos, confidence=confidence)
+    except Exception as e:                                          # inference.py:282-287
+        print('Failed on', getattr(orig, 'name', idx), e)
+        traceback.print_exc()
+        return None
+
+
+def infer_multiple_complexes(rows, *a, **kw):
+    """inference.py:294-304 over a list of rows (dicts with 'complex_graph'); -> (results, count_succeeded)."""
+    results = [infer_single_complex(i, row, *a, **kw) for i, row in rows]
+    return results, sum(r is not None for r in results)
+
+
+def infer_sharded(rows, model, args, score_model_args, device, filtering_model=None, filtering_model_args=None, group=None):
+    """Complexes split over the ranks like ``np.array_split`` (inference.py:468); every rank docks its shard with no
+    communication; one all-gather of (complex index, best confidence) at the end -> global ranking on every rank."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi = shard_range(len(rows), rank, world)
+    sched = get_t_schedule('expbeta', args.inference_steps, inf_sched_alpha=args.inf_sched_alpha, inf_sched_beta=args.inf_sched_beta)   # inference.py:457-459
+    local, ok = infer_multiple_complexes([(i, rows[i]) for i in range(lo, hi)], model, args, score_model_args,
+                                         filtering_model=filtering_model, filtering_model_args=filtering_model_args,
+                                         tr_schedule=sched, device=device)
+    # the single collective of the path: all-gather of the shards' best confidences (padded to the largest shard)
+    width = -(-len(rows) // world) if len(rows) else 1
+    mine = torch.full((width,), float('-inf'), device=device)
+    for r in local:
+        if r is not None and r['confidence'] is not None:
+            mine[r['index'] - lo] = float(r['confidence'][0])
+    if world > 1:
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=group)
+    else:
+        parts = [mine]
+    best = torch.cat([parts[r][:shard_range(len(rows), r, world)[1] - shard_range(len(rows), r, world)[0]] for r in range(world)])
+    return local, best.cpu(), ok

@@ -50,3 +50,12 @@ def test_gather_and_rank_world2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, 0, 4, True), (1, 4, 7, True)]
+
+
+def test_inference_defaults_match_reference_parser():
+    """The sampler flags that reach the hot path carry inference.py's defaults (:75-101)."""
+    from diffdock_pocket_b200 import inference
+    a = inference.default_args()
+    assert (a.samples_per_complex, a.batch_size, a.inference_steps) == (10, 32, 30)
+    assert abs(a.temp_sampling_tr - 0.9766350103728372) < 1e-15 and abs(a.temp_psi_sc_tor - 1.339614553802453) < 1e-15
+    assert abs(a.temp_sigma_data - 0.48884149503636976) < 1e-15
