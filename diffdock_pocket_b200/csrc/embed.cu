@@ -160,6 +160,57 @@ constexpr int kMaxUpdates = 4;
 struct UpdatePack { ddp_update_t u[kMaxUpdates]; int n; };
 
 // One warp per node row: the per-node counts are read once, channels are covered by the lanes (coalesced rows).
+// VEC: rows are read as float2 with every load of the row issued before the first use (f_new, ld even; <= 64 * ITERS).
+template <int ITERS>
+__global__ void node_update_vec_kernel(const float *__restrict__ old_x, int f_old, int ld_old, UpdatePack up, int n,
+                                       int f_new, float *__restrict__ new_x, int ld_new) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    bool live[kMaxUpdates];
+#pragma unroll
+    for (int k = 0; k < kMaxUpdates; ++k) live[k] = k < up.n && *up.u[k].n_edges_dev > 0;
+    for (int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; node < n; node += warps) {
+        float cnt[kMaxUpdates];
+#pragma unroll
+        for (int k = 0; k < kMaxUpdates; ++k) {
+            cnt[k] = 1.f;
+            if (live[k]) {
+                const int dg = up.u[k].deg[node];
+                cnt[k] = (float)(dg < 1 ? 1 : dg);
+            }
+        }
+        float2 o[ITERS], sm[kMaxUpdates][ITERS];
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+            const int c = 2 * (lane + 32 * it);
+            o[it] = make_float2(0.f, 0.f);
+            if (old_x != nullptr && c < f_old) o[it] = *reinterpret_cast<const float2 *>(old_x + (size_t)node * ld_old + c);
+#pragma unroll
+            for (int k = 0; k < kMaxUpdates; ++k) {
+                sm[k][it] = make_float2(0.f, 0.f);
+                if (live[k] && c < f_new) sm[k][it] = *reinterpret_cast<const float2 *>(up.u[k].sum + (size_t)node * f_new + c);
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+            const int c = 2 * (lane + 32 * it);
+            if (c < f_new) {
+                float vx = o[it].x, vy = o[it].y;
+#pragma unroll
+                for (int k = 0; k < kMaxUpdates; ++k) {
+                    if (live[k]) {
+                        const float scx = up.u[k].scale ? __ldg(up.u[k].scale + c) : 1.f, scy = up.u[k].scale ? __ldg(up.u[k].scale + c + 1) : 1.f;
+                        const float sfx = up.u[k].shift ? __ldg(up.u[k].shift + c) : 0.f, sfy = up.u[k].shift ? __ldg(up.u[k].shift + c + 1) : 0.f;
+                        vx += fmaf(__fdiv_rn(sm[k][it].x, cnt[k]), scx, sfx);
+                        vy += fmaf(__fdiv_rn(sm[k][it].y, cnt[k]), scy, sfy);
+                    }
+                }
+                *reinterpret_cast<float2 *>(new_x + (size_t)node * ld_new + c) = make_float2(vx, vy);
+            }
+        }
+    }
+}
+
 __global__ void node_update_kernel(const float *__restrict__ old_x, int f_old, int ld_old, UpdatePack up, int n,
                                    int f_new, float *__restrict__ new_x, int ld_new) {
     const int lane = threadIdx.x & 31;
@@ -385,8 +436,17 @@ extern "C" int ddp_node_update(const float *old_x, int32_t f_old, int32_t ld_old
     UpdatePack up;
     up.n = n_updates;
     for (int i = 0; i < n_updates; ++i) up.u[i] = updates[i];
-    node_update_kernel<<<grid_for((size_t)n * 32, 256), 256, 0, (cudaStream_t)stream>>>(old_x, f_old, ld_old, up, n, f_new,
-                                                                                      new_x, ld_new);
+    // vector path: even widths / strides and 8-byte aligned bases (every buffer of the resident plan qualifies)
+    bool vec = (f_new % 2 == 0) && (f_old % 2 == 0) && (ld_new % 2 == 0) && (ld_old % 2 == 0) && f_new <= 192 &&
+               (reinterpret_cast<uintptr_t>(new_x) % 8 == 0) && (reinterpret_cast<uintptr_t>(old_x) % 8 == 0);
+    for (int i = 0; i < n_updates; ++i) vec = vec && (reinterpret_cast<uintptr_t>(updates[i].sum) % 8 == 0);
+    const int grid = grid_for((size_t)n * 32, 256);
+    if (vec && f_new <= 128)
+        node_update_vec_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(old_x, f_old, ld_old, up, n, f_new, new_x, ld_new);
+    else if (vec)
+        node_update_vec_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>(old_x, f_old, ld_old, up, n, f_new, new_x, ld_new);
+    else
+        node_update_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(old_x, f_old, ld_old, up, n, f_new, new_x, ld_new);
     DDP_LAUNCH_CHECK();
     return 0;
 }
