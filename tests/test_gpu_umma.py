@@ -161,3 +161,29 @@ def test_forward_is_se3_equivariant_at_full_size(mode, n, tol):
     assert T.rel_err(b[0], a[0] @ Rm.T) < tol and T.rel_err(b[1], a[1] @ Rm.T) < tol
     assert T.rel_err(b[2], a[2]) < tol and T.rel_err(b[3], a[3]) < tol
     assert a[2].numel() > 0 and a[3].numel() > 0
+
+
+def test_full_model_final_poses_within_tenth_angstrom_between_modes():
+    """North-star pose gate at FULL model size (README big score model, 20 steps, 3dpf apo with 7 flexible residues):
+    the tensor-core modes end within 0.1 A RMSD of the fp32 CUDA-core mode (itself within 1e-4 of the oracle per
+    layer) for ligand and flexible side-chain atoms, from identical initial poses and noise."""
+    m, c, om, oc, sa, ca = T.models(DEV)
+    g = T.graph('3dpf_apo')
+    dl = T.randomized_list(g, 4, sa, seed=0)
+    steps = 20
+    sch = du.get_t_schedule('expbeta', steps)
+    kw = dict(temp_sampling=[0.9766, 6.0774, 6.7616, 1.4488], temp_psi=[1.5103, 0.8141, 0.7662, 1.3396], temp_sigma_data=0.48884)
+    out = {}
+    try:
+        for mode in ('fp32', 'bf16x3', 'bf16'):
+            m.conv_mode = mode
+            torch.manual_seed(5)
+            res, _ = ps.sampling(copy.deepcopy(dl), m, steps, sch, sch, sch, sch, DEV, partial(du.t_to_sigma, args=sa), sa, batch_size=4, **kw)
+            out[mode] = (torch.stack([r['ligand'].pos for r in res]), torch.stack([r['atom'].pos for r in res]))
+    finally:
+        m.conv_mode = 'fp32'
+    flex = g['flexResidues'].subcomponents.unique()
+    for mode, tol in (('bf16x3', 1e-2), ('bf16', 0.1)):
+        lig = ((out[mode][0] - out['fp32'][0]) ** 2).sum(-1).mean(-1).sqrt().max()
+        sc = ((out[mode][1][:, flex] - out['fp32'][1][:, flex]) ** 2).sum(-1).mean(-1).sqrt().max()
+        assert float(lig) < tol and float(sc) < tol, (mode, float(lig), float(sc))
