@@ -67,29 +67,75 @@ def infer_single_complex(idx, protein_ligand_info_row, model, args, score_model_
             temp_psi=[args.temp_psi_tr, args.temp_psi_rot, args.temp_psi_tor, args.temp_psi_sc_tor],
             flexible_sidechains=flex)     # reference quirk kept: --temp_sigma_data is parsed (:101) but never passed
         #                                   to sampling() (:177-196), so its default 0.5 applies
-        center = np.asarray(orig.original_center.cpu().numpy() if torch.is_tensor(orig.original_center) else orig.original_center)
-        ligand_pos = np.asarray([g['ligand'].pos.cpu().numpy() + center for g in data_list])
-        atom_pos = np.asarray([g['atom'].pos.cpu().numpy() + center for g in data_list])
-        if confidence is not None:
-            if confidence.dim() == 2:                               # multi-cutoff confidence heads: first column ranks
-                confidence = confidence[:, 0]
-            confidence = confidence.cpu().numpy()
-            order = np.argsort(confidence)[::-1]
-            confidence, ligand_pos, atom_pos = confidence[order], ligand_pos[order], atom_pos[order]
-        return dict(name=orig.name, index=idx, ligand_pos=ligand_pos, atom_pos=atom_pos, confidence=confidence)
+        return _rank(orig, idx, data_list, confidence)                  # inference.py:198-219
     except Exception as e:                                          # inference.py:282-287
         print('Failed on', getattr(orig, 'name', idx), e)
         traceback.print_exc()
         return None
 
 
-def infer_multiple_complexes(rows, *a, **kw):
-    """inference.py:294-304 over a list of rows (dicts with 'complex_graph'); -> (results, count_succeeded)."""
-    results = [infer_single_complex(i, row, *a, **kw) for i, row in rows]
+def _rank(orig, idx, graphs, confidence):
+    center = np.asarray(orig.original_center.cpu().numpy() if torch.is_tensor(orig.original_center) else orig.original_center)
+    ligand_pos = np.asarray([g['ligand'].pos.cpu().numpy() + center for g in graphs])
+    atom_pos = np.asarray([g['atom'].pos.cpu().numpy() + center for g in graphs])
+    if confidence is not None:
+        if confidence.dim() == 2:
+            confidence = confidence[:, 0]
+        confidence = confidence.cpu().numpy()
+        order = np.argsort(confidence)[::-1]
+        confidence, ligand_pos, atom_pos = confidence[order], ligand_pos[order], atom_pos[order]
+    return dict(name=orig.name, index=idx, ligand_pos=ligand_pos, atom_pos=atom_pos, confidence=confidence)
+
+
+def infer_complex_group(group, model, args, score_model_args, filtering_model=None, filtering_model_args=None,
+                        tr_schedule=None, t_schedule=None, device=None):
+    """Cross-complex batching (the reference's sampler assumes one complex per call, F9): the samples
+    of several complexes share one ``sampling()`` call, so that small ``samples_per_complex`` still fill the mini-batch
+    (virtual screening).  ``group``: [(idx, row), ...].  Falls back to one call per complex if the joint call fails."""
+    spc = args.samples_per_complex
+    flex = False if args.rigid else score_model_args.flexible_sidechains
+    try:
+        data_list = []
+        for _, row in group:
+            dl = [copy.deepcopy(row['complex_graph']) for _ in range(spc)]
+            randomize_position(dl, score_model_args.no_torsion, args.no_random, score_model_args.tr_sigma_max, flexible_sidechains=flex)
+            data_list += dl
+        steps = args.actual_steps if args.actual_steps is not None else args.inference_steps
+        data_list, confidence = sampling(
+            data_list=data_list, model=model, inference_steps=steps, tr_schedule=tr_schedule, rot_schedule=tr_schedule,
+            tor_schedule=tr_schedule, sidechain_tor_schedule=tr_schedule, t_schedule=t_schedule,
+            t_to_sigma=partial(t_to_sigma_compl, args=score_model_args), model_args=score_model_args,
+            confidence_model=filtering_model, device=device, no_random=args.no_random, ode=args.ode,
+            filtering_model_args=filtering_model_args, batch_size=args.batch_size, no_final_step_noise=args.no_final_step_noise,
+            temp_sampling=[args.temp_sampling_tr, args.temp_sampling_rot, args.temp_sampling_tor, args.temp_sampling_sc_tor],
+            temp_psi=[args.temp_psi_tr, args.temp_psi_rot, args.temp_psi_tor, args.temp_psi_sc_tor], flexible_sidechains=flex)
+        return [_rank(row['complex_graph'], idx, data_list[k * spc:(k + 1) * spc],
+                      confidence[k * spc:(k + 1) * spc] if confidence is not None else None) for k, (idx, row) in enumerate(group)]
+    except Exception as e:
+        print('Joint call failed for', [row['complex_graph'].name for _, row in group], e, '- retrying one complex at a time')
+        return [infer_single_complex(idx, row, model, args, score_model_args, filtering_model=filtering_model,
+                                     filtering_model_args=filtering_model_args, tr_schedule=tr_schedule, t_schedule=t_schedule,
+                                     device=device) for idx, row in group]
+
+
+def infer_multiple_complexes(rows, *a, batch_complexes=False, **kw):
+    """inference.py:294-304 over a list of (idx, row) (rows: dicts with 'complex_graph'); -> (results, count_succeeded).
+    ``batch_complexes``: pack floor(batch_size / samples_per_complex) complexes into each sampler call."""
+    args = a[1] if len(a) > 1 else kw['args']
+    per_call = max(1, args.batch_size // args.samples_per_complex) if batch_complexes else 1
+    if per_call == 1:
+        results = [infer_single_complex(i, row, *a, **kw) for i, row in rows]
+    else:
+        model, score_model_args = (a[0] if a else kw['model']), (a[2] if len(a) > 2 else kw['score_model_args'])
+        passthrough = {k: kw[k] for k in ('filtering_model', 'filtering_model_args', 'tr_schedule', 't_schedule', 'device') if k in kw}
+        results = []
+        for j in range(0, len(rows), per_call):
+            results += infer_complex_group(rows[j:j + per_call], model, args, score_model_args, **passthrough)
     return results, sum(r is not None for r in results)
 
 
-def infer_sharded(rows, model, args, score_model_args, device, filtering_model=None, filtering_model_args=None, group=None):
+def infer_sharded(rows, model, args, score_model_args, device, filtering_model=None, filtering_model_args=None, group=None,
+                  batch_complexes=False):
     """Complexes split over the ranks like ``np.array_split`` (inference.py:468); every rank docks its shard with no
     communication; one all-gather of (complex index, best confidence) at the end -> global ranking on every rank."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -98,7 +144,7 @@ def infer_sharded(rows, model, args, score_model_args, device, filtering_model=N
     sched = get_t_schedule('expbeta', args.inference_steps, inf_sched_alpha=args.inf_sched_alpha, inf_sched_beta=args.inf_sched_beta)   # inference.py:457-459
     local, ok = infer_multiple_complexes([(i, rows[i]) for i in range(lo, hi)], model, args, score_model_args,
                                          filtering_model=filtering_model, filtering_model_args=filtering_model_args,
-                                         tr_schedule=sched, device=device)
+                                         tr_schedule=sched, device=device, batch_complexes=batch_complexes)
     # the single collective of the path: all-gather of the shards' best confidences (padded to the largest shard)
     width = -(-len(rows) // world) if len(rows) else 1
     mine = torch.full((width,), float('-inf'), device=device)

@@ -23,6 +23,7 @@ p.add_argument('--complexes', type=int, default=16)
 p.add_argument('--samples', type=int, default=10)
 p.add_argument('--steps', type=int, default=20)
 p.add_argument('--mode', default='bf16')
+p.add_argument('--batch-complexes', action='store_true', help='pack several complexes into one sampler call')
 p.add_argument('--one-pocket', action='store_true', help='configs[4]: one pocket, many ligands')
 a = p.parse_args()
 world, rank, local = (int(os.environ.get(k, d)) for k, d in (('WORLD_SIZE', 1), ('RANK', 0), ('LOCAL_RANK', 0)))
@@ -44,7 +45,8 @@ np.random.seed(1 + rank)
 torch.manual_seed(1 + rank)
 torch.cuda.synchronize()
 t0 = time.time()
-res, best, ok = inference.infer_sharded(rows, model, args, sa, dev, filtering_model=conf, filtering_model_args=ca)
+res, best, ok = inference.infer_sharded(rows, model, args, sa, dev, filtering_model=conf, filtering_model_args=ca,
+                                        batch_complexes=a.batch_complexes)
 torch.cuda.synchronize()
 dt = time.time() - t0
 if world > 1:

@@ -210,3 +210,28 @@ def test_sampling_parity_small_model():
         rmsd_sc = float(((a['atom'].pos.cpu()[idx] - r['atom'].pos[idx]) ** 2).sum(-1).mean().sqrt())
         assert rmsd < 0.1 and rmsd_sc < 0.1, (rmsd, rmsd_sc)
     assert T.rel_err(conf, ref_conf) < 1e-2
+
+
+def test_mixed_complex_batch_equals_per_complex_calls():
+    """Cross-complex batching: samples of three different complexes (different ligand / pocket sizes, one without
+    flexible residues' torsions) in ONE sampler call end where three separate calls end (noise off => deterministic)."""
+    from functools import partial
+    from diffdock_pocket_b200 import diffusion_utils as du, inputs as inp, sampling as ps
+    m, c, om, oc, sa, ca = T.models(DEV, small=True)
+    graphs = [inp.synthetic_complex(11, n_lig=12, n_res=30, flexible_residues=2), inp.synthetic_complex(12, n_lig=25, n_res=45, flexible_residues=3),
+              inp.synthetic_complex(13, n_lig=9, n_res=26, flexible_residues=1)]
+    lists = [T.randomized_list(g, 3, sa, seed=20 + i) for i, g in enumerate(graphs)]
+    steps = 5
+    sch = du.get_t_schedule('expbeta', steps)
+    kw = dict(temp_sampling=[0.9766, 6.0774, 6.7616, 1.4488], temp_psi=[1.5103, 0.8141, 0.7662, 1.3396], temp_sigma_data=0.48884,
+              no_random=True, confidence_model=c, filtering_model_args=ca)
+    run = lambda dl, bs: ps.sampling(copy.deepcopy(dl), m, steps, sch, sch, sch, sch, DEV, partial(du.t_to_sigma, args=sa), sa, batch_size=bs, **kw)
+    joint, conf_j = run([g for dl in lists for g in dl], 5)                  # mini-batches straddle complexes
+    k = 0
+    for dl in lists:
+        sep, conf_s = run(dl, 3)
+        for a, b in zip(joint[k:k + 3], sep):
+            assert float((a['ligand'].pos - b['ligand'].pos).abs().max()) < 2e-3
+            assert float((a['atom'].pos - b['atom'].pos).abs().max()) < 2e-3
+        assert T.rel_err(conf_j[k:k + 3], conf_s) < 1e-3
+        k += 3
