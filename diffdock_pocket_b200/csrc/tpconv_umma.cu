@@ -183,18 +183,6 @@ __device__ __forceinline__ uint32_t instr_desc(int n) {
     // c=f32 (1<<4), a=bf16 (1<<7), b=bf16 (1<<10), K-major A and B, N>>3 at bit 17, M>>4 at bit 24
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
 // Asynchronous TMEM load of 16 columns (this thread's lane): the registers are valid only after tmem_wait16(v).
 __device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
@@ -366,7 +354,7 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
     int *pref = reinterpret_cast<int *>(tmem_base_smem + 2);            // [MAX_JOBS + 1]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_jobs = jobs.n, f_in = jobs.f_in, f_out = jobs.f_out;
+    const int n_jobs = jobs.n, f_out = jobs.f_out;
     const Header *hdr = reinterpret_cast<const Header *>(jobs.job[0].image);
     const int n_tiles = hdr->n_tiles;
 
