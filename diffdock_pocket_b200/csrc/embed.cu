@@ -169,6 +169,20 @@ __global__ void node_update_vec_kernel(const float *__restrict__ old_x, int f_ol
     bool live[kMaxUpdates];
 #pragma unroll
     for (int k = 0; k < kMaxUpdates; ++k) live[k] = k < up.n && *up.u[k].n_edges_dev > 0;
+    // per-channel BatchNorm scale / shift of this lane's channels: loaded once, reused for every node of the warp
+    float2 sc[kMaxUpdates][ITERS], sf[kMaxUpdates][ITERS];
+#pragma unroll
+    for (int k = 0; k < kMaxUpdates; ++k)
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+            const int c = 2 * (lane + 32 * it);
+            sc[k][it] = make_float2(1.f, 1.f);
+            sf[k][it] = make_float2(0.f, 0.f);
+            if (live[k] && c < f_new) {
+                if (up.u[k].scale) sc[k][it] = make_float2(__ldg(up.u[k].scale + c), __ldg(up.u[k].scale + c + 1));
+                if (up.u[k].shift) sf[k][it] = make_float2(__ldg(up.u[k].shift + c), __ldg(up.u[k].shift + c + 1));
+            }
+        }
     for (int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; node < n; node += warps) {
         float cnt[kMaxUpdates];
 #pragma unroll
@@ -199,10 +213,8 @@ __global__ void node_update_vec_kernel(const float *__restrict__ old_x, int f_ol
 #pragma unroll
                 for (int k = 0; k < kMaxUpdates; ++k) {
                     if (live[k]) {
-                        const float scx = up.u[k].scale ? __ldg(up.u[k].scale + c) : 1.f, scy = up.u[k].scale ? __ldg(up.u[k].scale + c + 1) : 1.f;
-                        const float sfx = up.u[k].shift ? __ldg(up.u[k].shift + c) : 0.f, sfy = up.u[k].shift ? __ldg(up.u[k].shift + c + 1) : 0.f;
-                        vx += fmaf(__fdiv_rn(sm[k][it].x, cnt[k]), scx, sfx);
-                        vy += fmaf(__fdiv_rn(sm[k][it].y, cnt[k]), scy, sfy);
+                        vx += fmaf(__fdiv_rn(sm[k][it].x, cnt[k]), sc[k][it].x, sf[k][it].x);
+                        vy += fmaf(__fdiv_rn(sm[k][it].y, cnt[k]), sc[k][it].y, sf[k][it].y);
                     }
                 }
                 *reinterpret_cast<float2 *>(new_x + (size_t)node * ld_new + c) = make_float2(vx, vy);
@@ -440,7 +452,8 @@ extern "C" int ddp_node_update(const float *old_x, int32_t f_old, int32_t ld_old
     bool vec = (f_new % 2 == 0) && (f_old % 2 == 0) && (ld_new % 2 == 0) && (ld_old % 2 == 0) && f_new <= 192 &&
                (reinterpret_cast<uintptr_t>(new_x) % 8 == 0) && (reinterpret_cast<uintptr_t>(old_x) % 8 == 0);
     for (int i = 0; i < n_updates; ++i) vec = vec && (reinterpret_cast<uintptr_t>(updates[i].sum) % 8 == 0);
-    const int grid = grid_for((size_t)n * 32, 256);
+    int grid = grid_for((size_t)n * 32, 256);
+    if (vec && grid > 6 * ddp_num_sms()) grid = 6 * ddp_num_sms();      // several nodes per warp: scale / shift stay in registers
     if (vec && f_new <= 128)
         node_update_vec_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(old_x, f_old, ld_old, up, n, f_new, new_x, ld_new);
     else if (vec)
