@@ -49,6 +49,10 @@ class MlpLayer(C.Structure):
     _fields_ = [('wt', vp), ('b', vp), ('n_in', i32), ('n_out', i32), ('act', i32)]
 
 
+class FtpPath(C.Structure):
+    _fields_ = [('in_off', i32), ('d_in', i32), ('out_off', i32), ('d_out', i32), ('c_off', i32)]
+
+
 class StepCoef(C.Structure):
     _fields_ = [(k, f32) for k in ('a_tr', 'b_tr', 'a_rot', 'b_rot', 'a_tor', 'b_tor', 'a_sc', 'b_sc')]
 
@@ -77,6 +81,7 @@ _SIGS = {
     'ddp_segment_mean': (i32, [vp, vp, vp, i32, i32, i32, vp, i32, vp]),
     'ddp_bond_geometry': (i32, [vp, vp, i32, vp, i32, i32, vp, vp, vp, vp]),
     'ddp_tor_edge_sh': (i32, [vp, i32, vp, vp, vp, vp, i32, vp, vp]),
+    'ddp_tor_edge_sh_generic': (i32, [vp, i32, vp, C.POINTER(FtpPath), i32, vp, vp, vp, i32, vp, i32, vp]),
     'ddp_row_mlp': (i32, [vp, i32, i32, C.POINTER(MlpLayer), i32, vp, vp, i32, vp]),
     'ddp_tr_rot_head': (i32, [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
     'ddp_pose_update': (i32, [C.POINTER(Pose), C.POINTER(StepCoef), vp]),

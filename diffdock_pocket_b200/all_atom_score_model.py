@@ -143,28 +143,49 @@ class TensorProductScoreModel(nn.Module):
             self.tr_final_layer = nn.Sequential(nn.Linear(1 + sigma_embed_dim, ns), nn.Dropout(dropout), nn.ReLU(), nn.Linear(ns, 1))
             self.rot_final_layer = nn.Sequential(nn.Linear(1 + sigma_embed_dim, ns), nn.Dropout(dropout), nn.ReLU(), nn.Linear(ns, 1))
             tor_sh = tpmod.full_tp_out_irreps(self.sh_irreps, '1x2e')
+            self._tor_ftp = self._tor_ftp_table(last, tor_sh, ns)
             if not no_torsion:
                 self.final_edge_embedding = _mlp(distance_embed_dim, ns, ns, dropout)
                 self.final_tp_tor = nn.Module()          # o3.FullTensorProduct has no parameters
-                self.tor_bond_conv = self._tor_conv(last, tor_sh, ns, dropout, batch_norm)
+                self.tor_bond_conv = self._tor_conv(last, tor_sh, ns, dropout, batch_norm, self._tor_ftp)
                 self.tor_final_layer = nn.Sequential(nn.Linear(2 * ns, ns, bias=False), nn.Tanh(), nn.Dropout(dropout),
                                                      nn.Linear(ns, 1, bias=False))
             if flexible_sidechains:
                 self.sidechain_final_edge_embedding = _mlp(distance_embed_dim, ns, ns, dropout)
                 self.final_tp_sc_tor = nn.Module()
-                self.sc_tor_bond_conv = self._tor_conv(last, tor_sh, ns, dropout, batch_norm)
+                self.sc_tor_bond_conv = self._tor_conv(last, tor_sh, ns, dropout, batch_norm, self._tor_ftp)
                 self.sc_tor_final_layer = nn.Sequential(nn.Linear(2 * ns, ns, bias=False), nn.Tanh(), nn.Dropout(dropout),
                                                         nn.Linear(ns, 1, bias=False))
         self._packed = None
 
+    def _tor_ftp_table(self, last, tor_sh, ns):
+        """Which irreps of sh_tor = FullTensorProduct(sh_edge, Y2(bond)) the torsion convs read, and how to compute them.
+        lmax 1: only the 1o part, laid out [1 | 1o] so the conv looks FasterTensorProduct-shaped (tensor-core eligible,
+        ``ddp_tor_edge_sh``).  lmax 2: 0e, 1o, 1e via the generic path table of ``ddp_tor_edge_sh_generic``."""
+        used = tpmod.fctp_used_sh(last, tor_sh, f'{ns}x0o + {ns}x0e')
+        if self.sh_lmax == 1:
+            assert used == [0]
+            return dict(keep=[0], base=1, dim=4, paths=None, ctab=None)
+        prov = tpmod.full_tp_paths(self.sh_irreps, '1x2e')
+        sh_off = tpmod.irreps_offsets(self.sh_irreps)
+        paths, ctab, o = [], [], 0
+        for k in used:
+            lo, _, i1, _ = prov[k]
+            l1 = self.sh_irreps[i1][1]
+            cg = tpmod.wigner_3j(l1, 2, lo) * np.sqrt(2 * lo + 1)             # e3nn FullTensorProduct, component normalisation
+            paths.append(dict(in_off=sh_off[i1], d_in=2 * l1 + 1, out_off=o, d_out=2 * lo + 1, c_off=len(ctab)))
+            ctab += [float(v) for v in cg.reshape(-1)]
+            o += 2 * lo + 1
+        return dict(keep=used, base=0, dim=o, paths=paths, ctab=ctab)
+
     @staticmethod
-    def _tor_conv(last, tor_sh, ns, dropout, batch_norm):
+    def _tor_conv(last, tor_sh, ns, dropout, batch_norm, ftp):
         conv = TensorProductConvLayer(last, tor_sh, f'{ns}x0o + {ns}x0e', 3 * ns, residual=False, dropout=dropout,
                                       batch_norm=batch_norm)
-        # only the 1o part of sh_tor is materialised, as [1 | 1o] (ddp_tor_edge_sh); valid while node irreps have l <= 1
-        spec = tpmod.fctp_spec(last, tor_sh, f'{ns}x0o + {ns}x0e', sh_keep=[0], sh_base=1)
+        # only the sh_tor irreps the conv can couple to are materialised (valid while node irreps have l <= 1)
+        spec = tpmod.fctp_spec(last, tor_sh, f'{ns}x0o + {ns}x0e', sh_keep=ftp['keep'], sh_base=ftp['base'])
         assert spec.weight_numel == conv.tp.weight_numel
-        spec.tc_eligible = all(l <= 1 for _, l, _ in tpmod.parse_irreps(last))
+        spec.tc_eligible = ftp['paths'] is None and all(l <= 1 for _, l, _ in tpmod.parse_irreps(last))
         conv.tp = _TP(spec)
         return conv
 
@@ -244,6 +265,9 @@ class TensorProductScoreModel(nn.Module):
             P['tr'] = lin(self.tr_final_layer[0]) + lin(self.tr_final_layer[3])
             P['rot'] = lin(self.rot_final_layer[0]) + lin(self.rot_final_layer[3])
             P['c121'] = torch.tensor((tpmod.wigner_3j(1, 2, 1) * np.sqrt(3.0)).reshape(-1), **f32)
+            if self._tor_ftp['paths'] is not None:
+                P['ftp_ctab'] = torch.tensor(self._tor_ftp['ctab'], **f32)
+                P['ftp_paths'] = (_lib.FtpPath * len(self._tor_ftp['paths']))(*[_lib.FtpPath(**q) for q in self._tor_ftp['paths']])
             if not self.no_torsion:
                 P['tor_conv'] = self.tor_bond_conv.packed(dev, ns, ns, em['tor']['fold'])
                 P['tor_mlp'] = [lin(self.tor_final_layer[0]), lin(self.tor_final_layer[3])]
@@ -400,7 +424,7 @@ class TensorProductScoreModel(nn.Module):
         h.batch = bond_batch.to(**i32)
         h.mid, h.y2, h.attr = torch.zeros(n, 3, **f32), torch.zeros(n, 5, **f32), torch.zeros(n, self.ns, **f32)
         h.es = _EdgeSet(n * min(32, max_seg), self.ns, self.sh_dim, dev, with_slab=(n, min(32, max_seg)))
-        h.sh_tor = torch.zeros(h.es.cap, 4, **f32)
+        h.sh_tor = torch.zeros(h.es.cap, self._tor_ftp['dim'], **f32)
         h.deg = torch.zeros(n, **i32)
         h.sum = torch.zeros(n, 2 * self.ns, **f32)
         h.feat = torch.zeros(n, 2 * self.ns, **f32)
@@ -640,7 +664,11 @@ class TensorProductScoreModel(nn.Module):
                              ptr(e.slab), e.slab_w, ptr(e.counts), ptr(e.edge), e.cap, ptr(e.n_dev), st), f'ddp_radius({key})')
             chk(L.ddp_edge_embed(ptr(h.mid), ptr(pos), ptr(e.edge), e.cap, ptr(e.n_dev), ptr(h.batch), None, 0, None,
                                  C.byref(em[emk]['desc']), ptr(e.sh), ptr(e.emb), st), f'ddp_edge_embed({key})')
-            chk(L.ddp_tor_edge_sh(ptr(e.sh), self.sh_dim, ptr(h.y2), ptr(P['c121']), ptr(e.edge), ptr(e.n_dev), e.cap, ptr(h.sh_tor), st), 'tor_edge_sh')
+            if self._tor_ftp['paths'] is None:
+                chk(L.ddp_tor_edge_sh(ptr(e.sh), self.sh_dim, ptr(h.y2), ptr(P['c121']), ptr(e.edge), ptr(e.n_dev), e.cap, ptr(h.sh_tor), st), 'tor_edge_sh')
+            else:
+                chk(L.ddp_tor_edge_sh_generic(ptr(e.sh), self.sh_dim, ptr(h.y2), P['ftp_paths'], len(P['ftp_paths']), ptr(P['ftp_ctab']),
+                                              ptr(e.edge), ptr(e.n_dev), e.cap, ptr(h.sh_tor), self._tor_ftp['dim'], st), 'tor_edge_sh_generic')
             e.sh_conv = h.sh_tor
             h.sum.zero_()
             h.deg.zero_()

@@ -316,6 +316,34 @@ __global__ void tor_edge_sh_kernel(const float *__restrict__ sh, int sh_dim, con
     }
 }
 
+// Generic form: out[e][p.out_off + k] = sum_{i, j} ctab[p.c_off + (i * 5 + j) * p.d_out + k] * sh[e][p.in_off + i] * y2[bond][j]
+constexpr int kMaxFtpPaths = 8;
+struct FtpPack { ddp_ftp_path_t p[kMaxFtpPaths]; int n; };
+
+__global__ void tor_edge_sh_generic_kernel(const float *__restrict__ sh, int sh_dim, const float *__restrict__ y2, FtpPack fp,
+                                           const float *__restrict__ ctab, const int32_t *__restrict__ edge,
+                                           const int32_t *__restrict__ n_edges_dev, int cap, float *__restrict__ out, int out_dim) {
+    const int n_edges = min(*n_edges_dev, cap);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += gridDim.x * blockDim.x) {
+        const int bnd = edge[e];
+        float y[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) y[j] = y2[5 * bnd + j];
+        for (int q = 0; q < fp.n; ++q) {
+            const ddp_ftp_path_t p = fp.p[q];
+            for (int k = 0; k < p.d_out; ++k) {
+                float o = 0.f;
+                for (int i = 0; i < p.d_in; ++i) {
+                    const float a = sh[(size_t)e * sh_dim + p.in_off + i];
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) o = fmaf(__ldg(ctab + p.c_off + (i * 5 + j) * p.d_out + k), a * y[j], o);
+                }
+                out[(size_t)e * out_dim + p.out_off + k] = o;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxLayers = 4;
 struct MlpPack { ddp_mlp_layer_t l[kMaxLayers]; int n; };
@@ -488,6 +516,25 @@ extern "C" int ddp_tor_edge_sh(const float *sh, int32_t sh_dim, const float *y2,
     if (edge_cap <= 0) return 0;
     tor_edge_sh_kernel<<<grid_for(edge_cap, 128), 128, 0, (cudaStream_t)stream>>>(sh, sh_dim, y2, c121, edge, n_edges_dev,
                                                                                  edge_cap, sh_tor);
+    DDP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ddp_tor_edge_sh_generic(const float *sh, int32_t sh_dim, const float *y2, const ddp_ftp_path_t *paths_host,
+                                       int32_t n_paths, const float *ctab, const int32_t *edge, const int32_t *n_edges_dev,
+                                       int32_t edge_cap, float *out, int32_t out_dim, void *stream) {
+    if (!sh || !y2 || !paths_host || !ctab || !edge || !n_edges_dev || !out) return DDP_E_ARG;
+    if (n_paths <= 0 || n_paths > kMaxFtpPaths) return DDP_E_SHAPE;
+    FtpPack fp;
+    fp.n = n_paths;
+    for (int i = 0; i < n_paths; ++i) {
+        fp.p[i] = paths_host[i];
+        if (fp.p[i].in_off < 0 || fp.p[i].in_off + fp.p[i].d_in > sh_dim || fp.p[i].out_off < 0 || fp.p[i].out_off + fp.p[i].d_out > out_dim)
+            return DDP_E_SHAPE;
+    }
+    if (edge_cap <= 0) return 0;
+    tor_edge_sh_generic_kernel<<<grid_for(edge_cap, 128), 128, 0, (cudaStream_t)stream>>>(sh, sh_dim, y2, fp, ctab, edge, n_edges_dev,
+                                                                                         edge_cap, out, out_dim);
     DDP_LAUNCH_CHECK();
     return 0;
 }

@@ -201,6 +201,21 @@ def full_tp_out_irreps(ir1, ir2):
     return sorted(outs, key=lambda t: (t[1], t[2]))
 
 
+def full_tp_paths(ir1, ir2):
+    """FullTensorProduct outputs in e3nn's sorted order with their provenance: [(l_out, p_out, i1, i2)]."""
+    ir1, ir2 = parse_irreps(ir1), parse_irreps(ir2)
+    outs = [(lo, p1 * p2, a, b) for a, (m1, l1, p1) in enumerate(ir1) for b, (m2, l2, p2) in enumerate(ir2)
+            for lo in range(abs(l1 - l2), l1 + l2 + 1)]
+    return sorted(outs, key=lambda t: (t[0], t[1]))
+
+
+def fctp_used_sh(in_irreps, sh_irreps, out_irreps):
+    """Indices of the sh irreps that some FullyConnectedTensorProduct instruction reads."""
+    in_irreps, sh_irreps, out_irreps = parse_irreps(in_irreps), parse_irreps(sh_irreps), parse_irreps(out_irreps)
+    return sorted({i2 for (_, l1, p1) in in_irreps for i2, (_, l2, p2) in enumerate(sh_irreps)
+                   for (_, lo, po) in out_irreps if abs(l1 - l2) <= lo <= l1 + l2 and po == p1 * p2})
+
+
 def batch_norm_fold(irreps, running_mean, running_var, weight, bias, eps=1e-5):
     """e3nn.nn.BatchNorm (eval) as per-channel scale / shift over the flattened feature vector:
     y = x * scale + shift with shift != 0 only on 0e channels."""

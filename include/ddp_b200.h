@@ -216,6 +216,16 @@ int ddp_bond_geometry(const float *pos, const int32_t *bonds, int32_t n_bonds, c
 int ddp_tor_edge_sh(const float *sh, int32_t sh_dim, const float *y2, const float *c121 /* [3][5][3], sqrt(3) folded */,
                     const int32_t *edge, const int32_t *n_edges_dev, int32_t edge_cap, float *sh_tor, void *stream);
 
+/* General form for sh_lmax = 2 (all_atom_score_model.py:193,219,395,419): the l <= 1 output irreps of
+ * FullTensorProduct(sh_edge, Y2[bond]) that the torsion convolutions can couple to (0e from 2e x 2e, 1o from 1o x 2e,
+ * 1e from 2e x 2e), written contiguously to out [cap][out_dim].  Path q:
+ *   out[e][out_off + k] = sum_{i < d_in, j < 5} ctab[c_off + (i * 5 + j) * d_out + k] * sh[e][in_off + i] * y2[bond][j]
+ * with ctab = sqrt(2 l_out + 1) * wigner_3j(l_in, 2, l_out) (e3nn FullTensorProduct, component normalisation). */
+typedef struct { int32_t in_off, d_in, out_off, d_out, c_off; } ddp_ftp_path_t;
+int ddp_tor_edge_sh_generic(const float *sh, int32_t sh_dim, const float *y2, const ddp_ftp_path_t *paths_host, int32_t n_paths,
+                            const float *ctab, const int32_t *edge, const int32_t *n_edges_dev, int32_t edge_cap, float *out,
+                            int32_t out_dim, void *stream);
+
 /* row MLP (tor_final_layer / sc_tor_final_layer :402,427; confidence_predictor :344 with BatchNorm1d folded):
  * x <- act_l(W_l x + b_l) for up to 4 layers (W input-major [n_in][n_out], b may be NULL; act 0 none,
  * 1 relu, 2 tanh), then out[row][:] = x * (row_scale ? row_scale[row] : 1).  Widths <= 256. */

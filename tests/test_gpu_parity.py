@@ -235,3 +235,26 @@ def test_mixed_complex_batch_equals_per_complex_calls():
             assert float((a['atom'].pos - b['atom'].pos).abs().max()) < 2e-3
         assert T.rel_err(conf_j[k:k + 3], conf_s) < 1e-3
         k += 3
+
+
+def test_forward_sh_lmax2_model_vs_oracle():
+    """sh_lmax = 2 (the argparse / model default, utils/parsing.py:131): trunk convs are e3nn FullyConnectedTensorProducts
+    with 9 spherical harmonics, the torsion heads couple to the 0e, 1o and 1e parts of FullTensorProduct(sh, Y2(bond))."""
+    from diffdock_pocket_b200 import inputs as inp, so3, torus, utils
+    from oracle import factory
+    sa = utils.score_model_args(sh_lmax=2, ns=16, nv=4, num_conv_layers=3, sigma_embed_dim=32, distance_embed_dim=32,
+                                cross_distance_embed_dim=32)
+    m, _, sa, _ = utils.build_models(DEV, score_args=sa, with_confidence=False, seed=3)
+    om = factory.oracle_model(sa, m.state_dict(), so3.score_norm_np, torus.score_norm)
+    g = inp.synthetic_complex(7, n_lig=18, n_res=36, flexible_residues=3)
+    dl = T.randomized_list(g, 3, sa, seed=1)
+    b = T.batch_at(dl, 0.35)
+    m.conv_mode = 'fp32'
+    with torch.no_grad():
+        pl = m.make_plan(copy.deepcopy(b))
+        got = m.run_plan(pl, b.complex_t, return_layers=True)
+        want = om(copy.deepcopy(b))
+    for l, ((gl, ga, gr), (wl, wa, wr)) in enumerate(zip(pl.last_layers, om._debug['layers'])):
+        assert T.rel_err(gl, wl) < 1e-4 and T.rel_err(ga[:, :wa.shape[1]], wa) < 1e-4, l
+    for a, w, key in zip(got, want, ('tr', 'rot', 'tor', 'sc')):
+        assert a.numel() > 0 and T.rel_err(a, w) < 1e-4, (key, T.rel_err(a, w))
