@@ -298,7 +298,7 @@ struct Cfg {
     static constexpr int NBUF = (TS || SPLIT) ? 1 : 2;
     static constexpr int A_TOTAL = A_BYTES * (SPLIT ? 2 : 1) * NBUF;
     static constexpr int MAX_TILES = 64;
-    static constexpr int FIXED = 1024 + A_TOTAL + MAX_TILES * (int)sizeof(TileDesc) + 512;
+    static constexpr int FIXED = 1024 + A_TOTAL + MAX_TILES * (int)sizeof(TileDesc) + 1024;
     static constexpr int STAGES_FIT = (220 * 1024 - FIXED) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_FIT > 12 ? 12 : STAGES_FIT;
     static constexpr size_t SMEM = (size_t)FIXED + (size_t)STAGES * STAGE_BYTES;
@@ -316,6 +316,25 @@ __device__ __forceinline__ void locate(const int *pref, int n_jobs, int g, int &
     while (j + 1 < n_jobs && g >= pref[j + 1]) ++j;
     job = j;
     et = g - pref[j];
+}
+
+// Work items.  Edge tiles are dealt round-robin to the CTAs; the last, partial round (R = n_etiles mod grid tiles for
+// grid CTAs) would leave most SMs idle for a whole tile time, so each of its edge tiles is split `k` ways along the
+// weight tiles (contiguous ranges of equal MMA cost): every part redoes the cheap gather + GEMM1 and adds its partial
+// sums with the same atomics.  Item w < n_full: edge tile w, all weight tiles; else edge tile n_full + (w - n_full) / k,
+// weight tiles [split[p], split[p + 1]) with p = (w - n_full) % k.
+constexpr int SPLIT_MAX = 8;
+struct Work {
+    int n_items, n_full, k;
+    int split[SPLIT_MAX + 1];
+};
+__device__ __forceinline__ void work_item(const Work &wk, int w, int n_tiles, int &g, int &t0, int &t1) {
+    if (w < wk.n_full) { g = w; t0 = 0; t1 = n_tiles; return; }
+    const int idx = w - wk.n_full;
+    g = wk.n_full + idx / wk.k;
+    const int p = idx % wk.k;
+    t0 = wk.split[p];
+    t1 = wk.split[p + 1];
 }
 
 // Issue the global loads of the gathered node features one weight tile reads (n_fl floats from xg): pairs when the
@@ -352,6 +371,9 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
     uint64_t *a_ready = tmem_empty + 2, *a_free = a_ready + 2, *h_ready = a_free + 2;
     uint32_t *tmem_base_smem = reinterpret_cast<uint32_t *>(h_ready + 1);
     int *pref = reinterpret_cast<int *>(tmem_base_smem + 2);            // [MAX_JOBS + 1]
+    Work *work = reinterpret_cast<Work *>(pref + MAX_JOBS + 1);
+    uint32_t *tile_off = reinterpret_cast<uint32_t *>(work + 1);        // [MAX_TILES + 1] byte offset of every tile's slabs
+    int *cum = reinterpret_cast<int *>(tile_off + C::MAX_TILES + 1);    // [MAX_TILES + 1] MMA cost prefix (set-up only)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_jobs = jobs.n, f_out = jobs.f_out;
@@ -387,17 +409,48 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
-    const int n_etiles = pref[n_jobs];
     const int slabs_off = (int)hdr->slabs_off;
+    if (threadIdx.x == 0) {
+        // slab byte offsets (W1 slabs first, then every weight tile) and MMA cost prefix (cost ~ UMMA N + exposed A read)
+        uint32_t off = (uint32_t)slab_bytes(C::N1, C::STAGE_K, SPLIT) * (C::KP / C::STAGE_K);
+        cum[0] = 0;                                                         // (shared memory: a stack array would be cold DRAM round trips)
+        for (int t = 0; t < n_tiles; ++t) {
+            tile_off[t] = off;
+            off += (uint32_t)slab_bytes(tiles[t].n_cols, C::STAGE_K, SPLIT) * (C::KP / C::STAGE_K);
+            cum[t + 1] = cum[t] + tiles[t].n_cols + 86;
+        }
+        tile_off[n_tiles] = off;
+        const int total = pref[n_jobs], G = (int)gridDim.x;
+        const int R = total % G;
+        int k = 1;
+        if (R > 0) k = min(min(SPLIT_MAX, G / R), n_tiles);
+        work->n_full = k > 1 ? total - R : total;
+        work->k = k;
+        work->n_items = work->n_full + (k > 1 ? R * k : 0);
+        int t = 0;
+        for (int p = 0; p <= k; ++p) {
+            const int target = (int)((long long)cum[n_tiles] * p / k);
+            while (t < n_tiles && cum[t] < target) ++t;
+            work->split[p] = p == k ? n_tiles : t;
+        }
+        for (int p = 1; p < k; ++p)                                         // every part keeps at least one tile
+            work->split[p] = min(max(work->split[p], work->split[p - 1] + 1), n_tiles - (k - p));
+    }
+    __syncthreads();
+    const Work &wk = *work;
+    const int n_items = wk.n_items;
 
     if (warp == 4) {
         // =============================== TMA producer (warp-uniform, one elected lane issues) =====
         uint32_t stage = 0, phase = 0;
-        for (int g = blockIdx.x; g < n_etiles; g += gridDim.x) {
-            int job, et;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+            int g, t0, t1, job, et;
+            work_item(wk, w, n_tiles, g, t0, t1);
             locate(pref, n_jobs, g, job, et);
-            const uint8_t *src = jobs.job[job].image + slabs_off;
-            for (int t = -1; t < n_tiles; ++t) {
+            const uint8_t *base = jobs.job[job].image + slabs_off;
+            for (int tt = -1; tt < t1 - t0; ++tt) {
+                const int t = tt < 0 ? -1 : t0 + tt;
+                const uint8_t *src = t < 0 ? base : base + tile_off[t];
                 const int ncol = (t < 0) ? C::N1 : tiles[t].n_cols;
                 const uint32_t bytes = slab_bytes(ncol, C::STAGE_K, SPLIT);
 #pragma unroll 1
@@ -426,20 +479,24 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
         bool pre_a = false, pre_te = false, pre_full = false;   // waits of the upcoming tile / group already taken
         int it = 0;
         constexpr int NG = C::KP / C::STAGE_K;
-        for (int g = blockIdx.x; g < n_etiles; g += gridDim.x, ++it) {
+        int titer = 0;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+            int g, t0, t1;
+            work_item(wk, w, n_tiles, g, t0, t1);
+            const int nt = t1 - t0;
             const int ab = it % C::NBUF;
-            const bool more = g + (int)gridDim.x < n_etiles;
+            const bool more = w + (int)gridDim.x < n_items;
             const uint32_t a_hi_addr = smem_u32(a_base + (size_t)ab * C::A_BYTES * (SPLIT ? 2 : 1));
             // descriptor low words: A has LBO = 128 rows x 16 B between the two K chunks of one MMA
             const uint32_t a_hi_lo = ((a_hi_addr >> 4) & 0x3FFFu) | ((uint32_t)(TILE_M * 16 >> 4) << 16);
             const uint32_t a_lo_lo = (((a_hi_addr + C::A_BYTES) >> 4) & 0x3FFFu) | ((uint32_t)(TILE_M * 16 >> 4) << 16);
-            for (int t = -1; t < n_tiles; ++t) {
+            for (int tt = -1; tt < nt; ++tt, ++titer) {
+                const int t = tt < 0 ? -1 : t0 + tt;                     // weight tile (-1: GEMM1)
                 const uint32_t ncol = (t < 0) ? (uint32_t)C::N1 : (uint32_t)tiles[t].n_cols;
-                const uint32_t buf = (uint32_t)(t + 1) & 1u;
-                const int titer = it * (n_tiles + 1) + t + 1;
+                const uint32_t buf = (uint32_t)(tt + 1) & 1u;
                 trace_ev(jobs.trace, 0, titer, 0);
                 if (t < 0 && !pre_a) mbar_wait(&a_ready[ab], (uint32_t)(it / C::NBUF) & 1u);
-                if (t == 0) { mbar_wait(h_ready, hr_phase); hr_phase ^= 1; }
+                if (tt == 0) { mbar_wait(h_ready, hr_phase); hr_phase ^= 1; }
                 if (!pre_te) {
                     mbar_wait(&tmem_empty[buf], ((te_phase >> buf) & 1u) ^ 1u);
                     te_phase ^= 1u << buf;
@@ -455,10 +512,10 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                 const bool ts = C::TS && t >= 0;                        // GEMM2 reads the hidden activations from TMEM
                 // what may be taken early for the tile after this one (never anything that needs THIS tile's MMAs to
                 // complete: tile 0's h_ready; the accumulator this tile writes; in SS mode the A buffer)
-                const bool wrap = t + 1 == n_tiles;
-                const bool nx_any = t != -1 && (!wrap || more);
+                const bool wrap = tt + 1 == nt;
+                const bool nx_any = tt != -1 && (!wrap || more);
                 const bool nx_a = nx_any && wrap && (C::TS || C::NBUF == 2);
-                const uint32_t nbuf = wrap ? 0u : (uint32_t)(t + 2) & 1u;
+                const uint32_t nbuf = wrap ? 0u : (uint32_t)(tt + 2) & 1u;
                 const bool nx_te = nx_any && nbuf != buf;
                 const uint32_t nte_par = ((te_phase >> nbuf) & 1u) ^ 1u;
                 const uint32_t na_par = (uint32_t)((it + 1) / C::NBUF) & 1u;
@@ -495,7 +552,7 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                         if (ks == NG - 1) {
                             umma_commit(&tmem_full[buf]);
                             // the smem A buffer is free once its last reader has run: GEMM1 (TS) / the last GEMM2 tile (SS)
-                            if (C::TS ? t < 0 : t == n_tiles - 1) umma_commit(&a_free[ab]);
+                            if (C::TS ? tt < 0 : tt == nt - 1) umma_commit(&a_free[ab]);
                         }
                     }
                     __syncwarp();
@@ -522,8 +579,9 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
         // core-matrix order while the tensor cores still work on the previous tile.
         const int gt = threadIdx.x - 6 * 32;
         int it = 0;
-        for (int g = blockIdx.x; g < n_etiles; g += gridDim.x, ++it) {
-            int job, et;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+            int g, t0, t1, job, et;
+            work_item(wk, w, n_tiles, g, t0, t1);
             locate(pref, n_jobs, g, job, et);
             const ddp_tpconv_edges_t &ed = jobs.job[job].ed;
             const int n_edges = min(*ed.n_edges_dev, ed.edge_cap);
@@ -597,8 +655,11 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
         uint32_t tf_phase = 0;                           // bit b: parity to wait on tmem_full[b]
         const uint32_t a_row_off = (uint32_t)((r >> 3) * 128 + (r & 7) * 16);
         int it = 0;
-        for (int g = blockIdx.x; g < n_etiles; g += gridDim.x, ++it) {
-            int job, et;
+        int titer = 0;
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+            int g, t0, t1, job, et;
+            work_item(wk, w, n_tiles, g, t0, t1);
+            const int nt = t1 - t0;
             locate(pref, n_jobs, g, job, et);
             const ddp_tpconv_edges_t &ed = jobs.job[job].ed;
             float *__restrict__ sum = jobs.job[job].sum;
@@ -619,7 +680,7 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
             }
             // node features of weight tile 0 (registers; every tile prefetches the next one's)
             float xn[C::XN];
-            uint4 tdw = *reinterpret_cast<const uint4 *>(&tiles[0]);
+            uint4 tdw = *reinterpret_cast<const uint4 *>(&tiles[t0]);
             {
                 const int kind = (int)((tdw.x >> 16) & 0xffu), n_rows = (int)(tdw.x >> 24);
                 x_prefetch<C::XN>(xg + (tdw.z & 0xffffu), n_rows * ((kind == 0 || kind == 2) ? 1 : 3), xn);
@@ -628,11 +689,11 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
             // ---- GEMM1 result -> ReLU -> hidden activations become the A operand of GEMM2 ----
             // TS: packed bf16 pairs into tensor memory (column c of the lane = k 2c, 2c + 1); SS (split mode): hi / lo
             // images back into the shared-memory A buffer in core-matrix order.
-            if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1), 0);
+            if (r == 0) trace_ev(jobs.trace, 1, titer, 0);
             mbar_wait(&tmem_full[0], tf_phase & 1u);
             tf_phase ^= 1u;
             tc_fence_after();
-            if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1), 1);
+            if (r == 0) trace_ev(jobs.trace, 1, titer, 1);
             {
                 uint32_t w[2][16];
                 tmem_ld16_async(tmem_base + lane_base, w[0]);
@@ -674,7 +735,8 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
             if (!C::TS) fence_proxy_async();
             mbar_arrive(h_ready);
             mbar_arrive(&tmem_empty[0]);
-            if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1), 2);
+            if (r == 0) trace_ev(jobs.trace, 1, titer, 2);
+            ++titer;
 
             // ---- weight tiles: TMEM accumulator x tensor-product basis -> per-edge output registers ----
             // Every tile has one basis kind; its node features arrive in registers (prefetched during the previous
@@ -682,10 +744,13 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
             // Scalar tiles: ROWS_S rows in one pass; vector tiles: up to 2 NV rows in two passes of NV rows.
             float acc[NS];
 #pragma unroll 1
-            for (int t = 0; t < n_tiles; ++t) {
+            for (int tt = 0; tt < nt; ++tt, ++titer) {
+                const int t = t0 + tt;
                 const int kind = (int)((tdw.x >> 16) & 0xffu), n_rows = (int)(tdw.x >> 24);
-                const int out_off = (int)(tdw.y & 0xffffu), flags = (int)((tdw.y >> 16) & 0xffu);
-                const uint32_t buf = (uint32_t)(t + 1) & 1u;
+                const int out_off = (int)(tdw.y & 0xffffu);
+                // a split item starts / ends inside a block: its partial sums are zeroed / flushed at the item bounds
+                const int flags = (int)((tdw.y >> 16) & 0xffu) | (tt == 0 ? 1 : 0) | (tt == nt - 1 ? 4 : 0);
+                const uint32_t buf = (uint32_t)(tt + 1) & 1u;
                 const uint32_t taddr = tmem_base + lane_base + buf * (uint32_t)C::ACC_STRIDE;
                 if (flags & 1) {
 #pragma unroll
@@ -702,16 +767,16 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                         for (int rr = 0; rr < C::ROWS_S; ++rr)
                             b[rr] = rr < n_rows ? xn[3 * rr] * s1x + xn[3 * rr + 1] * s1y + xn[3 * rr + 2] * s1z : 0.f;
                     }
-                    if (t + 1 < n_tiles) {
+                    if (tt + 1 < nt) {
                         tdw = *reinterpret_cast<const uint4 *>(&tiles[t + 1]);
                         const int k2 = (int)((tdw.x >> 16) & 0xffu), nr2 = (int)(tdw.x >> 24);
                         x_prefetch<C::XN>(xg + (tdw.z & 0xffffu), nr2 * ((k2 == 0 || k2 == 2) ? 1 : 3), xn);
                     }
-                    if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1) + t + 1, 0);
+                    if (r == 0) trace_ev(jobs.trace, 1, titer, 0);
                     mbar_wait(&tmem_full[buf], (tf_phase >> buf) & 1u);
                     tf_phase ^= 1u << buf;
                     tc_fence_after();
-                    if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1) + t + 1, 1);
+                    if (r == 0) trace_ev(jobs.trace, 1, titer, 1);
                     tmem_ld16_async(taddr, w[0]);
                     constexpr int NCH = (C::NVAL_S + 15) / 16;
 #pragma unroll
@@ -726,9 +791,9 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                     }
                     tc_fence_before();
                     mbar_arrive(&tmem_empty[buf]);
-                    if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1) + t + 1, 2);
+                    if (r == 0) trace_ev(jobs.trace, 1, titer, 2);
                     if ((flags & 4) && valid) red_row<NS>(sum + (size_t)agg * f_out + out_off, acc);
-                    if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1) + t + 1, 3);
+                    if (r == 0) trace_ev(jobs.trace, 1, titer, 3);
                 } else {
                     // pass p covers basis rows [p NV, (p + 1) NV) = weight columns [p NV^2, (p + 1) NV^2)
                     float bx[NV], by[NV], bz[NV];
@@ -760,15 +825,15 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                         }
                         (void)stride;
                         if (pass == 0) {
-                            if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1) + t + 1, 0);
+                            if (r == 0) trace_ev(jobs.trace, 1, titer, 0);
                             mbar_wait(&tmem_full[buf], (tf_phase >> buf) & 1u);
                             tf_phase ^= 1u << buf;
                             tc_fence_after();
-                            if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1) + t + 1, 1);
+                            if (r == 0) trace_ev(jobs.trace, 1, titer, 1);
                         }
                         if (pass == 1 || n_rows <= NV) {
                             // the last basis rows are in registers: fetch the next tile's node features
-                            if (t + 1 < n_tiles) {
+                            if (tt + 1 < nt) {
                                 tdw = *reinterpret_cast<const uint4 *>(&tiles[t + 1]);
                                 const int k2 = (int)((tdw.x >> 16) & 0xffu), nr2 = (int)(tdw.x >> 24);
                                 x_prefetch<C::XN>(xg + (tdw.z & 0xffffu), nr2 * ((k2 == 0 || k2 == 2) ? 1 : 3), xn);
@@ -798,9 +863,9 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                     }
                     tc_fence_before();
                     mbar_arrive(&tmem_empty[buf]);
-                    if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1) + t + 1, 2);
+                    if (r == 0) trace_ev(jobs.trace, 1, titer, 2);
                     if ((flags & 4) && valid) red_row<3 * NV>(sum + (size_t)agg * f_out + out_off, acc);
-                    if (r == 0) trace_ev(jobs.trace, 1, it * (n_tiles + 1) + t + 1, 3);
+                    if (r == 0) trace_ev(jobs.trace, 1, titer, 3);
                 }
             }
         }
