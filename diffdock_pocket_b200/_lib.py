@@ -38,7 +38,7 @@ class TpConv(C.Structure):
 class TpEdges(C.Structure):
     _fields_ = [('emb', vp), ('p1', vp), ('i1', vp), ('ld1', i32), ('p2', vp), ('i2', vp), ('ld2', i32),
                 ('x', vp), ('gather', vp), ('ldx', i32), ('sh', vp), ('agg', vp), ('ew', vp),
-                ('n_edges_dev', vp), ('edge_cap', i32)]
+                ('n_edges_dev', vp), ('edge_cap', i32), ('out_scale', vp), ('agg_deg', vp)]
 
 
 class Update(C.Structure):

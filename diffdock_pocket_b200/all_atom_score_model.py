@@ -362,7 +362,10 @@ class TensorProductScoreModel(nn.Module):
             es[nm].deg[r] = pl.deg_arena[o:o + n]
             o += n
         # scatter-sum arena: three updates per node type
-        pl.sum_arena = torch.zeros(3 * (pl.NL + pl.NA + pl.NR) * F + 64, **f32)
+        pl.sum_arena = torch.zeros((pl.NL + pl.NA + pl.NR) * F + 64, **f32)
+        pl.sum_used = [min(pl.sum_arena.numel(), (pl.NL + pl.NA + pl.NR) * d + 16) for d in [tpmod.irreps_dim(tpmod.parse_irreps(q)) for q in self.irrep_seq]]
+        pl.ones_F = torch.ones(F, **f32)
+        pl.one_i32 = torch.ones(1, **i32)
         pl.sig = torch.zeros(B, self.sigma_embed_dim, **f32)
         pl.U = torch.zeros(len(P['proj_names']), B, ns, **f32)
         # ---- per-forward host scalars -> one pinned staging buffer ------------------------------
@@ -459,19 +462,20 @@ class TensorProductScoreModel(nn.Module):
 
     # ------------------------------------------------------------------------------------------ forward
     @staticmethod
-    def _edges_desc(es, flip, x, p1, i1_row, p2, i2_row):
-        """ddp_tpconv_edges_t of one conv: agg / gather rows follow ``flip`` (torch.flip of edge_index)."""
+    def _edges_desc(es, flip, x, p1, i1_row, p2, i2_row, out_scale=None, agg_deg=None):
+        """ddp_tpconv_edges_t of one conv: agg / gather rows follow ``flip`` (torch.flip of edge_index).  With
+        ``out_scale`` / ``agg_deg`` the conv accumulates mean- and BatchNorm-scaled contributions."""
         agg_r, gat_r = (1, 0) if flip else (0, 1)
         return _lib.TpEdges(emb=ptr(es.emb), p1=ptr(p1) if p1 is not None else None,
                             i1=es.row(i1_row) if p1 is not None else None, ld1=p1.shape[1] if p1 is not None else 0,
                             p2=ptr(p2) if p2 is not None else None, i2=es.row(i2_row) if p2 is not None else None,
                             ld2=p2.shape[1] if p2 is not None else 0, x=ptr(x), gather=es.row(gat_r), ldx=x.shape[1],
                             sh=ptr(es.sh_conv if hasattr(es, 'sh_conv') else es.sh), agg=es.row(agg_r), ew=None,
-                            n_edges_dev=ptr(es.n_dev), edge_cap=es.cap)
+                            n_edges_dev=ptr(es.n_dev), edge_cap=es.cap, out_scale=ptr(out_scale), agg_deg=ptr(agg_deg))
 
     def _conv_group(self, L, st, items):
         """Fused tensor-product convolutions that share irreps (the convs of one interaction layer, or a single
-        head conv).  items: (layer, packed, edge set, flip, x, p1, i1_row, p2, i2_row, sum_buf).  On the tensor-core
+        head conv).  items: (layer, packed, edge set, flip, x, p1, i1_row, p2, i2_row, sum_buf[, out_scale, agg_deg]).  On the tensor-core
         path they run as ONE persistent kernel over the union of their edge tiles (ddp_tpconv_umma_group)."""
         if len(items) > 1 and not getattr(self, 'group_convs', True):      # one launch per conv (per-conv timing)
             for it in items:
@@ -482,7 +486,7 @@ class TensorProductScoreModel(nn.Module):
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
         tc = self.conv_mode != 'fp32' and all(it[1].spec.tc_eligible and it[5] is not None and it[7] is not None for it in items)
-        eds = [self._edges_desc(*it[2:9]) for it in items]
+        eds = [self._edges_desc(*it[2:9], *it[10:12]) for it in items]
         if tc:
             mode = 0 if self.conv_mode == 'bf16' else 1
             n = len(items)
@@ -564,7 +568,7 @@ class TensorProductScoreModel(nn.Module):
             last = l == self.num_conv_layers - 1
             f_old, f_new = seq_dims[min(l, 3)], seq_dims[min(l + 1, 3)]
             Cv, Pk = self.conv_layers, P['convs']
-            pl.sum_arena.zero_()
+            pl.sum_arena[:pl.sum_used[min(l + 1, 3)]].zero_()
             o = 0
 
             def take(n):
@@ -572,38 +576,45 @@ class TensorProductScoreModel(nn.Module):
                 v = pl.sum_arena[o:o + n * f_new].view(n, f_new)
                 o += (n * f_new + 3) // 4 * 4                                # keep every slice 16-byte aligned
                 return v
-            s_ll, s_lr, s_la = take(pl.NL), take(pl.NL), take(pl.NL)
-            grp = [(Cv[9 * l], Pk[9 * l], es['ll'], False, xl, xl, 0, xl, 1, s_ll),
-                   (Cv[9 * l + 1], Pk[9 * l + 1], es['lr'], False, xr, xl, 0, xr, 1, s_lr),
-                   (Cv[9 * l + 2], Pk[9 * l + 2], es['la'], False, xa, xl, 0, xa, 1, s_la)]
+
+            # One accumulation buffer per node type: every conv adds out * bn_scale / in-degree (its scatter-mean and
+            # BatchNorm scale, all_atom_score_model.py:315-324 + score_model.py:117,123) straight into it.
+            def job(ci, nm, flip, x, p1, i1, p2, i2, buf):
+                agg_r = 1 if flip else 0
+                sc = Pk[ci].bn_scale if Pk[ci].bn_scale is not None else pl.ones_F
+                return (Cv[ci], Pk[ci], es[nm], flip, x, p1, i1, p2, i2, buf, sc, es[nm].deg[agg_r])
+            s_l = take(pl.NL)
+            grp = [job(9 * l, 'll', False, xl, xl, 0, xl, 1, s_l), job(9 * l + 1, 'lr', False, xr, xl, 0, xr, 1, s_l),
+                   job(9 * l + 2, 'la', False, xa, xl, 0, xa, 1, s_l)]
             do_atom = self.flexible_sidechains or not last
             if do_atom:
-                s_aa, s_al, s_ar = take(pl.NA), take(pl.NA), take(pl.NA)
-                grp += [(Cv[9 * l + 3], Pk[9 * l + 3], es['aa'], False, xa, xa, 0, xa, 1, s_aa),
-                        (Cv[9 * l + 4], Pk[9 * l + 4], es['la'], True, xl, xa, 1, xl, 0, s_al),
-                        (Cv[9 * l + 5], Pk[9 * l + 5], es['ar'], False, xr, xa, 0, xr, 1, s_ar)]
+                s_a = take(pl.NA)
+                grp += [job(9 * l + 3, 'aa', False, xa, xa, 0, xa, 1, s_a), job(9 * l + 4, 'la', True, xl, xa, 1, xl, 0, s_a),
+                        job(9 * l + 5, 'ar', False, xr, xa, 0, xr, 1, s_a)]
                 if not last:
-                    s_rr, s_rl, s_ra = take(pl.NR), take(pl.NR), take(pl.NR)
-                    grp += [(Cv[9 * l + 6], Pk[9 * l + 6], es['rr'], False, xr, xr, 0, xr, 1, s_rr),
-                            (Cv[9 * l + 7], Pk[9 * l + 7], es['lr'], True, xl, xr, 1, xl, 0, s_rl),
-                            (Cv[9 * l + 8], Pk[9 * l + 8], es['ar'], True, xa, xr, 1, xa, 0, s_ra)]
+                    s_r = take(pl.NR)
+                    grp += [job(9 * l + 6, 'rr', False, xr, xr, 0, xr, 1, s_r), job(9 * l + 7, 'lr', True, xl, xr, 1, xl, 0, s_r),
+                            job(9 * l + 8, 'ar', True, xa, xr, 1, xa, 0, s_r)]
             # largest edge sets first: the round-robin tile walk then ends on the small ones
             grp.sort(key=lambda it: -it[2].cap)
             self._conv_group(L, st, grp)
 
-            def update(key, x_old, n, items):
-                ups = (_lib.Update * len(items))(*[
-                    _lib.Update(sum=ptr(s), deg=ptr(es[nm].deg[r]), scale=ptr(Pk[ci].bn_scale), shift=ptr(Pk[ci].bn_shift),
-                                n_edges_dev=ptr(es[nm].n_dev)) for (s, nm, r, ci) in items])
+            def update(key, x_old, n, buf, items):
+                # the buffer is already normalised (deg = NULL); every live conv still contributes its BatchNorm shift
+                # (empty edge sets: `return 0`, score_model.py:109-111); the buffer itself is always read
+                ups = (_lib.Update * (len(items) + 1))(
+                    _lib.Update(sum=ptr(buf), deg=None, scale=None, shift=None, n_edges_dev=ptr(pl.one_i32)),
+                    *[_lib.Update(sum=None, deg=None, scale=None, shift=ptr(Pk[ci].bn_shift), n_edges_dev=ptr(es[nm].n_dev))
+                      for (nm, ci) in items])
                 x_new = pl.x[key][1 - cur[key]]
-                chk(L.ddp_node_update(ptr(x_old), f_old, F, ups, len(items), n, f_new, ptr(x_new), F, st), 'ddp_node_update')
+                chk(L.ddp_node_update(ptr(x_old), f_old, F, ups, len(items) + 1, n, f_new, ptr(x_new), F, st), 'ddp_node_update')
                 cur[key] = 1 - cur[key]
                 return x_new
-            xl_new = update('l', xl, pl.NL, [(s_ll, 'll', 0, 9 * l), (s_la, 'la', 0, 9 * l + 2), (s_lr, 'lr', 0, 9 * l + 1)])
+            xl_new = update('l', xl, pl.NL, s_l, [('ll', 9 * l), ('la', 9 * l + 2), ('lr', 9 * l + 1)])
             if do_atom:
-                xa_new = update('a', xa, pl.NA, [(s_aa, 'aa', 0, 9 * l + 3), (s_al, 'la', 1, 9 * l + 4), (s_ar, 'ar', 0, 9 * l + 5)])
+                xa_new = update('a', xa, pl.NA, s_a, [('aa', 9 * l + 3), ('la', 9 * l + 4), ('ar', 9 * l + 5)])
                 if not last:
-                    xr = update('r', xr, pl.NR, [(s_rr, 'rr', 0, 9 * l + 6), (s_ra, 'ar', 1, 9 * l + 8), (s_rl, 'lr', 1, 9 * l + 7)])
+                    xr = update('r', xr, pl.NR, s_r, [('rr', 9 * l + 6), ('ar', 9 * l + 8), ('lr', 9 * l + 7)])
                 xa = xa_new
             xl = xl_new
             if return_layers:

@@ -159,67 +159,36 @@ edge_embed_kernel(const float *__restrict__ pos_a, const float *__restrict__ pos
 constexpr int kMaxUpdates = 4;
 struct UpdatePack { ddp_update_t u[kMaxUpdates]; int n; };
 
-// One warp per node row: the per-node counts are read once, channels are covered by the lanes (coalesced rows).
-// VEC: rows are read as float2 with every load of the row issued before the first use (f_new, ld even; <= 64 * ITERS).
-template <int ITERS>
-__global__ void node_update_vec_kernel(const float *__restrict__ old_x, int f_old, int ld_old, UpdatePack up, int n,
-                                       int f_new, float *__restrict__ new_x, int ld_new) {
-    const int lane = threadIdx.x & 31;
-    const int warps = (gridDim.x * blockDim.x) >> 5;
-    bool live[kMaxUpdates];
-#pragma unroll
-    for (int k = 0; k < kMaxUpdates; ++k) live[k] = k < up.n && *up.u[k].n_edges_dev > 0;
-    // per-channel BatchNorm scale / shift of this lane's channels: loaded once, reused for every node of the warp
-    float2 sc[kMaxUpdates][ITERS], sf[kMaxUpdates][ITERS];
-#pragma unroll
-    for (int k = 0; k < kMaxUpdates; ++k)
-#pragma unroll
-        for (int it = 0; it < ITERS; ++it) {
-            const int c = 2 * (lane + 32 * it);
-            sc[k][it] = make_float2(1.f, 1.f);
-            sf[k][it] = make_float2(0.f, 0.f);
-            if (live[k] && c < f_new) {
-                if (up.u[k].scale) sc[k][it] = make_float2(__ldg(up.u[k].scale + c), __ldg(up.u[k].scale + c + 1));
-                if (up.u[k].shift) sf[k][it] = make_float2(__ldg(up.u[k].shift + c), __ldg(up.u[k].shift + c + 1));
-            }
-        }
-    for (int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; node < n; node += warps) {
-        float cnt[kMaxUpdates];
+// Flat float2 form: one thread per channel pair, few registers, full occupancy (f_new, strides even, 8-byte aligned bases).
+__global__ void __launch_bounds__(256) node_update_vec_kernel(const float *__restrict__ old_x, int f_old, int ld_old, UpdatePack up,
+                                                              int n, int f_new, float *__restrict__ new_x, int ld_new) {
+    const int h = f_new >> 1;
+    const int total = n * h;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int node = idx / h, c = 2 * (idx - node * h);
+        float2 v = make_float2(0.f, 0.f);
+        if (old_x != nullptr && c < f_old) v = *reinterpret_cast<const float2 *>(old_x + (size_t)node * ld_old + c);
 #pragma unroll
         for (int k = 0; k < kMaxUpdates; ++k) {
-            cnt[k] = 1.f;
-            if (live[k]) {
-                const int dg = up.u[k].deg[node];
-                cnt[k] = (float)(dg < 1 ? 1 : dg);
-            }
-        }
-        float2 o[ITERS], sm[kMaxUpdates][ITERS];
-#pragma unroll
-        for (int it = 0; it < ITERS; ++it) {
-            const int c = 2 * (lane + 32 * it);
-            o[it] = make_float2(0.f, 0.f);
-            if (old_x != nullptr && c < f_old) o[it] = *reinterpret_cast<const float2 *>(old_x + (size_t)node * ld_old + c);
-#pragma unroll
-            for (int k = 0; k < kMaxUpdates; ++k) {
-                sm[k][it] = make_float2(0.f, 0.f);
-                if (live[k] && c < f_new) sm[k][it] = *reinterpret_cast<const float2 *>(up.u[k].sum + (size_t)node * f_new + c);
-            }
-        }
-#pragma unroll
-        for (int it = 0; it < ITERS; ++it) {
-            const int c = 2 * (lane + 32 * it);
-            if (c < f_new) {
-                float vx = o[it].x, vy = o[it].y;
-#pragma unroll
-                for (int k = 0; k < kMaxUpdates; ++k) {
-                    if (live[k]) {
-                        vx += fmaf(__fdiv_rn(sm[k][it].x, cnt[k]), sc[k][it].x, sf[k][it].x);
-                        vy += fmaf(__fdiv_rn(sm[k][it].y, cnt[k]), sc[k][it].y, sf[k][it].y);
+            if (k < up.n && __ldg(up.u[k].n_edges_dev) > 0) {
+                float2 m = make_float2(0.f, 0.f);
+                if (up.u[k].sum != nullptr) {
+                    m = *reinterpret_cast<const float2 *>(up.u[k].sum + (size_t)node * f_new + c);
+                    if (up.u[k].deg != nullptr) {
+                        const int dg = __ldg(up.u[k].deg + node);
+                        const float cnt = (float)(dg < 1 ? 1 : dg);
+                        m.x = __fdiv_rn(m.x, cnt);
+                        m.y = __fdiv_rn(m.y, cnt);
                     }
                 }
-                *reinterpret_cast<float2 *>(new_x + (size_t)node * ld_new + c) = make_float2(vx, vy);
+                float2 sc = make_float2(1.f, 1.f), sf = make_float2(0.f, 0.f);
+                if (up.u[k].scale != nullptr && up.u[k].deg != nullptr) sc = __ldg(reinterpret_cast<const float2 *>(up.u[k].scale + c));
+                if (up.u[k].shift != nullptr) sf = __ldg(reinterpret_cast<const float2 *>(up.u[k].shift + c));
+                v.x += fmaf(m.x, sc.x, sf.x);
+                v.y += fmaf(m.y, sc.y, sf.y);
             }
         }
+        *reinterpret_cast<float2 *>(new_x + (size_t)node * ld_new + c) = v;
     }
 }
 
@@ -235,7 +204,7 @@ __global__ void node_update_kernel(const float *__restrict__ old_x, int f_old, i
 #pragma unroll
         for (int k = 0; k < kMaxUpdates; ++k) {
             cnt[k] = 1.f;
-            if (live[k]) {
+            if (live[k] && up.u[k].deg != nullptr) {
                 const int dg = up.u[k].deg[node];
                 cnt[k] = (float)(dg < 1 ? 1 : dg);
             }
@@ -245,8 +214,8 @@ __global__ void node_update_kernel(const float *__restrict__ old_x, int f_old, i
 #pragma unroll
             for (int k = 0; k < kMaxUpdates; ++k) {
                 if (live[k]) {
-                    const float m = __fdiv_rn(up.u[k].sum[(size_t)node * f_new + c], cnt[k]);
-                    const float sc = up.u[k].scale ? __ldg(up.u[k].scale + c) : 1.f;
+                    const float m = up.u[k].sum ? __fdiv_rn(up.u[k].sum[(size_t)node * f_new + c], cnt[k]) : 0.f;
+                    const float sc = (up.u[k].scale && up.u[k].deg) ? __ldg(up.u[k].scale + c) : 1.f;
                     const float sf = up.u[k].shift ? __ldg(up.u[k].shift + c) : 0.f;
                     v += fmaf(m, sc, sf);
                 }
@@ -480,14 +449,13 @@ extern "C" int ddp_node_update(const float *old_x, int32_t f_old, int32_t ld_old
     bool vec = (f_new % 2 == 0) && (f_old % 2 == 0) && (ld_new % 2 == 0) && (ld_old % 2 == 0) && f_new <= 192 &&
                (reinterpret_cast<uintptr_t>(new_x) % 8 == 0) && (reinterpret_cast<uintptr_t>(old_x) % 8 == 0);
     for (int i = 0; i < n_updates; ++i) vec = vec && (reinterpret_cast<uintptr_t>(updates[i].sum) % 8 == 0);
-    int grid = grid_for((size_t)n * 32, 256);
-    if (vec && grid > 6 * ddp_num_sms()) grid = 6 * ddp_num_sms();      // several nodes per warp: scale / shift stay in registers
-    if (vec && f_new <= 128)
-        node_update_vec_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(old_x, f_old, ld_old, up, n, f_new, new_x, ld_new);
-    else if (vec)
-        node_update_vec_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>(old_x, f_old, ld_old, up, n, f_new, new_x, ld_new);
+    for (int i = 0; i < n_updates; ++i)
+        vec = vec && (reinterpret_cast<uintptr_t>(updates[i].scale) % 8 == 0) && (reinterpret_cast<uintptr_t>(updates[i].shift) % 8 == 0);
+    if (vec)
+        node_update_vec_kernel<<<(int)(((size_t)n * (f_new / 2) + 255) / 256), 256, 0, (cudaStream_t)stream>>>(old_x, f_old, ld_old, up, n,
+                                                                                                      f_new, new_x, ld_new);
     else
-        node_update_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(old_x, f_old, ld_old, up, n, f_new, new_x, ld_new);
+        node_update_kernel<<<grid_for((size_t)n * 32, 256), 256, 0, (cudaStream_t)stream>>>(old_x, f_old, ld_old, up, n, f_new, new_x, ld_new);
     DDP_LAUNCH_CHECK();
     return 0;
 }

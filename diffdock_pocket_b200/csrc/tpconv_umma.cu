@@ -671,9 +671,11 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
             uint8_t *a_lo = a_hi + C::A_BYTES;
             int agg = 0;
             float s0 = 0.f, s1x = 0.f, s1y = 0.f, s1z = 0.f;
+            float inv_deg = 1.f;                         // pre-normalised accumulation: 1 / max(in-degree of agg, 1)
             const float *xg = ed.x;                      // invalid rows read node 0 and are never written back
             if (valid) {
                 agg = __ldg(ed.agg + e);
+                if (ed.agg_deg != nullptr) inv_deg = __frcp_rn((float)max(__ldg(ed.agg_deg + agg), 1));
                 const float4 sh4 = __ldg(reinterpret_cast<const float4 *>(ed.sh + (size_t)e * 4));
                 s0 = sh4.x; s1x = sh4.y; s1y = sh4.z; s1z = sh4.w;
                 xg = ed.x + (size_t)__ldg(ed.gather + e) * ed.ldx;
@@ -792,7 +794,13 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                     tc_fence_before();
                     mbar_arrive(&tmem_empty[buf]);
                     if (r == 0) trace_ev(jobs.trace, 1, titer, 2);
-                    if ((flags & 4) && valid) red_row<NS>(sum + (size_t)agg * f_out + out_off, acc);
+                    if ((flags & 4) && valid) {
+                        if (ed.out_scale != nullptr) {
+#pragma unroll
+                            for (int o = 0; o < NS; ++o) acc[o] *= __ldg(ed.out_scale + out_off + o) * inv_deg;
+                        }
+                        red_row<NS>(sum + (size_t)agg * f_out + out_off, acc);
+                    }
                     if (r == 0) trace_ev(jobs.trace, 1, titer, 3);
                 } else {
                     // pass p covers basis rows [p NV, (p + 1) NV) = weight columns [p NV^2, (p + 1) NV^2)
@@ -864,7 +872,13 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                     tc_fence_before();
                     mbar_arrive(&tmem_empty[buf]);
                     if (r == 0) trace_ev(jobs.trace, 1, titer, 2);
-                    if ((flags & 4) && valid) red_row<3 * NV>(sum + (size_t)agg * f_out + out_off, acc);
+                    if ((flags & 4) && valid) {
+                        if (ed.out_scale != nullptr) {
+#pragma unroll
+                            for (int o = 0; o < 3 * NV; ++o) acc[o] *= __ldg(ed.out_scale + out_off + o) * inv_deg;
+                        }
+                        red_row<3 * NV>(sum + (size_t)agg * f_out + out_off, acc);
+                    }
                     if (r == 0) trace_ev(jobs.trace, 1, titer, 3);
                 }
             }

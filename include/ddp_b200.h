@@ -156,6 +156,11 @@ typedef struct {
     const int32_t *agg;           /* edge_index[0] */
     const float *ew;              /* optional per-edge weight (smooth_edges) */
     const int32_t *n_edges_dev; int32_t edge_cap;
+    /* optional pre-normalised accumulation: sum[agg][c] += out[c] * out_scale[c] / max(agg_deg[agg], 1), i.e. the
+     * scatter-MEAN and the BatchNorm scale of this conv applied on the fly, so that several convs of a layer can
+     * accumulate into ONE buffer (ddp_node_update then adds only their shifts).  Both NULL: plain sums. */
+    const float *out_scale;       /* [f_out] */
+    const int32_t *agg_deg;       /* [n_out] in-degree of the aggregation nodes for this edge set */
 } ddp_tpconv_edges_t;
 
 /* fp32 CUDA-core path: exact-arithmetic mode and fallback for irreps the tensor-core kernel does not
@@ -191,7 +196,8 @@ int ddp_tpconv_umma_set_trace(void *trace_dev);
 /* node update (all_atom_score_model.py:315-324 + scatter-mean + e3nn BatchNorm eval, score_model.py:117,123):
  *   new[n][c] = (c < f_old ? old[n][c] : 0) + sum_u live_u * (sum_u[n][c] / max(deg_u[n],1) * scale_u[c] + shift_u[c])
  * live_u = (*n_edges_u > 0) reproduces `return 0` for an empty edge set (score_model.py:109-111).
- * old may be NULL (heads). */
+ * old may be NULL (heads).  deg == NULL: sum is already normalised (see ddp_tpconv_edges_t.out_scale / agg_deg; scale
+ * is then ignored); sum == NULL: the update contributes only its shift. */
 typedef struct {
     const float *sum; const int32_t *deg; const float *scale; const float *shift; const int32_t *n_edges_dev;
 } ddp_update_t;
