@@ -45,6 +45,15 @@ class Update(C.Structure):
     _fields_ = [('sum', vp), ('deg', vp), ('scale', vp), ('shift', vp), ('n_edges_dev', vp)]
 
 
+class NodeUpdateJob(C.Structure):
+    _fields_ = [('old_x', vp), ('f_old', i32), ('ld_old', i32), ('updates', Update * 4), ('n_updates', i32), ('n', i32),
+                ('f_new', i32), ('new_x', vp), ('ld_new', i32)]
+
+
+class DegreeJob(C.Structure):
+    _fields_ = [('idx', vp), ('n_edges_dev', vp), ('edge_cap', i32), ('start', i32), ('deg', vp)]
+
+
 class MlpLayer(C.Structure):
     _fields_ = [('wt', vp), ('b', vp), ('n_in', i32), ('n_out', i32), ('act', i32)]
 
@@ -78,6 +87,8 @@ _SIGS = {
     'ddp_tpconv_umma_group': (i32, [vp, vp, i32, vp, vp, i32, vp]),
     'ddp_tpconv_umma_set_trace': (i32, [vp]),
     'ddp_node_update': (i32, [vp, i32, i32, C.POINTER(Update), i32, i32, i32, vp, i32, vp]),
+    'ddp_node_update_multi': (i32, [C.POINTER(NodeUpdateJob), i32, vp]),
+    'ddp_degree_multi': (i32, [C.POINTER(DegreeJob), i32, vp]),
     'ddp_segment_mean': (i32, [vp, vp, vp, i32, i32, i32, vp, i32, vp]),
     'ddp_bond_geometry': (i32, [vp, vp, i32, vp, i32, i32, vp, vp, vp, vp]),
     'ddp_tor_edge_sh': (i32, [vp, i32, vp, vp, vp, vp, i32, vp, vp]),

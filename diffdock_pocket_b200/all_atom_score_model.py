@@ -361,6 +361,20 @@ class TensorProductScoreModel(nn.Module):
         for (nm, r), n in sides.items():
             es[nm].deg[r] = pl.deg_arena[o:o + n]
             o += n
+        # static part of the degrees (receptor-receptor, atom-receptor, ligand bond edges): counted once per complex
+        pl.deg_base = torch.zeros_like(pl.deg_arena)
+        o = 0
+        for (nm, r), n in sides.items():
+            if nm in ('rr', 'ar'):
+                src = (rr if nm == 'rr' else ar)[r]
+                pl.deg_base[o:o + n] = torch.bincount(src.cpu(), minlength=n).to(**i32)
+            elif nm == 'll' and Eb > 0:
+                pl.deg_base[o:o + n] = torch.bincount(bond_ei[r].cpu(), minlength=n).to(**i32)
+            o += n
+        dyn = [(nm, r) for (nm, r) in sides if nm not in ('rr', 'ar')]
+        pl.deg_jobs = (_lib.DegreeJob * len(dyn))(*[
+            _lib.DegreeJob(idx=es[nm].row(r), n_edges_dev=ptr(es[nm].n_dev), edge_cap=es[nm].cap,
+                           start=Eb if nm == 'll' else 0, deg=ptr(es[nm].deg[r])) for (nm, r) in dyn])
         # scatter-sum arena: three updates per node type
         pl.sum_arena = torch.zeros((pl.NL + pl.NA + pl.NR) * F + 64, **f32)
         pl.sum_used = [min(pl.sum_arena.numel(), (pl.NL + pl.NA + pl.NR) * d + 16) for d in [tpmod.irreps_dim(tpmod.parse_irreps(q)) for q in self.irrep_seq]]
@@ -547,10 +561,8 @@ class TensorProductScoreModel(nn.Module):
         chk(L.ddp_radius(ptr(pl.atom_pos), ptr(pl.lig_pos), ptr(pl.atom_ptr), ptr(pl.lig_ptr), B, pl.NL, None,
                          float(self.lig_max_radius), 10000, 0, 0, ptr(e.slab), e.slab_w, ptr(e.counts), ptr(e.edge), e.cap,
                          ptr(e.n_dev), st), 'ddp_radius(la)')
-        pl.deg_arena.zero_()
-        for nm in ('ll', 'lr', 'la', 'aa', 'ar', 'rr'):
-            for r, d in es[nm].deg.items():
-                chk(L.ddp_degree(es[nm].row(r), ptr(es[nm].n_dev), es[nm].cap, ptr(d), st), 'ddp_degree')
+        pl.deg_arena.copy_(pl.deg_base)                               # static edge sets + ligand bond edges
+        chk(L.ddp_degree_multi(pl.deg_jobs, len(pl.deg_jobs), st), 'ddp_degree_multi')   # dynamic ones, one launch
         # ---- edge geometry + embeddings ------------------------------------------------------------
         em = P['em']
         geo = {'ll': (pl.lig_pos, pl.lig_pos, pl.lig_batch), 'rr': (pl.rec_pos, pl.rec_pos, pl.rec_batch),
@@ -602,20 +614,24 @@ class TensorProductScoreModel(nn.Module):
             def update(key, x_old, n, buf, items):
                 # the buffer is already normalised (deg = NULL); every live conv still contributes its BatchNorm shift
                 # (empty edge sets: `return 0`, score_model.py:109-111); the buffer itself is always read
-                ups = (_lib.Update * (len(items) + 1))(
-                    _lib.Update(sum=ptr(buf), deg=None, scale=None, shift=None, n_edges_dev=ptr(pl.one_i32)),
-                    *[_lib.Update(sum=None, deg=None, scale=None, shift=ptr(Pk[ci].bn_shift), n_edges_dev=ptr(es[nm].n_dev))
-                      for (nm, ci) in items])
                 x_new = pl.x[key][1 - cur[key]]
-                chk(L.ddp_node_update(ptr(x_old), f_old, F, ups, len(items) + 1, n, f_new, ptr(x_new), F, st), 'ddp_node_update')
                 cur[key] = 1 - cur[key]
-                return x_new
-            xl_new = update('l', xl, pl.NL, s_l, [('ll', 9 * l), ('la', 9 * l + 2), ('lr', 9 * l + 1)])
+                J = _lib.NodeUpdateJob(old_x=ptr(x_old), f_old=f_old, ld_old=F, n_updates=len(items) + 1, n=n, f_new=f_new,
+                                       new_x=ptr(x_new), ld_new=F)
+                J.updates[0] = _lib.Update(sum=ptr(buf), deg=None, scale=None, shift=None, n_edges_dev=ptr(pl.one_i32))
+                for k, (nm, ci) in enumerate(items):
+                    J.updates[k + 1] = _lib.Update(sum=None, deg=None, scale=None, shift=ptr(Pk[ci].bn_shift), n_edges_dev=ptr(es[nm].n_dev))
+                return x_new, J
+            xl_new, Jl = update('l', xl, pl.NL, s_l, [('ll', 9 * l), ('la', 9 * l + 2), ('lr', 9 * l + 1)])
+            node_jobs = [Jl]
             if do_atom:
-                xa_new = update('a', xa, pl.NA, s_a, [('aa', 9 * l + 3), ('la', 9 * l + 4), ('ar', 9 * l + 5)])
+                xa_new, Ja = update('a', xa, pl.NA, s_a, [('aa', 9 * l + 3), ('la', 9 * l + 4), ('ar', 9 * l + 5)])
+                node_jobs.append(Ja)
                 if not last:
-                    xr = update('r', xr, pl.NR, s_r, [('rr', 9 * l + 6), ('ar', 9 * l + 8), ('lr', 9 * l + 7)])
+                    xr, Jr = update('r', xr, pl.NR, s_r, [('rr', 9 * l + 6), ('ar', 9 * l + 8), ('lr', 9 * l + 7)])
+                    node_jobs.append(Jr)
                 xa = xa_new
+            chk(L.ddp_node_update_multi((_lib.NodeUpdateJob * len(node_jobs))(*node_jobs), len(node_jobs), st), 'ddp_node_update_multi')
             xl = xl_new
             if return_layers:
                 layers_out.append((xl[:, :f_new].clone(), xa[:, :f_new if do_atom else f_old].clone(), xr.clone()))

@@ -192,6 +192,42 @@ __global__ void __launch_bounds__(256) node_update_vec_kernel(const float *__res
     }
 }
 
+// Up to three node types (ligand / atom / receptor) of one interaction layer in one launch: blockIdx.y selects the job.
+constexpr int kMaxNodeJobs = 3;
+struct NodeJobs { ddp_node_update_job_t j[kMaxNodeJobs]; };
+__global__ void __launch_bounds__(256) node_update_multi_kernel(NodeJobs jobs) {
+    const ddp_node_update_job_t &J = jobs.j[blockIdx.y];
+    const int h = J.f_new >> 1;
+    const int total = J.n * h;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int node = idx / h, c = 2 * (idx - node * h);
+        float2 v = make_float2(0.f, 0.f);
+        if (J.old_x != nullptr && c < J.f_old) v = *reinterpret_cast<const float2 *>(J.old_x + (size_t)node * J.ld_old + c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k < J.n_updates && __ldg(J.updates[k].n_edges_dev) > 0) {
+                const ddp_update_t &u = J.updates[k];
+                float2 m = make_float2(0.f, 0.f);
+                if (u.sum != nullptr) {
+                    m = *reinterpret_cast<const float2 *>(u.sum + (size_t)node * J.f_new + c);
+                    if (u.deg != nullptr) {
+                        const int dg = __ldg(u.deg + node);
+                        const float cnt = (float)(dg < 1 ? 1 : dg);
+                        m.x = __fdiv_rn(m.x, cnt);
+                        m.y = __fdiv_rn(m.y, cnt);
+                    }
+                }
+                float2 sc = make_float2(1.f, 1.f), sf = make_float2(0.f, 0.f);
+                if (u.scale != nullptr && u.deg != nullptr) sc = __ldg(reinterpret_cast<const float2 *>(u.scale + c));
+                if (u.shift != nullptr) sf = __ldg(reinterpret_cast<const float2 *>(u.shift + c));
+                v.x += fmaf(m.x, sc.x, sf.x);
+                v.y += fmaf(m.y, sc.y, sf.y);
+            }
+        }
+        *reinterpret_cast<float2 *>(J.new_x + (size_t)node * J.ld_new + c) = v;
+    }
+}
+
 __global__ void node_update_kernel(const float *__restrict__ old_x, int f_old, int ld_old, UpdatePack up, int n,
                                    int f_new, float *__restrict__ new_x, int ld_new) {
     const int lane = threadIdx.x & 31;
@@ -456,6 +492,31 @@ extern "C" int ddp_node_update(const float *old_x, int32_t f_old, int32_t ld_old
                                                                                                       f_new, new_x, ld_new);
     else
         node_update_kernel<<<grid_for((size_t)n * 32, 256), 256, 0, (cudaStream_t)stream>>>(old_x, f_old, ld_old, up, n, f_new, new_x, ld_new);
+    DDP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ddp_node_update_multi(const ddp_node_update_job_t *jobs_host, int32_t n_jobs, void *stream) {
+    if (!jobs_host || n_jobs < 0 || n_jobs > kMaxNodeJobs) return DDP_E_ARG;
+    NodeJobs jobs;
+    size_t most = 0;
+    int m = 0;
+    for (int i = 0; i < n_jobs; ++i) {
+        const ddp_node_update_job_t &J = jobs_host[i];
+        if (J.n <= 0) continue;
+        if (!J.new_x || J.n_updates < 0 || J.n_updates > 4) return DDP_E_ARG;
+        bool ok = (J.f_new % 2 == 0) && (J.f_old % 2 == 0) && (J.ld_new % 2 == 0) && (J.ld_old % 2 == 0) &&
+                  (reinterpret_cast<uintptr_t>(J.new_x) % 8 == 0) && (reinterpret_cast<uintptr_t>(J.old_x) % 8 == 0);
+        for (int k = 0; k < J.n_updates; ++k)
+            ok = ok && J.updates[k].n_edges_dev && (reinterpret_cast<uintptr_t>(J.updates[k].sum) % 8 == 0) &&
+                 (reinterpret_cast<uintptr_t>(J.updates[k].scale) % 8 == 0) && (reinterpret_cast<uintptr_t>(J.updates[k].shift) % 8 == 0);
+        if (!ok) return DDP_E_UNSUPPORTED;
+        jobs.j[m++] = J;
+        const size_t tot = (size_t)J.n * (J.f_new / 2);
+        most = tot > most ? tot : most;
+    }
+    if (m == 0) return 0;
+    node_update_multi_kernel<<<dim3((unsigned)((most + 255) / 256), m), 256, 0, (cudaStream_t)stream>>>(jobs);
     DDP_LAUNCH_CHECK();
     return 0;
 }

@@ -233,6 +233,14 @@ __global__ void degree_kernel(const int32_t *__restrict__ idx, const int32_t *__
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) atomicAdd(&deg[idx[e]], 1);
 }
 
+constexpr int kMaxDegJobs = 12;
+struct DegPack { ddp_degree_job_t j[kMaxDegJobs]; };
+__global__ void degree_multi_kernel(DegPack p) {
+    const ddp_degree_job_t j = p.j[blockIdx.y];
+    const int n = min(*j.n_edges_dev, j.edge_cap);
+    for (int e = j.start + blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) atomicAdd(&j.deg[j.idx[e]], 1);
+}
+
 }  // namespace
 
 extern "C" int ddp_radius(const float *x, const float *y, const int32_t *ptr_x, const int32_t *ptr_y,
@@ -290,6 +298,24 @@ extern "C" int ddp_degree(const int32_t *idx, const int32_t *n_edges_dev, int32_
     int grid = (edge_cap + 255) / 256;
     if (grid > 4 * ddp_num_sms()) grid = 4 * ddp_num_sms();
     degree_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(idx, n_edges_dev, deg);
+    DDP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ddp_degree_multi(const ddp_degree_job_t *jobs_host, int32_t n_jobs, void *stream) {
+    if (!jobs_host || n_jobs < 0 || n_jobs > kMaxDegJobs) return DDP_E_ARG;
+    if (n_jobs == 0) return 0;
+    DegPack p;
+    int cap = 0;
+    for (int i = 0; i < n_jobs; ++i) {
+        if (!jobs_host[i].idx || !jobs_host[i].n_edges_dev || !jobs_host[i].deg || jobs_host[i].start < 0) return DDP_E_ARG;
+        p.j[i] = jobs_host[i];
+        cap = jobs_host[i].edge_cap > cap ? jobs_host[i].edge_cap : cap;
+    }
+    if (cap <= 0) return 0;
+    int gx = (cap + 255) / 256;
+    if (gx > 2 * ddp_num_sms()) gx = 2 * ddp_num_sms();
+    degree_multi_kernel<<<dim3(gx, n_jobs), 256, 0, (cudaStream_t)stream>>>(p);
     DDP_LAUNCH_CHECK();
     return 0;
 }

@@ -63,6 +63,11 @@ int ddp_knn_graph(const float *x, const int32_t *ptr, int32_t num_examples, int3
  * models/score_model.py:117): deg[idx[e]] += 1 for e < *n_edges_dev.  deg must be zeroed by the caller. */
 int ddp_degree(const int32_t *idx, const int32_t *n_edges_dev, int32_t edge_cap, int32_t *deg, void *stream);
 
+/* Several degree counts in one launch: deg[idx[e]] += 1 for start <= e < min(*n_edges_dev, edge_cap), per job
+ * (the dynamic edge sets of one forward; static ones are counted once per complex by the host). */
+typedef struct { const int32_t *idx; const int32_t *n_edges_dev; int32_t edge_cap; int32_t start; int32_t *deg; } ddp_degree_job_t;
+int ddp_degree_multi(const ddp_degree_job_t *jobs_host, int32_t n_jobs, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Edge geometry + edge embedding.  Replaces the per-edge-set blocks of build_*_conv_graph
  * (all_atom_score_model.py:476-481, 501-508, 527-534, 552-556, 566-570, 575-579, 594-598, 609-613):
@@ -203,6 +208,14 @@ typedef struct {
 } ddp_update_t;
 int ddp_node_update(const float *old_x, int32_t f_old, int32_t ld_old, const ddp_update_t *updates, int32_t n_updates,
                     int32_t n, int32_t f_new, float *new_x, int32_t ld_new, void *stream);
+/* The node updates of one interaction layer (ligand, atom, receptor) in one launch; widths / strides even and
+ * bases 8-byte aligned (the resident plan's buffers). */
+typedef struct {
+    const float *old_x; int32_t f_old, ld_old;
+    ddp_update_t updates[4]; int32_t n_updates;
+    int32_t n, f_new; float *new_x; int32_t ld_new;
+} ddp_node_update_job_t;
+int ddp_node_update_multi(const ddp_node_update_job_t *jobs_host, int32_t n_jobs, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Heads (all_atom_score_model.py:329-434). */
