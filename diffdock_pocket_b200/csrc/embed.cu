@@ -155,6 +155,100 @@ edge_embed_kernel(const float *__restrict__ pos_a, const float *__restrict__ pos
     }
 }
 
+// Folded form (mlp.w2 == NULL, ns % 4 == 0): 64 edges per block, 128 threads = 16 output quads x 8 edge octets; every
+// thread keeps a 4 x 8 register tile, so one weight float4 + two shared-memory float4 feed 32 FMAs.
+constexpr int kFE = 64;
+__global__ void __launch_bounds__(128)
+edge_embed_fold_kernel(const float *__restrict__ pos_a, const float *__restrict__ pos_b, const int32_t *__restrict__ edge,
+                       int cap, const int32_t *__restrict__ n_edges_dev, const int32_t *__restrict__ graph_of_a,
+                       const float *__restrict__ pre, int n_pre_rows, const float *__restrict__ u, ddp_edge_mlp_t p,
+                       float *__restrict__ sh_out, float *__restrict__ emb) {
+    __shared__ __align__(16) float s_in[(kMaxRbf + kMaxPre) * kFE];   // [k][edge]
+    __shared__ __align__(16) float s_w[(kMaxRbf + kMaxPre) * kMaxNs]; // [k][ns] first-layer weights (rbf rows, then pre rows)
+    __shared__ float s_d[kFE];
+    __shared__ int s_g[kFE];
+    const int n_edges = min(*n_edges_dev, cap);
+    const int e0 = blockIdx.x * kFE;
+    if (e0 >= n_edges) return;
+    const int tid = threadIdx.x;
+    // stage the weights once per block (coalesced; the K loop below then runs out of shared memory instead of paying an
+    // L2 round trip per unrolled group), overlapping the dependent edge -> position loads of the geometry phase
+    {
+        const int n4r = p.n_rbf * p.ns / 4, n4p = p.n_pre * p.ns / 4;
+        for (int i = tid; i < n4r; i += 128) reinterpret_cast<float4 *>(s_w)[i] = __ldg(reinterpret_cast<const float4 *>(p.w_rbf) + i);
+        for (int i = tid; i < n4p; i += 128) reinterpret_cast<float4 *>(s_w)[n4r + i] = __ldg(reinterpret_cast<const float4 *>(p.w_pre) + i);
+    }
+    if (tid < kFE) {
+        const int e = e0 + tid;
+        float d = 0.f;
+        int g = 0;
+        if (e < n_edges) {
+            const int a = edge[e], b = edge[cap + e];
+            const float vx = pos_b[3 * b] - pos_a[3 * a], vy = pos_b[3 * b + 1] - pos_a[3 * a + 1],
+                        vz = pos_b[3 * b + 2] - pos_a[3 * a + 2];
+            d = sqrtf(vx * vx + vy * vy + vz * vz);
+            const float inv = 1.f / fmaxf(d, 1e-12f);
+            const float x = vx * inv, y = vy * inv, z = vz * inv;
+            const float s3 = 1.7320508075688772f;
+            float *so = sh_out + (size_t)e * p.sh_dim;
+            so[0] = 1.f; so[1] = s3 * x; so[2] = s3 * y; so[3] = s3 * z;
+            if (p.sh_dim == 9) {
+                const float s5 = 2.23606797749979f;
+                so[4] = s5 * s3 * x * z;
+                so[5] = s5 * s3 * x * y;
+                so[6] = s5 * (y * y - 0.5f * (x * x + z * z));
+                so[7] = s5 * s3 * y * z;
+                so[8] = s5 * (s3 * 0.5f) * (z * z - x * x);
+            }
+            g = graph_of_a ? graph_of_a[a] : a;
+        }
+        s_d[tid] = d;
+        s_g[tid] = g;
+    }
+    __syncthreads();
+    for (int i = tid; i < p.n_rbf * kFE; i += 128) {
+        const int k = i / kFE, el = i % kFE;
+        const float t = s_d[el] - p.rbf_offset[k];
+        s_in[i] = expf(p.rbf_coeff * (t * t));
+    }
+    for (int i = tid; i < p.n_pre * kFE; i += 128) {
+        const int k = i / kFE, el = i % kFE;
+        const int e = e0 + el;
+        s_in[p.n_rbf * kFE + i] = (pre != nullptr && e < n_pre_rows) ? pre[(size_t)e * p.n_pre + k] : 0.f;
+    }
+    __syncthreads();
+    const int quad = tid & 15, oct = tid >> 4;
+    const int o = 4 * quad;
+    if (o >= p.ns) return;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 b = (u != nullptr) ? *reinterpret_cast<const float4 *>(u + (size_t)s_g[oct * 8 + i] * p.ns + o)
+                                        : *reinterpret_cast<const float4 *>(p.b1 + o);
+        acc[i][0] = b.x; acc[i][1] = b.y; acc[i][2] = b.z; acc[i][3] = b.w;
+    }
+    const int n_k = p.n_rbf + p.n_pre;
+#pragma unroll 8
+    for (int k = 0; k < n_k; ++k) {
+        const float4 w = *reinterpret_cast<const float4 *>(s_w + k * p.ns + o);
+        const float4 v0 = *reinterpret_cast<const float4 *>(s_in + k * kFE + oct * 8);
+        const float4 v1 = *reinterpret_cast<const float4 *>(s_in + k * kFE + oct * 8 + 4);
+        const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            acc[i][0] = fmaf(w.x, v[i], acc[i][0]); acc[i][1] = fmaf(w.y, v[i], acc[i][1]);
+            acc[i][2] = fmaf(w.z, v[i], acc[i][2]); acc[i][3] = fmaf(w.w, v[i], acc[i][3]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int e = e0 + oct * 8 + i;
+        if (e < n_edges)
+            *reinterpret_cast<float4 *>(emb + (size_t)e * p.ns + o) =
+                make_float4(fmaxf(acc[i][0], 0.f), fmaxf(acc[i][1], 0.f), fmaxf(acc[i][2], 0.f), fmaxf(acc[i][3], 0.f));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxUpdates = 4;
 struct UpdatePack { ddp_update_t u[kMaxUpdates]; int n; };
@@ -468,8 +562,15 @@ extern "C" int ddp_edge_embed(const float *pos_a, const float *pos_b, const int3
         return DDP_E_SHAPE;
     if (!u && !mlp->b1) return DDP_E_ARG;
     if (edge_cap <= 0) return 0;
-    edge_embed_kernel<<<(edge_cap + kEE - 1) / kEE, kEEThreads, 0, (cudaStream_t)stream>>>(
-        pos_a, pos_b, edge, edge_cap, n_edges_dev, graph_of_a, pre, n_pre_rows, u, *mlp, sh, emb);
+    const bool aligned = mlp->ns % 4 == 0 && reinterpret_cast<uintptr_t>(emb) % 16 == 0 && reinterpret_cast<uintptr_t>(u) % 16 == 0 &&
+                         reinterpret_cast<uintptr_t>(mlp->w_rbf) % 16 == 0 && reinterpret_cast<uintptr_t>(mlp->w_pre) % 16 == 0 &&
+                         reinterpret_cast<uintptr_t>(mlp->b1) % 16 == 0;
+    if (mlp->w2 == nullptr && aligned)
+        edge_embed_fold_kernel<<<(edge_cap + kFE - 1) / kFE, 128, 0, (cudaStream_t)stream>>>(
+            pos_a, pos_b, edge, edge_cap, n_edges_dev, graph_of_a, pre, n_pre_rows, u, *mlp, sh, emb);
+    else
+        edge_embed_kernel<<<(edge_cap + kEE - 1) / kEE, kEEThreads, 0, (cudaStream_t)stream>>>(
+            pos_a, pos_b, edge, edge_cap, n_edges_dev, graph_of_a, pre, n_pre_rows, u, *mlp, sh, emb);
     DDP_LAUNCH_CHECK();
     return 0;
 }
