@@ -64,6 +64,28 @@ class Plan:
     pass
 
 
+class _Branches:
+    """Fork / join of independent kernel chains onto side streams (works eagerly and under CUDA-graph capture:
+    the side streams join the capture through the fork event and are joined back before the forward returns)."""
+
+    def __init__(self, device, n=4):
+        self.side = [torch.cuda.Stream(device=device) for _ in range(n)]
+
+    def fork(self, k):
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        for s in self.side[:k]:
+            s.wait_event(ev)
+        return main
+
+    def join(self, main, k):
+        for s in self.side[:k]:
+            ev = torch.cuda.Event()
+            ev.record(s)
+            main.wait_event(ev)
+
+
 class TensorProductScoreModel(nn.Module):
     def __init__(self, t_to_sigma, device, timestep_emb_func, in_lig_edge_features=4, sigma_embed_dim=32, sh_lmax=2,
                  ns=16, nv=4, num_conv_layers=2, lig_max_radius=5, rec_max_radius=30, cross_max_distance=250,
@@ -522,6 +544,11 @@ class TensorProductScoreModel(nn.Module):
         self._host_scalars(pl, complex_t)
         return self.launch_plan(pl, return_layers)
 
+    def _branches(self, device):
+        if getattr(self, '_br', None) is None or self._br_dev != device:
+            self._br, self._br_dev = _Branches(device), device
+        return self._br
+
     def launch_plan(self, pl, return_layers=False):
         """Kernel launches only (per-graph scalars already staged in ``pl.scal``): CUDA-graph capturable."""
         P = self.packed()
@@ -541,38 +568,52 @@ class TensorProductScoreModel(nn.Module):
         chk(L.ddp_node_init(ptr(pl.lig_static), ptr(U['lig_node']), ptr(pl.lig_batch), pl.NL, ns, ptr(xl), F, st), 'node_init')
         chk(L.ddp_node_init(ptr(pl.rec_static), ptr(U['rec_node']), ptr(pl.rec_batch), pl.NR, ns, ptr(xr), F, st), 'node_init')
         chk(L.ddp_node_init(ptr(pl.atom_static), ptr(U['atom_node']), ptr(pl.atom_batch), pl.NA, ns, ptr(xa), F, st), 'node_init')
-        # ---- dynamic graphs --------------------------------------------------------------------
-        e = es['ll']
-        chk(L.ddp_radius(ptr(pl.lig_pos), ptr(pl.lig_pos), ptr(pl.lig_ptr), ptr(pl.lig_ptr), B, pl.NL, None,
-                         float(self.lig_max_radius), 33, 1, pl.Eb, ptr(e.slab), e.slab_w, ptr(e.counts), ptr(e.edge), e.cap,
-                         ptr(e.n_dev), st), 'ddp_radius(ll)')
-        e = es['aa']
-        chk(L.ddp_knn_graph(ptr(pl.atom_pos), ptr(pl.atom_ptr), B, pl.NA, pl.knn_k, ptr(e.slab), e.slab_w, ptr(e.counts),
-                            ptr(e.edge), e.cap, ptr(e.n_dev), st), 'ddp_knn_graph')
-        e = es['lr']
-        if self.dynamic_max_cross:
-            chk(L.ddp_radius(ptr(pl.rec_pos), ptr(pl.lig_pos), ptr(pl.rec_ptr), ptr(pl.lig_ptr), B, pl.NL, ptr(cutoff), 1.0, 10000,
-                             0, 0, ptr(e.slab), e.slab_w, ptr(e.counts), ptr(e.edge), e.cap, ptr(e.n_dev), st), 'ddp_radius(lr)')
-        else:
-            chk(L.ddp_radius(ptr(pl.rec_pos), ptr(pl.lig_pos), ptr(pl.rec_ptr), ptr(pl.lig_ptr), B, pl.NL, None,
-                             float(self.cross_max_distance), 10000, 0, 0, ptr(e.slab), e.slab_w, ptr(e.counts), ptr(e.edge), e.cap,
-                             ptr(e.n_dev), st), 'ddp_radius(lr)')
-        e = es['la']
-        chk(L.ddp_radius(ptr(pl.atom_pos), ptr(pl.lig_pos), ptr(pl.atom_ptr), ptr(pl.lig_ptr), B, pl.NL, None,
-                         float(self.lig_max_radius), 10000, 0, 0, ptr(e.slab), e.slab_w, ptr(e.counts), ptr(e.edge), e.cap,
-                         ptr(e.n_dev), st), 'ddp_radius(la)')
-        pl.deg_arena.copy_(pl.deg_base)                               # static edge sets + ligand bond edges
-        chk(L.ddp_degree_multi(pl.deg_jobs, len(pl.deg_jobs), st), 'ddp_degree_multi')   # dynamic ones, one launch
-        # ---- edge geometry + embeddings ------------------------------------------------------------
+        # ---- dynamic graphs + edge geometry / embeddings: one independent chain per edge set, on side streams ------
         em = P['em']
         geo = {'ll': (pl.lig_pos, pl.lig_pos, pl.lig_batch), 'rr': (pl.rec_pos, pl.rec_pos, pl.rec_batch),
                'aa': (pl.atom_pos, pl.atom_pos, pl.atom_batch), 'lr': (pl.lig_pos, pl.rec_pos, pl.lig_batch),
                'la': (pl.lig_pos, pl.atom_pos, pl.lig_batch), 'ar': (pl.atom_pos, pl.rec_pos, pl.atom_batch)}
-        for nm, (pa, pb, ga) in geo.items():
-            e = es[nm]
+
+        def embed(nm, st_):
+            pa, pb, ga = geo[nm]
+            e_ = es[nm]
             pre, npre = (pl.bond_attr, pl.Eb) if nm == 'll' else (None, 0)
-            chk(L.ddp_edge_embed(ptr(pa), ptr(pb), ptr(e.edge), e.cap, ptr(e.n_dev), ptr(ga), ptr(pre), npre, ptr(U[nm]),
-                                 C.byref(em[nm]['desc']), ptr(e.sh), ptr(e.emb), st), f'ddp_edge_embed({nm})')
+            chk(L.ddp_edge_embed(ptr(pa), ptr(pb), ptr(e_.edge), e_.cap, ptr(e_.n_dev), ptr(ga), ptr(pre), npre, ptr(U[nm]),
+                                 C.byref(em[nm]['desc']), ptr(e_.sh), ptr(e_.emb), st_), f'ddp_edge_embed({nm})')
+
+        def build(nm, st_):
+            e = es[nm]
+            if nm == 'll':
+                chk(L.ddp_radius(ptr(pl.lig_pos), ptr(pl.lig_pos), ptr(pl.lig_ptr), ptr(pl.lig_ptr), B, pl.NL, None,
+                                 float(self.lig_max_radius), 33, 1, pl.Eb, ptr(e.slab), e.slab_w, ptr(e.counts), ptr(e.edge), e.cap,
+                                 ptr(e.n_dev), st_), 'ddp_radius(ll)')
+            elif nm == 'aa':
+                chk(L.ddp_knn_graph(ptr(pl.atom_pos), ptr(pl.atom_ptr), B, pl.NA, pl.knn_k, ptr(e.slab), e.slab_w, ptr(e.counts),
+                                    ptr(e.edge), e.cap, ptr(e.n_dev), st_), 'ddp_knn_graph')
+            elif nm == 'lr' and self.dynamic_max_cross:
+                chk(L.ddp_radius(ptr(pl.rec_pos), ptr(pl.lig_pos), ptr(pl.rec_ptr), ptr(pl.lig_ptr), B, pl.NL, ptr(cutoff), 1.0, 10000,
+                                 0, 0, ptr(e.slab), e.slab_w, ptr(e.counts), ptr(e.edge), e.cap, ptr(e.n_dev), st_), 'ddp_radius(lr)')
+            elif nm == 'lr':
+                chk(L.ddp_radius(ptr(pl.rec_pos), ptr(pl.lig_pos), ptr(pl.rec_ptr), ptr(pl.lig_ptr), B, pl.NL, None,
+                                 float(self.cross_max_distance), 10000, 0, 0, ptr(e.slab), e.slab_w, ptr(e.counts), ptr(e.edge), e.cap,
+                                 ptr(e.n_dev), st_), 'ddp_radius(lr)')
+            else:
+                chk(L.ddp_radius(ptr(pl.atom_pos), ptr(pl.lig_pos), ptr(pl.atom_ptr), ptr(pl.lig_ptr), B, pl.NL, None,
+                                 float(self.lig_max_radius), 10000, 0, 0, ptr(e.slab), e.slab_w, ptr(e.counts), ptr(e.edge), e.cap,
+                                 ptr(e.n_dev), st_), 'ddp_radius(la)')
+            embed(nm, st_)
+
+        br = self._branches(pl.device)
+        main = br.fork(3)
+        for side, nm in zip(br.side, ('aa', 'lr', 'la')):
+            with torch.cuda.stream(side):
+                build(nm, _lib.stream_ptr())
+        build('ll', st)
+        embed('rr', st)
+        embed('ar', st)
+        br.join(main, 3)
+        pl.deg_arena.copy_(pl.deg_base)                               # static edge sets + ligand bond edges
+        chk(L.ddp_degree_multi(pl.deg_jobs, len(pl.deg_jobs), st), 'ddp_degree_multi')   # dynamic ones, one launch
         # ---- interaction layers (all_atom_score_model.py:271-324) --------------------------------
         layers_out = []
         seq_dims = [tpmod.irreps_dim(tpmod.parse_irreps(s)) for s in self.irrep_seq]
@@ -659,7 +700,46 @@ class TensorProductScoreModel(nn.Module):
             chk(L.ddp_row_mlp(ptr(pl.conf_in), B, ld, arr, 3, None, ptr(pl.conf_out), pl.conf_out.shape[1], st), 'row_mlp')
             return pl.conf_out.squeeze(dim=-1)
 
-        # ---- translation / rotation head (:357-384) ---------------------------------------------------
+        # ---- heads: the two torsion heads run on side streams next to the translation / rotation head --------------
+        def tor_head(key, n, pos, xn, nptr, conv, mlp_key, emk, out, soff, st_):           # :386-434
+            h = getattr(pl, key)
+            e = h.es
+            chk(L.ddp_bond_geometry(ptr(pos), ptr(h.bonds), n, ptr(xn), F, ns, ptr(h.mid), ptr(h.y2), ptr(h.attr), st_), 'bond_geometry')
+            chk(L.ddp_radius(ptr(pos), ptr(h.mid), ptr(nptr), ptr(h.ptr), B, n, None, float(self.lig_max_radius), 32, 0, 0,
+                             ptr(e.slab), e.slab_w, ptr(e.counts), ptr(e.edge), e.cap, ptr(e.n_dev), st_), f'ddp_radius({key})')
+            chk(L.ddp_edge_embed(ptr(h.mid), ptr(pos), ptr(e.edge), e.cap, ptr(e.n_dev), ptr(h.batch), None, 0, None,
+                                 C.byref(em[emk]['desc']), ptr(e.sh), ptr(e.emb), st_), f'ddp_edge_embed({key})')
+            if self._tor_ftp['paths'] is None:
+                chk(L.ddp_tor_edge_sh(ptr(e.sh), self.sh_dim, ptr(h.y2), ptr(P['c121']), ptr(e.edge), ptr(e.n_dev), e.cap, ptr(h.sh_tor), st_), 'tor_edge_sh')
+            else:
+                chk(L.ddp_tor_edge_sh_generic(ptr(e.sh), self.sh_dim, ptr(h.y2), P['ftp_paths'], len(P['ftp_paths']), ptr(P['ftp_ctab']),
+                                              ptr(e.edge), ptr(e.n_dev), e.cap, ptr(h.sh_tor), self._tor_ftp['dim'], st_), 'tor_edge_sh_generic')
+            e.sh_conv = h.sh_tor
+            h.sum.zero_()
+            h.deg.zero_()
+            chk(L.ddp_degree(e.row(0), ptr(e.n_dev), e.cap, ptr(h.deg), st_), 'ddp_degree')
+            pk = P[key + '_conv']
+            self._conv_group(L, st_, [(conv, pk, e, False, xn, xn, 1, h.attr, 0, h.sum)])
+            up = _lib.Update(sum=ptr(h.sum), deg=ptr(h.deg), scale=ptr(pk.bn_scale), shift=ptr(pk.bn_shift), n_edges_dev=ptr(e.n_dev))
+            chk(L.ddp_node_update(None, 0, 0, C.byref(up), 1, n, 2 * ns, ptr(h.feat), 2 * ns, st_), 'ddp_node_update')
+            (w1, _), (w2, _) = P[mlp_key]
+            arr = (_lib.MlpLayer * 2)(_lib.MlpLayer(wt=ptr(w1), b=None, n_in=2 * ns, n_out=ns, act=2),
+                                      _lib.MlpLayer(wt=ptr(w2), b=None, n_in=ns, n_out=1, act=0))
+            rs = pl.scal[soff:soff + n] if self.scale_by_sigma else None
+            chk(L.ddp_row_mlp(ptr(h.feat), n, 2 * ns, arr, 2, ptr(rs), ptr(out), 1, st_), 'row_mlp')
+            return out[:n]
+
+        heads = (('tor', pl.T, pl.lig_pos, xl, pl.lig_ptr, getattr(self, 'tor_bond_conv', None), 'tor_mlp', 'tor', pl.tor_out, 4 * B),
+                 ('sc', pl.S, pl.atom_pos, xa, pl.atom_ptr, getattr(self, 'sc_tor_bond_conv', None), 'sc_mlp', 'sc', pl.sc_out, 4 * B + pl.T))
+        main = br.fork(2)
+        outs = []
+        for side, hd in zip(br.side, heads):
+            if hd[1] == 0:
+                outs.append(torch.empty(0, device=pl.device))
+                continue
+            with torch.cuda.stream(side):
+                outs.append(tor_head(*hd, _lib.stream_ptr()))
+        # translation / rotation head (:357-384)
         ec = es['center']
         chk(L.ddp_segment_mean(ptr(pl.lig_pos), None, ptr(pl.lig_ptr), B, 3, 3, ptr(pl.center), 3, st), 'segment_mean')
         chk(L.ddp_edge_embed(ptr(pl.center), ptr(pl.lig_pos), ptr(ec.edge), ec.cap, ptr(ec.n_dev), None, None, 0, ptr(U['center']),
@@ -673,43 +753,10 @@ class TensorProductScoreModel(nn.Module):
         if self.scale_by_sigma:
             trs, son = tr_sigma, so3n
         else:
-            trs = son = torch.ones(B, device=pl.device)
+            trs = son = pl.ones_F[:B] if B <= pl.ones_F.numel() else torch.ones(B, device=pl.device)
         chk(L.ddp_tr_rot_head(ptr(pl.g), ptr(pl.sig), self.sigma_embed_dim, B, ptr(tw1), ptr(tb1), ptr(tw2), ptr(tb2), ptr(rw1),
                               ptr(rb1), ptr(rw2), ptr(rb2), ns, ptr(trs), ptr(son), ptr(pl.tr_out), ptr(pl.rot_out), st), 'tr_rot_head')
-        # ---- torsion heads (:386-434) ----------------------------------------------------------------------
-        outs = []
-        for key, n, pos, xn, nptr, conv, mlp_key, emk, out, soff in (
-                ('tor', pl.T, pl.lig_pos, xl, pl.lig_ptr, getattr(self, 'tor_bond_conv', None), 'tor_mlp', 'tor', pl.tor_out, 4 * B),
-                ('sc', pl.S, pl.atom_pos, xa, pl.atom_ptr, getattr(self, 'sc_tor_bond_conv', None), 'sc_mlp', 'sc', pl.sc_out, 4 * B + pl.T)):
-            if n == 0:
-                outs.append(torch.empty(0, device=pl.device))
-                continue
-            h = getattr(pl, key)
-            e = h.es
-            chk(L.ddp_bond_geometry(ptr(pos), ptr(h.bonds), n, ptr(xn), F, ns, ptr(h.mid), ptr(h.y2), ptr(h.attr), st), 'bond_geometry')
-            chk(L.ddp_radius(ptr(pos), ptr(h.mid), ptr(nptr), ptr(h.ptr), B, n, None, float(self.lig_max_radius), 32, 0, 0,
-                             ptr(e.slab), e.slab_w, ptr(e.counts), ptr(e.edge), e.cap, ptr(e.n_dev), st), f'ddp_radius({key})')
-            chk(L.ddp_edge_embed(ptr(h.mid), ptr(pos), ptr(e.edge), e.cap, ptr(e.n_dev), ptr(h.batch), None, 0, None,
-                                 C.byref(em[emk]['desc']), ptr(e.sh), ptr(e.emb), st), f'ddp_edge_embed({key})')
-            if self._tor_ftp['paths'] is None:
-                chk(L.ddp_tor_edge_sh(ptr(e.sh), self.sh_dim, ptr(h.y2), ptr(P['c121']), ptr(e.edge), ptr(e.n_dev), e.cap, ptr(h.sh_tor), st), 'tor_edge_sh')
-            else:
-                chk(L.ddp_tor_edge_sh_generic(ptr(e.sh), self.sh_dim, ptr(h.y2), P['ftp_paths'], len(P['ftp_paths']), ptr(P['ftp_ctab']),
-                                              ptr(e.edge), ptr(e.n_dev), e.cap, ptr(h.sh_tor), self._tor_ftp['dim'], st), 'tor_edge_sh_generic')
-            e.sh_conv = h.sh_tor
-            h.sum.zero_()
-            h.deg.zero_()
-            chk(L.ddp_degree(e.row(0), ptr(e.n_dev), e.cap, ptr(h.deg), st), 'ddp_degree')
-            pk = P[key + '_conv']
-            self._conv_group(L, st, [(conv, pk, e, False, xn, xn, 1, h.attr, 0, h.sum)])
-            up = _lib.Update(sum=ptr(h.sum), deg=ptr(h.deg), scale=ptr(pk.bn_scale), shift=ptr(pk.bn_shift), n_edges_dev=ptr(e.n_dev))
-            chk(L.ddp_node_update(None, 0, 0, C.byref(up), 1, n, 2 * ns, ptr(h.feat), 2 * ns, st), 'ddp_node_update')
-            (w1, _), (w2, _) = P[mlp_key]
-            arr = (_lib.MlpLayer * 2)(_lib.MlpLayer(wt=ptr(w1), b=None, n_in=2 * ns, n_out=ns, act=2),
-                                      _lib.MlpLayer(wt=ptr(w2), b=None, n_in=ns, n_out=1, act=0))
-            rs = pl.scal[soff:soff + n] if self.scale_by_sigma else None
-            chk(L.ddp_row_mlp(ptr(h.feat), n, 2 * ns, arr, 2, ptr(rs), ptr(out), 1, st), 'row_mlp')
-            outs.append(out[:n])
+        br.join(main, 2)
         return pl.tr_out, pl.rot_out, outs[0], outs[1]
 
     def forward(self, data):
