@@ -144,6 +144,100 @@ __global__ void knn_scan_kernel(const float *__restrict__ x, const int32_t *__re
     }
 }
 
+// Filtered form for small k on dense point sets (heavy atoms of a protein pocket) whose examples fit one shared-memory
+// stage: kKnnFSub threads per centre scan a quarter of the example each and only RECORD the candidates closer than a
+// radius (a rare, cheap event - no divergent sorted insertion inside the scan); the k + 1 nearest are then selected
+// among the ~30 recorded ones with the (distance, index) order of the sequential scan.  Exact: if at least k + 1
+// candidates lie inside the radius, the k + 1 nearest do too.  A centre with too few (surface atom) or too many
+// recorded candidates retries with the next radius; the last resort is the full insertion scan.
+constexpr int kKnnFilterCap = 96;
+constexpr int kKnnFC = 32;           // centres per block
+constexpr int kKnnFSub = 8;          // threads per centre (the scan is a latency-bound LDS -> FADD chain: more, shorter chains)
+template <int KP>
+__global__ void __launch_bounds__(kKnnFC * kKnnFSub)
+knn_scan_filter_kernel(const float *__restrict__ x, const int32_t *__restrict__ ptr, int num_examples, int n,
+                       int32_t *__restrict__ slab, int slab_w, int32_t *__restrict__ counts) {
+    extern __shared__ __align__(16) unsigned char knn_smem[];
+    float *sx = reinterpret_cast<float *>(knn_smem);                              // [kKnnStage * 3]
+    int *cand = reinterpret_cast<int *>(sx + kKnnStage * 3);                       // [kKnnFilterCap][kKnnFC]
+    int *cnt = cand + kKnnFilterCap * kKnnFC;                                      // [kKnnFC]
+    const int tid = threadIdx.x, sub = tid % kKnnFSub, c = tid / kKnnFSub;
+    // block -> (example, block inside the example): blocks never straddle examples (grid = ceil(n / FC) + num_examples)
+    int b = 0, lb = blockIdx.x;
+    while (b < num_examples) {
+        const int nb = (ptr[b + 1] - ptr[b] + kKnnFC - 1) / kKnnFC;
+        if (lb < nb) break;
+        lb -= nb;
+        ++b;
+    }
+    if (b >= num_examples) return;
+    const int beg = ptr[b], m = ptr[b + 1] - beg;
+    const int j0 = beg + lb * kKnnFC + c;
+    const int j = j0 < beg + m ? j0 : n;                                           // n marks an idle lane
+    float yx = 0.f, yy = 0.f, yz = 0.f;
+    if (j < n) { yx = x[3 * j]; yy = x[3 * j + 1]; yz = x[3 * j + 2]; }
+    if (m > kKnnStage) {                                                           // example too large to stage: plain scan
+        if (j < n && sub == 0) {
+            float bd[KP];
+            int bi[KP];
+#pragma unroll
+            for (int e = 0; e < KP; ++e) { bd[e] = 1e10f; bi[e] = -1; }
+            for (int i = beg; i < beg + m; ++i) knn_insert<KP>(bd, bi, ddp_sqdist(x[3 * i], x[3 * i + 1], x[3 * i + 2], yx, yy, yz), i);
+            int o = 0;
+#pragma unroll
+            for (int e = 0; e < KP; ++e)
+                if (bi[e] != -1 && bi[e] != j) { slab[(size_t)j * slab_w + o] = bi[e]; ++o; }
+            counts[j] = o;
+        }
+        return;
+    }
+    for (int t = tid; t < 3 * m; t += kKnnFC * kKnnFSub) sx[t] = x[3 * beg + t];
+    const int per = (m + kKnnFSub - 1) / kKnnFSub;
+    const int q0 = sub * per, q1 = min(m, (sub + 1) * per);
+    const unsigned group = ((1u << kKnnFSub) - 1u) << ((tid & 31) - sub);                              // the kKnnFSub lanes of this centre
+    bool need = j < n;
+    const float radii2[3] = {5.5f * 5.5f, 7.25f * 7.25f, 10.f * 10.f};      // sparse (surface) atoms retry with a wider ball
+#pragma unroll 1
+    for (int pass = 0; pass < 3; ++pass) {
+        if (sub == 0) cnt[c] = 0;
+        if (pass == 0) __syncthreads(); else __syncwarp(group);
+        if (need) {
+            const float r2 = radii2[pass];
+            for (int t = q0; t < q1; ++t) {
+                if (ddp_sqdist(sx[3 * t], sx[3 * t + 1], sx[3 * t + 2], yx, yy, yz) < r2) {
+                    const int pos = atomicAdd(&cnt[c], 1);
+                    if (pos < kKnnFilterCap) cand[pos * kKnnFC + c] = beg + t;
+                }
+            }
+        }
+        __syncwarp(group);
+        const int got = cnt[c];
+        // enough candidates (or simply every point of a tiny example) and no overflow: done
+        need = need && !((got >= KP || got == m) && got <= kKnnFilterCap);
+        if (!__any_sync(group, need)) break;
+    }
+    if (j >= n || sub != 0) return;
+    float bd[KP];
+    int bi[KP];
+#pragma unroll
+    for (int e = 0; e < KP; ++e) { bd[e] = 1e10f; bi[e] = -1; }
+    if (!need) {
+        const int got = cnt[c];
+        for (int k = 0; k < got; ++k) {
+            const int i = cand[k * kKnnFC + c] - beg;
+            knn_insert_lex<KP>(bd, bi, ddp_sqdist(sx[3 * i], sx[3 * i + 1], sx[3 * i + 2], yx, yy, yz), beg + i);
+        }
+    } else {
+        for (int t = 0; t < m; ++t) knn_insert<KP>(bd, bi, ddp_sqdist(sx[3 * t], sx[3 * t + 1], sx[3 * t + 2], yx, yy, yz), beg + t);
+    }
+    int o = 0;
+#pragma unroll
+    for (int e = 0; e < KP; ++e) {
+        if (bi[e] != -1 && bi[e] != j) { slab[(size_t)j * slab_w + o] = bi[e]; ++o; }
+    }
+    counts[j] = o;
+}
+
 // Generic-k fallback (k + 1 <= 101, arrays in local memory).
 __global__ void knn_scan_generic_kernel(const float *__restrict__ x, const int32_t *__restrict__ ptr, int num_examples,
                                         int n, int kp, int32_t *__restrict__ slab, int slab_w,
@@ -276,7 +370,19 @@ extern "C" int ddp_knn_graph(const float *x, const int32_t *ptr, int32_t num_exa
     if (n > 0) {
         const int qpb = kKnnThreads / kKnnSub;
         const int grid_sub = (n + qpb - 1) / qpb, grid = (n + kKnnThreads - 1) / kKnnThreads;
-        if (kp == 9) knn_scan_kernel<9><<<grid_sub, kKnnThreads, 0, st>>>(x, ptr, num_examples, n, slab, slab_w, counts);
+        const size_t fsm = (size_t)kKnnStage * 3 * sizeof(float) + (size_t)(kKnnFilterCap + 1) * kKnnFC * sizeof(int);
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e1 = cudaFuncSetAttribute(knn_scan_filter_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
+            cudaError_t e2 = cudaFuncSetAttribute(knn_scan_filter_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
+            if (e1 != cudaSuccess || e2 != cudaSuccess) return (int)(e1 != cudaSuccess ? e1 : e2);
+            configured = true;
+        }
+        const bool filt = kp == 9 || kp == 13;
+        const int fgrid = (n + kKnnFC - 1) / kKnnFC + num_examples;
+        if (filt && kp == 9) knn_scan_filter_kernel<9><<<fgrid, kKnnFC * kKnnFSub, fsm, st>>>(x, ptr, num_examples, n, slab, slab_w, counts);
+        else if (filt) knn_scan_filter_kernel<13><<<fgrid, kKnnFC * kKnnFSub, fsm, st>>>(x, ptr, num_examples, n, slab, slab_w, counts);
+        else if (kp == 9) knn_scan_kernel<9><<<grid_sub, kKnnThreads, 0, st>>>(x, ptr, num_examples, n, slab, slab_w, counts);
         else if (kp == 13) knn_scan_kernel<13><<<grid_sub, kKnnThreads, 0, st>>>(x, ptr, num_examples, n, slab, slab_w, counts);
         else if (kp == 33) knn_scan_kernel<33><<<grid_sub, kKnnThreads, 0, st>>>(x, ptr, num_examples, n, slab, slab_w, counts);
         else knn_scan_generic_kernel<<<grid, kKnnThreads, 0, st>>>(x, ptr, num_examples, n, kp, slab, slab_w, counts);
