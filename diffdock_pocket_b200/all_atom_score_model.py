@@ -279,7 +279,7 @@ class TensorProductScoreModel(nn.Module):
         half = sd // 2
         P['freq'] = torch.exp(torch.arange(half, dtype=torch.float32) * -(np.log(10000) / (half - 1))).to(dev)
         conv_edges = ('ll', 'lr', 'la', 'aa', 'la', 'ar', 'rr', 'lr', 'ar')       # edge embedding each of a layer's 9 convs reads
-        P['convs'] = [c.packed(dev, ns, ns, em[conv_edges[i % 9]]['fold']) for i, c in enumerate(self.conv_layers)]
+        P['convs'] = [c.packed(dev, ns, ns, em[conv_edges[i % 9]]['fold'], fold_bn=True) for i, c in enumerate(self.conv_layers)]
         if not self.confidence_mode:
             P['final_conv'] = self.final_conv.packed(dev, ns, ns, em['center']['fold'])
             def lin(l):
@@ -634,8 +634,8 @@ class TensorProductScoreModel(nn.Module):
             # BatchNorm scale, all_atom_score_model.py:315-324 + score_model.py:117,123) straight into it.
             def job(ci, nm, flip, x, p1, i1, p2, i2, buf):
                 agg_r = 1 if flip else 0
-                sc = Pk[ci].bn_scale if Pk[ci].bn_scale is not None else pl.ones_F
-                return (Cv[ci], Pk[ci], es[nm], flip, x, p1, i1, p2, i2, buf, sc, es[nm].deg[agg_r])
+                # BatchNorm scale lives in the packed weights (PackedConv fold_bn); without BatchNorm out_scale stays NULL
+                return (Cv[ci], Pk[ci], es[nm], flip, x, p1, i1, p2, i2, buf, None, es[nm].deg[agg_r])
             s_l = take(pl.NL)
             grp = [job(9 * l, 'll', False, xl, xl, 0, xl, 1, s_l), job(9 * l + 1, 'lr', False, xr, xl, 0, xr, 1, s_l),
                    job(9 * l + 2, 'la', False, xa, xl, 0, xa, 1, s_l)]

@@ -161,7 +161,8 @@ tpconv_fp32_kernel(ddp_tpconv_t c, ddp_tpconv_edges_t ed, int ctab_len, float *_
             if (node >= 0) {
                 float v = s.out[k * LDS_E + el];
                 if (ed.ew != nullptr) v *= ed.ew[e0 + el];
-                if (ed.out_scale != nullptr) v *= ed.out_scale[k] * __frcp_rn((float)max(ed.agg_deg ? ed.agg_deg[node] : 1, 1));
+                if (ed.out_scale != nullptr) v *= ed.out_scale[k];
+                if (ed.agg_deg != nullptr) v *= __frcp_rn((float)max(ed.agg_deg[node], 1));
                 atomicAdd(sum + (size_t)node * c.f_out + k, v);
             }
         }

@@ -677,7 +677,8 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                 agg = __ldg(ed.agg + e);
                 if (ed.agg_deg != nullptr) inv_deg = __frcp_rn((float)max(__ldg(ed.agg_deg + agg), 1));
                 const float4 sh4 = __ldg(reinterpret_cast<const float4 *>(ed.sh + (size_t)e * 4));
-                s0 = sh4.x; s1x = sh4.y; s1y = sh4.z; s1z = sh4.w;
+                // every basis row is linear in the edge harmonics: scaling them applies the scatter-mean for free
+                s0 = sh4.x * inv_deg; s1x = sh4.y * inv_deg; s1y = sh4.z * inv_deg; s1z = sh4.w * inv_deg;
                 xg = ed.x + (size_t)__ldg(ed.gather + e) * ed.ldx;
             }
             // node features of weight tile 0 (registers; every tile prefetches the next one's)
@@ -795,9 +796,14 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                     mbar_arrive(&tmem_empty[buf]);
                     if (r == 0) trace_ev(jobs.trace, 1, titer, 2);
                     if ((flags & 4) && valid) {
-                        if (ed.out_scale != nullptr) {
+                        if (ed.out_scale != nullptr) {                       // block offsets and widths are even: 8-byte loads
+                            const float2 *sc2 = reinterpret_cast<const float2 *>(ed.out_scale + out_off);
 #pragma unroll
-                            for (int o = 0; o < NS; ++o) acc[o] *= __ldg(ed.out_scale + out_off + o) * inv_deg;
+                            for (int o = 0; o < NS; o += 2) {
+                                const float2 v = __ldg(sc2 + (o >> 1));
+                                acc[o] *= v.x;
+                                acc[o + 1] *= v.y;
+                            }
                         }
                         red_row<NS>(sum + (size_t)agg * f_out + out_off, acc);
                     }
@@ -874,8 +880,13 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                     if (r == 0) trace_ev(jobs.trace, 1, titer, 2);
                     if ((flags & 4) && valid) {
                         if (ed.out_scale != nullptr) {
+                            const float2 *sc2 = reinterpret_cast<const float2 *>(ed.out_scale + out_off);
 #pragma unroll
-                            for (int o = 0; o < 3 * NV; ++o) acc[o] *= __ldg(ed.out_scale + out_off + o) * inv_deg;
+                            for (int o = 0; o < 3 * NV; o += 2) {
+                                const float2 v = __ldg(sc2 + (o >> 1));
+                                acc[o] *= v.x;
+                                acc[o + 1] *= v.y;
+                            }
                         }
                         red_row<3 * NV>(sum + (size_t)agg * f_out + out_off, acc);
                     }

@@ -148,7 +148,7 @@ class _TP(nn.Module):
 class PackedConv:
     """Device-side, kernel-friendly image of one TensorProductConvLayer (built once per weight load)."""
 
-    def __init__(self, layer, device, n_emb, ns, edge_fold=None):
+    def __init__(self, layer, device, n_emb, ns, edge_fold=None, fold_bn=False):
         """``edge_fold`` = (W2e [n_emb, h], b2e [n_emb]) of the edge-embedding MLP's second Linear: folded into the
         first n_emb input columns of fc[0], so that the conv consumes the MLP's hidden activations directly."""
         spec = layer.tp.spec
@@ -163,8 +163,20 @@ class PackedConv:
         self.w1_host, self.b1_host = W1.float().contiguous(), b1.float().contiguous()       # nn.Linear layout, for the UMMA pack
         self.w1t = self.w1_host.T.contiguous().to(**f32)
         self.b1 = self.b1_host.to(**f32)
-        self.w2t = fc3.weight.detach().T.contiguous().to(**f32)
-        self.b2 = fc3.bias.detach().contiguous().to(**f32)
+        W2, b2 = fc3.weight.detach().double().cpu(), fc3.bias.detach().double().cpu()
+        self.bn_folded = bool(fold_bn and layer.batch_norm is not None)
+        if self.bn_folded:
+            # the BatchNorm (eval) scale of output channel c multiplies every weight column that feeds c; the shift stays
+            # with ddp_node_update.  Scale is constant over the components of an irrep, so one value per (group, o).
+            sc, _ = layer.batch_norm.folded()
+            col = torch.ones(spec.weight_numel, dtype=torch.float64)
+            for g in spec.groups:
+                o = torch.arange(g['mul_in'] * g['mul_out']) % g['mul_out']
+                col[g['w_off']:g['w_off'] + g['mul_in'] * g['mul_out']] = sc.double()[g['out_off'] + o * g['d_out']]
+            W2, b2 = W2 * col[:, None], b2 * col
+        self.w2_host, self.b2_host = W2.float().contiguous(), b2.float().contiguous()       # nn.Linear layout, for the UMMA pack
+        self.w2t = self.w2_host.T.contiguous().to(**f32)
+        self.b2 = self.b2_host.to(**f32)
         self.k1, self.hid = fc0.in_features, fc0.out_features
         garr = (_lib.TpGroup * len(spec.groups))(*[_lib.TpGroup(**g) for g in spec.groups])
         self.groups_host = garr
@@ -186,10 +198,8 @@ class PackedConv:
     def umma_image(self, layer, mode, device):
         if mode not in self.umma:
             L = _lib.lib()
-            fc3 = layer.fc[3]
             w1, b1 = self.w1_host, self.b1_host
-            w2 = fc3.weight.detach().cpu().float().contiguous()
-            b2 = fc3.bias.detach().cpu().float().contiguous()
+            w2, b2 = self.w2_host, self.b2_host
             ctab = torch.tensor(self.spec.ctab, dtype=torch.float32)
             args = (C.byref(self.cdesc), self.groups_host, ptr(ctab), ptr(w1), ptr(b1), ptr(w2), ptr(b2), mode)
             size = L.ddp_tpconv_pack(*args, None)
@@ -228,11 +238,11 @@ class TensorProductConvLayer(nn.Module):
         self._packed = None
         return super()._load_from_state_dict(*a, **k)
 
-    def packed(self, device, n_emb, ns, edge_fold=None):
-        key = None if edge_fold is None else tuple(id(t) for t in edge_fold)
+    def packed(self, device, n_emb, ns, edge_fold=None, fold_bn=False):
+        key = (None if edge_fold is None else tuple(id(t) for t in edge_fold), bool(fold_bn))
         if self._packed is None or self._packed.w1t.device != torch.device(device) or self._packed.cdesc.n_emb != n_emb \
                 or self._packed.fold_key != key:
-            self._packed = PackedConv(self, device, n_emb, ns, edge_fold)
+            self._packed = PackedConv(self, device, n_emb, ns, edge_fold, fold_bn)
             self._packed.fold_key = key
         return self._packed
 

@@ -163,7 +163,8 @@ typedef struct {
     const int32_t *n_edges_dev; int32_t edge_cap;
     /* optional pre-normalised accumulation: sum[agg][c] += out[c] * out_scale[c] / max(agg_deg[agg], 1), i.e. the
      * scatter-MEAN and the BatchNorm scale of this conv applied on the fly, so that several convs of a layer can
-     * accumulate into ONE buffer (ddp_node_update then adds only their shifts).  Both NULL: plain sums. */
+     * accumulate into ONE buffer (ddp_node_update then adds only their shifts).  Both NULL: plain sums.  Either may
+     * be given alone (the host mirror folds the BatchNorm scale into the packed weights and passes only agg_deg). */
     const float *out_scale;       /* [f_out] */
     const int32_t *agg_deg;       /* [n_out] in-degree of the aggregation nodes for this edge set */
 } ddp_tpconv_edges_t;
