@@ -270,10 +270,16 @@ struct Jobs {
     long long *trace;     // optional timing trace of CTA 0 (ddp_tpconv_umma_set_trace), NULL in production
     Job job[MAX_JOBS];
 };
-constexpr int TRACE_EVENTS = 8, TRACE_TILES = 256;
+[[maybe_unused]] constexpr int TRACE_EVENTS = 8, TRACE_TILES = 256;
 // trace[(role * TRACE_TILES + tile iteration) * TRACE_EVENTS + event] = clock64 (CTA 0, one lane per role)
+// Compiled in only with -DDDP_UMMA_TRACE (scripts/umma_trace.py builds such a library): the hooks sit in the per-tile
+// loops of the issue and epilogue warps and cost ~5 % of the epilogue's instructions even when the pointer is NULL.
 __device__ __forceinline__ void trace_ev(long long *trace, int role, int iter, int ev) {
+#ifdef DDP_UMMA_TRACE
     if (trace != nullptr && blockIdx.x == 0 && iter < TRACE_TILES) trace[(role * TRACE_TILES + iter) * TRACE_EVENTS + ev] = clock64();
+#else
+    (void)trace; (void)role; (void)iter; (void)ev;
+#endif
 }
 
 template <int NS, int NV, int KS, bool SPLIT>
@@ -355,6 +361,31 @@ __device__ __forceinline__ void x_prefetch(const float *xg, int n_fl, float (&xn
     }
 }
 
+// Same, for a compile-time count (the common case: full tiles): N / 2 unpredicated 8-byte loads.
+template <int N, int XN>
+__device__ __forceinline__ void x_prefetch_n(const float *xg, float (&xn)[XN]) {
+    static_assert(N % 2 == 0 && N <= XN, "pairs");
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) {
+        const float2 v = __ldg(reinterpret_cast<const float2 *>(xg) + j);
+        xn[2 * j] = v.x; xn[2 * j + 1] = v.y;
+    }
+}
+// Node features of the weight tile described by tdw: full tiles of every kind take the unpredicated path.
+template <int NS, int NV, int ROWS_S, int XN>
+__device__ __forceinline__ void x_prefetch_tile(const float *xg_row, const uint4 &tdw, int f_in, float (&xn)[XN]) {
+    const int kind = (int)((tdw.x >> 16) & 0xffu), n_rows = (int)(tdw.x >> 24), x_off = (int)(tdw.z & 0xffffu);
+    const float *xg = xg_row + x_off;
+    constexpr int N0 = ROWS_S + (ROWS_S & 1), N1 = 3 * ROWS_S + (ROWS_S & 1), N2 = 2 * NV, N3 = 3 * NV + (NV & 1);
+    const int full = kind == 0 ? N0 : (kind == 1 ? N1 : (kind == 2 ? N2 : N3));
+    const bool fast = (reinterpret_cast<uintptr_t>(xg) & 7) == 0 && x_off + full <= f_in;   // stays inside the node's row
+    if (fast && kind == 0) x_prefetch_n<N0, XN>(xg, xn);
+    else if (fast && kind == 1) x_prefetch_n<N1, XN>(xg, xn);
+    else if (fast && kind == 2) x_prefetch_n<N2, XN>(xg, xn);
+    else if (fast) x_prefetch_n<N3, XN>(xg, xn);
+    else x_prefetch<XN>(xg, n_rows * ((kind == 0 || kind == 2) ? 1 : 3), xn);
+}
+
 template <int NS, int NV, int KS, bool SPLIT>
 __global__ void __launch_bounds__(N_THREADS, 1)
 tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
@@ -376,7 +407,7 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
     int *cum = reinterpret_cast<int *>(tile_off + C::MAX_TILES + 1);    // [MAX_TILES + 1] MMA cost prefix (set-up only)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_jobs = jobs.n, f_out = jobs.f_out;
+    const int n_jobs = jobs.n, f_in = jobs.f_in, f_out = jobs.f_out;
     const Header *hdr = reinterpret_cast<const Header *>(jobs.job[0].image);
     const int n_tiles = hdr->n_tiles;
 
@@ -566,11 +597,13 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                     stage = ns_; phase = np_;
                 }
                 trace_ev(jobs.trace, 0, titer, 3);
+#ifdef DDP_UMMA_TRACE
                 if (jobs.trace != nullptr && blockIdx.x == 0 && titer < TRACE_TILES) {
                     unsigned long long ns_now;
                     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_now));
                     jobs.trace[(0 * TRACE_TILES + titer) * TRACE_EVENTS + 4] = (long long)ns_now;
                 }
+#endif
             }
         }
     } else if (warp >= 6) {
@@ -684,10 +717,7 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
             // node features of weight tile 0 (registers; every tile prefetches the next one's)
             float xn[C::XN];
             uint4 tdw = *reinterpret_cast<const uint4 *>(&tiles[t0]);
-            {
-                const int kind = (int)((tdw.x >> 16) & 0xffu), n_rows = (int)(tdw.x >> 24);
-                x_prefetch<C::XN>(xg + (tdw.z & 0xffffu), n_rows * ((kind == 0 || kind == 2) ? 1 : 3), xn);
-            }
+            x_prefetch_tile<NS, NV, C::ROWS_S, C::XN>(xg, tdw, f_in, xn);
 
             // ---- GEMM1 result -> ReLU -> hidden activations become the A operand of GEMM2 ----
             // TS: packed bf16 pairs into tensor memory (column c of the lane = k 2c, 2c + 1); SS (split mode): hi / lo
@@ -772,8 +802,7 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                     }
                     if (tt + 1 < nt) {
                         tdw = *reinterpret_cast<const uint4 *>(&tiles[t + 1]);
-                        const int k2 = (int)((tdw.x >> 16) & 0xffu), nr2 = (int)(tdw.x >> 24);
-                        x_prefetch<C::XN>(xg + (tdw.z & 0xffffu), nr2 * ((k2 == 0 || k2 == 2) ? 1 : 3), xn);
+                        x_prefetch_tile<NS, NV, C::ROWS_S, C::XN>(xg, tdw, f_in, xn);
                     }
                     if (r == 0) trace_ev(jobs.trace, 1, titer, 0);
                     mbar_wait(&tmem_full[buf], (tf_phase >> buf) & 1u);
@@ -849,8 +878,7 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                             // the last basis rows are in registers: fetch the next tile's node features
                             if (tt + 1 < nt) {
                                 tdw = *reinterpret_cast<const uint4 *>(&tiles[t + 1]);
-                                const int k2 = (int)((tdw.x >> 16) & 0xffu), nr2 = (int)(tdw.x >> 24);
-                                x_prefetch<C::XN>(xg + (tdw.z & 0xffffu), nr2 * ((k2 == 0 || k2 == 2) ? 1 : 3), xn);
+                                x_prefetch_tile<NS, NV, C::ROWS_S, C::XN>(xg, tdw, f_in, xn);
                             }
                         }
                         const uint32_t tp = taddr + (uint32_t)(pass * C::PASS_COLS);
@@ -1092,8 +1120,13 @@ static int launch_umma(const umma::Jobs &jobs, int tiles_cap, cudaStream_t st) {
 
 static long long *g_umma_trace = nullptr;
 extern "C" int ddp_tpconv_umma_set_trace(void *trace_dev) {
+#ifdef DDP_UMMA_TRACE
     g_umma_trace = static_cast<long long *>(trace_dev);
     return 2 * umma::TRACE_TILES * umma::TRACE_EVENTS;      // int64 slots the buffer must hold
+#else
+    (void)trace_dev;
+    return DDP_E_UNSUPPORTED;                               // library built without -DDDP_UMMA_TRACE
+#endif
 }
 
 extern "C" int ddp_tpconv_umma_group(const ddp_tpconv_t *const *convs, const void *const *packed, int32_t mode,

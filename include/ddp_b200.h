@@ -196,7 +196,8 @@ int ddp_tpconv_umma_group(const ddp_tpconv_t *const *convs, const void *const *p
 
 /* Developer aid: when trace_dev != NULL, CTA 0 of every following tensor-core conv launch records clock64()
  * timestamps of its MMA-issue and epilogue roles per weight tile into trace_dev (device int64 buffer); NULL turns
- * it off.  Returns the number of int64 slots the buffer must hold.  Not part of the reference surface. */
+ * it off.  Returns the number of int64 slots the buffer must hold, or DDP_E_UNSUPPORTED when the library was built
+ * without -DDDP_UMMA_TRACE (the default: the hooks cost epilogue instructions).  Not part of the reference surface. */
 int ddp_tpconv_umma_set_trace(void *trace_dev);
 
 /* node update (all_atom_score_model.py:315-324 + scatter-mean + e3nn BatchNorm eval, score_model.py:117,123):

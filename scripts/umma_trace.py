@@ -1,5 +1,8 @@
 """Per-tile timeline of CTA 0 of the grouped layer-3 conv launch (MMA-issue warp vs epilogue warp 0), from the
-clock64 trace hooks of the UMMA kernel.  python scripts/umma_trace.py > gpurun_out/trace.txt"""
+clock64 trace hooks of the UMMA kernel.  The hooks are compiled out of the product library; build a traced copy first
+(here, no GPU needed) and point DDP_LIB at it on the GPU box:
+  DDP_NVCC_FLAGS=-DDDP_UMMA_TRACE DDP_LIB=$PWD/scripts/micro/libddp_trace.so python -c "from diffdock_pocket_b200 import _lib; _lib.build()"
+  DDP_LIB=$PWD/scripts/micro/libddp_trace.so python scripts/umma_trace.py > gpurun_out/trace.txt"""
 import copy
 import os
 import sys
@@ -28,6 +31,7 @@ with torch.no_grad():
     model.run_plan(pl, ct)
     torch.cuda.synchronize()
     slots = L.ddp_tpconv_umma_set_trace(None)
+    assert slots > 0, 'library built without -DDDP_UMMA_TRACE (see the module docstring)'
     buf = torch.zeros(slots, dtype=torch.int64, device=dev)
     # trace only the 4th grouped launch (layer 3): enable, run forward with a hook counting launches
     orig = L.ddp_tpconv_umma_group
