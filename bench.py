@@ -50,6 +50,7 @@ def parse():
     p.add_argument('--cpu-samples', type=int, default=2)
     p.add_argument('--cpu-steps', type=int, default=2)
     p.add_argument('--no-cpu-baseline', action='store_true')
+    p.add_argument('--single-stream', action='store_true', help='run the mini-batches back to back on one stream (A/B of the two-stream overlap)')
     p.add_argument('--no-graph', action='store_true', help='launch kernels eagerly instead of replaying the captured step graph')
     return p.parse_args()
 
@@ -190,14 +191,17 @@ def main():
     # ---- e2e pass through the public API (host graphs in, host poses out) --------------------------------
     def e2e_step(dl):
         torch.manual_seed(7)
-        out, c = ps.sampling(dl, model, args.inference_steps, sch, sch, sch, sch, dev, t2s, sa, **kw)
+        out, c = ps.sampling(dl, model, args.inference_steps, sch, sch, sch, sch, dev, t2s, sa, concurrent_batches=not args.single_stream, **kw)
         poses = torch.stack([o['ligand'].pos for o in out]).to(dev)
         return gather_rank(poses, c.reshape(-1).to(dev)).cpu()
 
     # ---- resident pass: plans + pose states (+ captured step graphs) built once, inputs already in HBM ----------
     chunks = [list(range(i, min(i + args.batch_size, args.samples))) for i in range(0, args.samples, args.batch_size)]
+    # independent mini-batches alternate between two streams, exactly as sampling() runs them
+    streams = [torch.cuda.Stream(device=dev) for _ in range(2)] if len(chunks) > 1 and not args.single_stream else [None]
     with torch.no_grad():
-        runners = [ps.StepRunner(model, [dl0[i] for i in idx], True, False, use_graph=not args.no_graph) for idx in chunks]
+        runners = [ps.StepRunner(model, [dl0[i] for i in idx], True, False, use_graph=not args.no_graph, stream=streams[k % len(streams)])
+                   for k, idx in enumerate(chunks)]
         cplans = [conf.make_plan(Batch.from_data_list([dl0[i] for i in idx])) for idx in chunks]
     plans = [r.pl for r in runners]
     init = [(pl.lig_pos.clone(), pl.atom_pos.clone()) for pl in plans]
@@ -212,6 +216,8 @@ def main():
             for pl, (lp, ap) in zip(plans, init):
                 pl.lig_pos.copy_(lp)
                 pl.atom_pos.copy_(ap)
+            for r in runners:
+                r.sync_in()
             for t_idx in range(args.inference_steps):
                 t, coef = coefs[t_idx]
                 z = noise[t_idx]
@@ -223,11 +229,14 @@ def main():
                     r.step(t, coef, row)
                     s0, t0, c0 = s0 + b, t0 + r.T, c0 + r.S
             cs = []
-            for idx, pl, cpl in zip(chunks, plans, cplans):
-                cpl.lig_pos.copy_(pl.lig_pos)
-                cpl.atom_pos.copy_(pl.atom_pos)
-                zt = torch.zeros(len(idx))
-                cs.append(conf.run_plan(cpl, {'tr': zt, 'rot': zt, 'tor': zt, 'sc_tor': zt}).reshape(-1).clone())
+            for idx, r, cpl in zip(chunks, runners, cplans):
+                with r.ctx():
+                    cpl.lig_pos.copy_(r.pl.lig_pos)
+                    cpl.atom_pos.copy_(r.pl.atom_pos)
+                    zt = torch.zeros(len(idx))
+                    cs.append(conf.run_plan(cpl, {'tr': zt, 'rot': zt, 'tor': zt, 'sc_tor': zt}).reshape(-1).clone())
+            for r in runners:
+                r.sync_out()
             return gather_rank(torch.cat([pl.lig_pos for pl in plans]).reshape(N, -1, 3), torch.cat(cs))
 
     # gpu_launches: kernels of ONE bench step, counted on an eager (non-graph) pass of identical work
@@ -317,7 +326,7 @@ def main():
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': {'bf16': 'bf16', 'bf16x3': 'bf16x3 (fp32-grade)', 'fp32': 'f32'}[args.mode], 'data': 'synthetic',
             'config': {'workload': f'{args.workload}: {args.samples} samples, batch {args.batch_size}, {args.inference_steps} reverse-diffusion steps + confidence pass, per GPU (BASELINE.json configs[1])',
-                       'weights': 'random init of the README big score model (ns=60 nv=10 6 layers lmax=1) + confidence model (no checkpoint offline)', 'conv_mode': args.mode,
+                       'weights': 'random init of the README big score model (ns=60 nv=10 6 layers lmax=1) + confidence model (no checkpoint offline)', 'conv_mode': args.mode, 'streams': len(streams),
                        'l2': 'weights + activations (>400 MB) exceed L2; 256 MiB flush between timed iterations'},
             'clocks': sampler.summary(), 'gpu_launches': launches,
             'e2e': {'value': world * args.samples / (e2e_ms / 1000.0), 'unit': 'poses/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},

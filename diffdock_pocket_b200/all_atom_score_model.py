@@ -545,9 +545,14 @@ class TensorProductScoreModel(nn.Module):
         return self.launch_plan(pl, return_layers)
 
     def _branches(self, device):
-        if getattr(self, '_br', None) is None or self._br_dev != device:
-            self._br, self._br_dev = _Branches(device), device
-        return self._br
+        """Side streams of the launching stream (one set per stream, so that forwards issued on different streams --
+        the sampler's concurrent mini-batches -- do not serialise on shared side streams)."""
+        if getattr(self, '_br', None) is None:
+            self._br = {}
+        key = (str(device), torch.cuda.current_stream().cuda_stream)
+        if key not in self._br:
+            self._br[key] = _Branches(device)
+        return self._br[key]
 
     def launch_plan(self, pl, return_layers=False):
         """Kernel launches only (per-graph scalars already staged in ``pl.scal``): CUDA-graph capturable."""

@@ -164,8 +164,8 @@ class Batch(HeteroData):
                     node_types.append(t)
         offsets: Dict[str, List[int]] = {}
         for t in node_types:
-            if any(t not in d._nodes for d in data_list):
-                continue
+            if any(t not in d._nodes or len(d._nodes[t]) == 0 for d in data_list):
+                continue                                   # absent, or an empty store left behind by data[t] look-ups
             st = Store()
             counts = [d._nodes[t].num_nodes for d in data_list]
             off = np.concatenate([[0], np.cumsum(counts)])

@@ -18,6 +18,7 @@ mini-batch, while at batch 20 the eager launch stream already runs ~4x ahead of 
 
 SVGD (svgd_weight > 0) and ``pivot`` are outside the accelerated path and raise NotImplementedError.
 """
+import contextlib
 import copy
 
 import numpy as np
@@ -104,9 +105,10 @@ class StepRunner:
     [per-graph scalars | 8 step coefficients | tr_z | rot_z | tor_z | sc_z], copies it to the device with one
     async H2D and replays the graph: no other host work, no synchronisation."""
 
-    def __init__(self, model, data_sub, flexible_sidechains, no_torsion, use_graph=True):
+    def __init__(self, model, data_sub, flexible_sidechains, no_torsion, use_graph=True, stream=None):
         b = len(data_sub)
         self.model, self.b = model, b
+        self.stream = stream                     # None: the caller's current stream
         n_tor = 0 if no_torsion else sum(int(g['ligand'].edge_mask.sum()) for g in data_sub)
         n_sc = sum(int(g['flexResidues'].edge_idx.shape[0]) for g in data_sub
                    if flexible_sidechains and 'flexResidues' in g and 'edge_idx' in g['flexResidues'])
@@ -147,7 +149,25 @@ class StepRunner:
             row[pl.n_scal + 8:] = noise_row
         pl.step_in.copy_(row, non_blocking=True)
 
+    def ctx(self):
+        """Context that makes this runner's stream current (mini-batches are independent through the whole loop, so
+        the sampler puts them on different streams: one mini-batch's graph-building front and pose-update tail, which
+        cannot fill the GPU, overlap the other's convolutions)."""
+        return torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()
+
+    def sync_in(self):
+        if self.stream is not None:
+            self.stream.wait_stream(torch.cuda.current_stream())
+
+    def sync_out(self):
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+
     def step(self, t4, coef, noise_row=None):
+        with self.ctx():
+            return self._step(t4, coef, noise_row)
+
+    def _step(self, t4, coef, noise_row):
         self.stage(t4, coef, noise_row)
         self.calls += 1
         if not self.use_graph or self.calls == 1:
@@ -166,7 +186,7 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
              t_schedule=None, batch_size=32, no_final_step_noise=False, pivot=None, return_full_trajectory=False,
              svgd_weight=0.0, svgd_repulsive_weight=1.0, svgd_only=False, svgd_rot_rel_weight=1.0, svgd_tor_rel_weight=1.0,
              svgd_sidechain_tor_rel_weight=1.0, temp_sampling=1.0, temp_psi=0.0, temp_sigma_data=0.5,
-             flexible_sidechains=None, max_steps=None, trace=None, use_graph=False):
+             flexible_sidechains=None, max_steps=None, trace=None, use_graph=False, concurrent_batches=True):
     if svgd_weight > 0 or pivot is not None or asyncronous_noise_schedule:
         raise NotImplementedError('SVGD / pivot / asynchronous schedules are outside the accelerated path')
     flexible_sidechains = model_args.flexible_sidechains if flexible_sidechains is None else flexible_sidechains
@@ -188,6 +208,11 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
     chunks = [list(range(i, min(i + batch_size, N))) for i in range(0, N, batch_size)]
     use_graph = bool(use_graph) and trace is None
     runners = [None] * len(chunks)
+    # independent mini-batches alternate between two streams (see StepRunner.ctx); host-visible intermediates
+    # (trace, trajectories, visualisation) keep the single-stream order
+    single = len(chunks) < 2 or trace is not None or return_full_trajectory or visualization_list is not None \
+        or sidechain_visualization_list is not None or not concurrent_batches
+    streams = [None] if single else [torch.cuda.Stream(device=device) for _ in range(2)]
     n_tor = [0 if ma.no_torsion else sum(int(data_list[i]['ligand'].edge_mask.sum()) for i in idx) for idx in chunks]
     n_sc = [sum(int(data_list[i]['flexResidues'].edge_idx.shape[0]) for i in idx
                 if flexible_sidechains and 'flexResidues' in data_list[i] and 'edge_idx' in data_list[i]['flexResidues'])
@@ -231,8 +256,10 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
             step_scores = []
             for k, idx in enumerate(chunks):
                 if runners[k] is None:
-                    runners[k] = StepRunner(model, [data_list[i] for i in idx], flexible_sidechains, ma.no_torsion, use_graph=use_graph)
+                    runners[k] = StepRunner(model, [data_list[i] for i in idx], flexible_sidechains, ma.no_torsion, use_graph=use_graph,
+                                            stream=streams[k % len(streams)])
                     assert (runners[k].T, runners[k].S) == (n_tor[k], n_sc[k])
+                    runners[k].sync_in()                              # plan + pose state were uploaded on the caller's stream
                 r = runners[k]
                 b = len(idx)
                 row = torch.cat([z[3 * s0:3 * (s0 + b)], z[3 * N + 3 * s0:3 * N + 3 * (s0 + b)], z[6 * N + t0:6 * N + t0 + r.T],
@@ -263,14 +290,26 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
                 conf_plans = [confidence_model.make_plan(Batch.from_data_list(
                     [(filtering_data_list if filtering_data_list is not None else data_list)[i] for i in idx])) for idx in chunks]
             conf = []
+            cur = torch.cuda.current_stream()
             for idx, r, cpl in zip(chunks, runners, conf_plans):
-                if r is not None:
+                zt = torch.zeros(len(idx))
+                if r is None:
+                    conf.append(confidence_model.run_plan(cpl, {'tr': zt, 'rot': zt, 'tor': zt, 'sc_tor': zt}).clone())
+                    continue
+                r.sync_in()                                           # the confidence plans were uploaded on the caller's stream
+                with r.ctx():
                     cpl.lig_pos.copy_(r.pl.lig_pos)
                     if filtering_data_list is None:                   # filtering graphs keep their own receptor atoms
                         cpl.atom_pos.copy_(r.pl.atom_pos)
-                zt = torch.zeros(len(idx))
-                conf.append(confidence_model.run_plan(cpl, {'tr': zt, 'rot': zt, 'tor': zt, 'sc_tor': zt}).clone())
+                    conf.append(confidence_model.run_plan(cpl, {'tr': zt, 'rot': zt, 'tor': zt, 'sc_tor': zt}).clone())
+                    conf[-1].record_stream(cur)
+            for r in runners:
+                if r is not None:
+                    r.sync_out()
             confidence = torch.cat(conf, dim=0)
+        for r in runners:
+            if r is not None:
+                r.sync_out()
         write_back_all()                                              # the one device->host read of the poses
         if filtering_data_list is not None:
             for i, g in enumerate(filtering_data_list):

@@ -258,3 +258,53 @@ def test_forward_sh_lmax2_model_vs_oracle():
         assert T.rel_err(gl, wl) < 1e-4 and T.rel_err(ga[:, :wa.shape[1]], wa) < 1e-4, l
     for a, w, key in zip(got, want, ('tr', 'rot', 'tor', 'sc')):
         assert a.numel() > 0 and T.rel_err(a, w) < 1e-4, (key, T.rel_err(a, w))
+
+
+def test_rigid_ligand_without_flexible_residues():
+    """No rotatable bond and no flexible residue: tor / sc scores are empty tensors (all_atom_score_model.py:386-387,
+    410-411), the sampler still moves the ligand rigidly and matches the oracle."""
+    m, c, om, oc, sa, ca = T.models(DEV, small=True)
+    g = inputs.synthetic_complex(21, n_lig=3, n_res=30, flexible_residues=0)
+    assert int(g['ligand'].edge_mask.sum()) == 0 and 'flexResidues' not in g
+    dl = T.randomized_list(g, 3, sa, seed=1)
+    b = T.batch_at(dl, 0.4)
+    m.conv_mode = 'fp32'
+    with torch.no_grad():
+        got = m(copy.deepcopy(b))
+        want = om(copy.deepcopy(b))
+    assert got[2].numel() == 0 and got[3].numel() == 0 and want[2].numel() == 0 and want[3].numel() == 0
+    assert T.rel_err(got[0], want[0]) < 1e-4 and T.rel_err(got[1], want[1]) < 1e-4
+    steps = 4
+    sch = D.get_t_schedule(steps)
+    torch.manual_seed(5)
+    ref, ref_conf = S.sampling(copy.deepcopy(dl), om, steps, sch, sch, sch, sch, partial(D.t_to_sigma, args=sa), sa,
+                               confidence_model=oc, batch_size=2)
+    torch.manual_seed(5)
+    out, conf = ps.sampling(copy.deepcopy(dl), m, steps, sch, sch, sch, sch, DEV, partial(du.t_to_sigma, args=sa), sa,
+                            confidence_model=c, filtering_model_args=ca, batch_size=2)
+    for a, r in zip(out, ref):
+        assert float(((a['ligand'].pos.cpu() - r['ligand'].pos) ** 2).sum(-1).mean().sqrt()) < 0.1
+        assert torch.equal(a['atom'].pos.cpu(), r['atom'].pos)                  # nothing flexible: receptor atoms untouched
+    assert T.rel_err(conf, ref_conf) < 1e-2
+
+
+def test_forward_batch64_equals_sub_batches():
+    """BASELINE.json configs[2] shape (64 pocket graphs, big model, t = 1 so every ligand-residue pair is an edge):
+    too large for the oracle, so the check is size-independent -- the 64-graph forward equals four 16-graph forwards."""
+    m, c, om, oc, sa, ca = T.models(DEV)
+    dl = T.randomized_list(T.graph('3dpf_apo'), 64, sa, seed=9)
+    m.conv_mode = 'bf16'
+    try:
+        with torch.no_grad():
+            b = T.batch_at(dl, 1.0)
+            pl = m.make_plan(copy.deepcopy(b))
+            full = [x.clone() for x in m.run_plan(pl, b.complex_t)]
+            assert int(pl.es['lr'].n_dev.item()) > 0.8 * 64 * dl[0]['ligand'].pos.shape[0] * dl[0]['receptor'].pos.shape[0]
+            parts = []
+            for k in range(0, 64, 16):
+                bb = T.batch_at(dl[k:k + 16], 1.0)
+                parts.append([x.clone() for x in m.run_plan(m.make_plan(copy.deepcopy(bb)), bb.complex_t)])
+    finally:
+        m.conv_mode = 'fp32'
+    for i in range(4):
+        assert T.rel_err(full[i], torch.cat([p[i] for p in parts])) < 1e-4, i
