@@ -12,8 +12,9 @@
 //              output in registers; vector red.global.add into the aggregation node at the end of each output block.
 //   warp 4     TMA producer: streams the pre-packed weight image (already in UMMA core-matrix order and in
 //              consumption order) slab by slab.
-//   warp 5     MMA issuer (one elected lane) + TMEM allocator.
-//   warps 6-7  gather: stage [emb | node scalars] of the NEXT edge tile as the bf16 A operand (double buffered),
+//   warps 5, 7 MMA issuers (one elected lane each), one per TMEM accumulator, so that one of them is always parked on
+//              the tensor pipe's queue while the other does its per-tile barrier work; warp 5 also allocates TMEM.
+//   warp 6     gather: stage [emb | node scalars] of the NEXT edge tile as the bf16 A operand (double buffered),
 //              so the gather latency hides under the current tile's GEMM2.
 //
 // Biases ride in the GEMMs: A has a constant-one column (padding slot of the first 64-wide source block)
@@ -77,6 +78,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// Debug build (-DDDP_UMMA_WATCHDOG, with -DDDP_UMMA_TRACE): a wait that has polled ~2^18 times records
+// (code, a, b, barrier parity asked for) of its warp in the host-visible trace buffer, so a deadlock can be read
+// from the host while the kernel still hangs (scripts/umma_watchdog.py).
+#ifdef DDP_UMMA_WATCHDOG
+__device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, long long *trace, int code, int a, int b) {
+    uint32_t done = 0;
+    unsigned long long polls = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (!done && ++polls == (1ull << 18) && trace != nullptr && (threadIdx.x & 31) == 0) {
+            long long *rec = trace + ((size_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 4;
+            rec[0] = code; rec[1] = a; rec[2] = b; rec[3] = parity;
+            __threadfence_system();
+        }
+    }
+}
+#define DDP_WAIT(bar, par, code, a, b) mbar_wait_wd(bar, par, jobs.trace, code, a, b)
+#else
+#define DDP_WAIT(bar, par, code, a, b) mbar_wait(bar, par)
+#endif
 // Split-phase barrier test for the MMA issue loop: mbar_test_pN starts a non-blocking phase test whose predicate
 // lives in a PTX register declared once per kernel (DDP_DECLARE_TEST_PREDS); mbar_finish_pN consumes it later (falling
 // back to the blocking wait), so the ~100-cycle shared-memory round trip overlaps the tcgen05.mma issue in between.
@@ -250,6 +277,12 @@ __host__ __device__ constexpr int stage_k_of(int ks, bool split) { return ks == 
 #ifndef DDP_UMMA_TS
 #define DDP_UMMA_TS 0
 #endif
+#ifndef DDP_UMMA_DUAL
+#define DDP_UMMA_DUAL 1
+#endif
+#ifndef DDP_UMMA_TOKEN
+#define DDP_UMMA_TOKEN 1
+#endif
 __host__ __device__ constexpr bool use_ts(bool split) { return DDP_UMMA_TS != 0 && !split; }
 __host__ __device__ constexpr int rows_scalar(int ns, bool ts) { return (ts ? 192 : 240) / ns; }
 __host__ __device__ constexpr int ncol_scalar(int ns, bool ts) { return (rows_scalar(ns, ts) * ns + 15) / 16 * 16; }
@@ -257,7 +290,7 @@ __host__ __device__ constexpr int rows_vector(int nv) { return 2 * nv; }
 __host__ __device__ constexpr int ncol_vector(int nv, int n_rows) { return (n_rows * nv + 15) / 16 * 16; }
 
 constexpr int MAX_JOBS = 9;
-constexpr int N_EPI = 128, N_GATHER = 64, N_THREADS = 256;
+constexpr int N_EPI = 128, N_GATHER = 64, N_THREADS = 256;   // N_GATHER: arrivals that complete an a_ready phase
 
 // One fused convolution of a grouped launch.  All jobs of a launch share irreps (tile table, f_in, f_out).
 struct Job {
@@ -308,6 +341,7 @@ struct Cfg {
     static constexpr int STAGES_FIT = (220 * 1024 - FIXED) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_FIT > 12 ? 12 : STAGES_FIT;
     static constexpr size_t SMEM = (size_t)FIXED + (size_t)STAGES * STAGE_BYTES;
+    static constexpr bool DUAL = DDP_UMMA_DUAL != 0 && STAGES >= KP / STAGE_K + 1;   // two MMA issuers (see the issue loop)
     static constexpr int XN_RAW = 3 * NV > 3 * ROWS_S ? 3 * NV : 3 * ROWS_S;   // floats of x one tile reads (x (x) s1 tiles: 2 NV,
     static constexpr int XN = XN_RAW + (XN_RAW & 1);                              //  stride-3 kinds: NV or ROWS_S rows of 3)
     static_assert(N1 % 16 == 0 && NCOL_MAX <= ACC_STRIDE && (TS ? H_COL + KP / 2 : H_COL) <= 512, "UMMA N / TMEM budget");
@@ -386,6 +420,72 @@ __device__ __forceinline__ void x_prefetch_tile(const float *xg_row, const uint4
     else x_prefetch<XN>(xg, n_rows * ((kind == 0 || kind == 2) ? 1 : 3), xn);
 }
 
+// Stage ROWS rows per lane (row0 + lane + 32 h) of the A operand of edge tile `et`: [emb | p1 | p2] as bf16 (constant
+// one in slot NS of source 0), written in UMMA core-matrix order (hi image, plus the lo image in split mode).  The
+// index loads are issued before the wait for the buffer, the feature loads after it.
+template <int NS, int KS, bool SPLIT, int ROWS>
+__device__ __forceinline__ void gather_rows(const ddp_tpconv_edges_t &ed, int n_edges, int et, int row0, int lane, uint8_t *a_hi,
+                                            uint8_t *a_lo, uint64_t *free_bar, uint32_t free_parity) {
+    const float *srcs[ROWS][3];
+#pragma unroll
+    for (int h = 0; h < ROWS; ++h) {
+        const int e = et * TILE_M + row0 + lane + h * 32;
+        const bool valid = e < n_edges;
+        srcs[h][0] = valid ? ed.emb + (size_t)e * NS : nullptr;
+        srcs[h][1] = valid ? ed.p1 + (size_t)__ldg(ed.i1 + e) * ed.ld1 : nullptr;
+        srcs[h][2] = valid ? ed.p2 + (size_t)__ldg(ed.i2 + e) * ed.ld2 : nullptr;
+    }
+    mbar_wait(free_bar, free_parity);
+#pragma unroll
+    for (int h = 0; h < ROWS; ++h) {
+        const int r = row0 + lane + h * 32;
+        const uint32_t a_row_off = (uint32_t)((r >> 3) * 128 + (r & 7) * 16);
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            const float *sp = srcs[h][s];
+            const bool v4 = (s == 0) ? (NS % 4 == 0) : (((s == 1 ? ed.ld1 : ed.ld2) & 3) == 0);
+#pragma unroll
+            for (int c8 = 0; c8 < KS / 8; ++c8) {
+                float v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = 0.f;
+                if (sp != nullptr) {
+                    if (v4 && NS % 4 == 0) {
+                        if (c8 * 8 < NS) {
+                            const float4 f = __ldg(reinterpret_cast<const float4 *>(sp + c8 * 8));
+                            v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+                        }
+                        if (c8 * 8 + 4 < NS) {
+                            const float4 f = __ldg(reinterpret_cast<const float4 *>(sp + c8 * 8 + 4));
+                            v[4] = f.x; v[5] = f.y; v[6] = f.z; v[7] = f.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            if (c8 * 8 + q < NS) v[q] = __ldg(sp + c8 * 8 + q);
+                    }
+                }
+                if (s == 0 && NS / 8 == c8) v[NS % 8] = 1.f;
+                uint4 hi;
+                hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
+                hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
+                const uint32_t off = (uint32_t)((s * (KS / 8) + c8) * (TILE_M * 16)) + a_row_off;
+                *reinterpret_cast<uint4 *>(a_hi + off) = hi;
+                if (SPLIT) {
+                    float w[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) w[q] = v[q] - __bfloat162float(__float2bfloat16_rn(v[q]));
+                    uint4 lo;
+                    lo.x = pack_bf16x2(w[0], w[1]); lo.y = pack_bf16x2(w[2], w[3]);
+                    lo.z = pack_bf16x2(w[4], w[5]); lo.w = pack_bf16x2(w[6], w[7]);
+                    *reinterpret_cast<uint4 *>(a_lo + off) = lo;
+                }
+            }
+        }
+    }
+    fence_proxy_async();
+}
+
 template <int NS, int NV, int KS, bool SPLIT>
 __global__ void __launch_bounds__(N_THREADS, 1)
 tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
@@ -400,7 +500,8 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
     uint64_t *full = bars, *empty = bars + C::STAGES;
     uint64_t *tmem_full = bars + 2 * C::STAGES, *tmem_empty = tmem_full + 2;
     uint64_t *a_ready = tmem_empty + 2, *a_free = a_ready + 2, *h_ready = a_free + 2;
-    uint32_t *tmem_base_smem = reinterpret_cast<uint32_t *>(h_ready + 1);
+    uint64_t *tok = h_ready + 1;                                        // [2] issue-order token of the two MMA issuers
+    uint32_t *tmem_base_smem = reinterpret_cast<uint32_t *>(tok + 2);
     int *pref = reinterpret_cast<int *>(tmem_base_smem + 2);            // [MAX_JOBS + 1]
     Work *work = reinterpret_cast<Work *>(pref + MAX_JOBS + 1);
     uint32_t *tile_off = reinterpret_cast<uint32_t *>(work + 1);        // [MAX_TILES + 1] byte offset of every tile's slabs
@@ -417,9 +518,10 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], N_EPI);
-            mbar_init(&a_ready[b], N_GATHER); mbar_init(&a_free[b], 1);
+            mbar_init(&a_ready[b], N_GATHER); mbar_init(&a_free[b], (C::TS || !C::DUAL) ? 1 : 2);
         }
         mbar_init(h_ready, N_EPI);
+        mbar_init(&tok[0], 1); mbar_init(&tok[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // tile counts of the jobs: one thread per job fetches its live edge count (independent loads), warp 7 scans them
@@ -471,6 +573,15 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
     const Work &wk = *work;
     const int n_items = wk.n_items;
 
+    if (C::DUAL && warp == 7 && (int)blockIdx.x < n_items) {
+        // rows 64..127 of the CTA's first edge tile (then this warp turns MMA issuer)
+        int g, t0, t1, job, et;
+        work_item(wk, blockIdx.x, n_tiles, g, t0, t1);
+        locate(pref, n_jobs, g, job, et);
+        const ddp_tpconv_edges_t &ed = jobs.job[job].ed;
+        gather_rows<NS, KS, SPLIT, 2>(ed, min(*ed.n_edges_dev, ed.edge_cap), et, 64, lane, a_base, a_base + C::A_BYTES, &a_free[0], 1u);
+        mbar_arrive(&a_ready[0]);
+    }
     if (warp == 4) {
         // =============================== TMA producer (warp-uniform, one elected lane issues) =====
         uint32_t stage = 0, phase = 0;
@@ -486,7 +597,7 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                 const uint32_t bytes = slab_bytes(ncol, C::STAGE_K, SPLIT);
 #pragma unroll 1
                 for (int ks = 0; ks < C::KP / C::STAGE_K; ++ks) {
-                    mbar_wait(&empty[stage], phase ^ 1);
+                    DDP_WAIT(&empty[stage], phase ^ 1, 1, w, tt * 8 + ks);
                     if (elect_one()) {
                         mbar_expect_tx(&full[stage], bytes);
                         bulk_g2s(ring + (size_t)stage * C::STAGE_BYTES, src, bytes, &full[stage]);
@@ -497,17 +608,25 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                 }
             }
         }
-    } else if (warp == 5) {
-        // =============================== MMA issuer (warp-uniform, one elected lane issues) =======
-        // The tensor pipe queues only ~1 MMA beyond the one executing and tcgen05.mma issue blocks while it is full, so
-        // anything between two issues longer than one MMA (~100 cycles) drains it.  Barrier round trips are therefore
-        // split-phase: the test for the NEXT K group's slab (p0), the next tile's accumulator (p1) and the next edge
-        // tile's A operand (p2) start before the current group is issued and are consumed after it.
+    } else if (warp == 5 || (warp == 7 && C::DUAL)) {
+        // =============================== MMA issuers (warp-uniform, one elected lane issues) ======
+        // Two issuers, one per accumulator: warp 5 owns accumulator 0 (GEMM1 and the odd weight tiles), warp 7
+        // accumulator 1 (the even weight tiles).  tcgen05.mma issue blocks while the tensor pipe's short queue is
+        // full, so a single issuer exposes everything it does between two tiles (barrier round trips, descriptor
+        // set-up: ~270 cycles per 1450-cycle tile in profiles/r1_umma_timeline_cta0_layer3_v17.txt); with two, one is
+        // already parked on the queue with its next tile while the other finishes the current one.  Tiles of the two
+        // accumulators are independent, so the order in which the pipe interleaves them does not matter; every slab
+        // stage, accumulator and barrier phase has exactly one owner.  Inside a tile the test of the next K group's
+        // slab is split-phase (started before the group is issued, consumed after it).
+        // (Configurations whose ring is shorter than one tile's slabs + 1 keep a single issuer: an issuer that skips a
+        // whole foreign tile could otherwise wait on a slab whose slot is still two fills behind -- parity aliasing.)
         DDP_DECLARE_TEST_PREDS();
+        const uint32_t me = warp == 5 ? 0u : 1u;
         uint32_t stage = 0, phase = 0;
         uint32_t te_phase = 0;               // bit b: parity to wait on tmem_empty[b]
         uint32_t hr_phase = 0;
-        bool pre_a = false, pre_te = false, pre_full = false;   // waits of the upcoming tile / group already taken
+        uint32_t tok_phase = 0;              // parity of the other issuer's next "tile issued" token
+        int tok_pending = 0;                 // foreign tiles skipped since this issuer's last tile
         int it = 0;
         constexpr int NG = C::KP / C::STAGE_K;
         int titer = 0;
@@ -516,52 +635,53 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
             work_item(wk, w, n_tiles, g, t0, t1);
             const int nt = t1 - t0;
             const int ab = it % C::NBUF;
-            const bool more = w + (int)gridDim.x < n_items;
             const uint32_t a_hi_addr = smem_u32(a_base + (size_t)ab * C::A_BYTES * (SPLIT ? 2 : 1));
             // descriptor low words: A has LBO = 128 rows x 16 B between the two K chunks of one MMA
             const uint32_t a_hi_lo = ((a_hi_addr >> 4) & 0x3FFFu) | ((uint32_t)(TILE_M * 16 >> 4) << 16);
             const uint32_t a_lo_lo = (((a_hi_addr + C::A_BYTES) >> 4) & 0x3FFFu) | ((uint32_t)(TILE_M * 16 >> 4) << 16);
             for (int tt = -1; tt < nt; ++tt, ++titer) {
+                const uint32_t buf = (uint32_t)(tt + 1) & 1u;
+                if (C::DUAL && buf != me) {                              // the other issuer's tile: only the ring position moves
+#pragma unroll
+                    for (int ks = 0; ks < NG; ++ks)
+                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    ++tok_pending;
+                    continue;
+                }
                 const int t = tt < 0 ? -1 : t0 + tt;                     // weight tile (-1: GEMM1)
                 const uint32_t ncol = (t < 0) ? (uint32_t)C::N1 : (uint32_t)tiles[t].n_cols;
-                const uint32_t buf = (uint32_t)(tt + 1) & 1u;
-                trace_ev(jobs.trace, 0, titer, 0);
-                if (t < 0 && !pre_a) mbar_wait(&a_ready[ab], (uint32_t)(it / C::NBUF) & 1u);
-                if (tt == 0) { mbar_wait(h_ready, hr_phase); hr_phase ^= 1; }
-                if (!pre_te) {
-                    mbar_wait(&tmem_empty[buf], ((te_phase >> buf) & 1u) ^ 1u);
-                    te_phase ^= 1u << buf;
-                }
-                if (!pre_full) mbar_wait(&full[stage], phase);
-                tc_fence_after();
-                trace_ev(jobs.trace, 0, titer, 1);
                 const uint32_t d_tmem = tmem_base + buf * (uint32_t)C::ACC_STRIDE;
                 const uint32_t idesc = instr_desc((int)ncol);
                 // B: LBO = ncol rows x 16 B; one K = 16 step advances the start address by 2 * LBO
                 const uint32_t b_lbo_word = ncol << 16;
                 const uint32_t b_step = 2u * ncol;                      // (2 * ncol * 16 B) >> 4
                 const bool ts = C::TS && t >= 0;                        // GEMM2 reads the hidden activations from TMEM
-                // what may be taken early for the tile after this one (never anything that needs THIS tile's MMAs to
-                // complete: tile 0's h_ready; the accumulator this tile writes; in SS mode the A buffer)
-                const bool wrap = tt + 1 == nt;
-                const bool nx_any = tt != -1 && (!wrap || more);
-                const bool nx_a = nx_any && wrap && (C::TS || C::NBUF == 2);
-                const uint32_t nbuf = wrap ? 0u : (uint32_t)(tt + 2) & 1u;
-                const bool nx_te = nx_any && nbuf != buf;
-                const uint32_t nte_par = ((te_phase >> nbuf) & 1u) ^ 1u;
-                const uint32_t na_par = (uint32_t)((it + 1) / C::NBUF) & 1u;
+                // the A buffer is free once its last reader has run: GEMM1 (TS) / both issuers' last tiles (SS)
+                const bool last_reader = C::TS ? tt < 0 : tt + (C::DUAL ? 2 : 1) >= nt;
+                trace_ev(jobs.trace, 0, titer, 0);
+                if (tt < 0) DDP_WAIT(&a_ready[ab], (uint32_t)(it / C::NBUF) & 1u, 2, it, tt);
+                if (tt == 0) { DDP_WAIT(h_ready, hr_phase, 3, it, tt); hr_phase ^= 1; }
+                DDP_WAIT(&tmem_empty[buf], ((te_phase >> buf) & 1u) ^ 1u, 4, it, tt);
+                te_phase ^= 1u << buf;
+                DDP_WAIT(&full[stage], phase, 5, it, tt * 16 + (int)stage);
+                if (C::DUAL && DDP_UMMA_TOKEN) {
+                    // tiles are issued in tile order: everything above overlapped the other issuer's tile, only the
+                    // first tcgen05.mma waits for its last one
+                    // (one token per run of the other issuer's tiles: warp 5 owns the last tile of an even-length item and
+                    // the next item's GEMM1 back to back and signals only after the second)
+                    if (tok_pending > 0) { DDP_WAIT(&tok[me ^ 1u], tok_phase, 6, it, tt); tok_phase ^= 1u; tok_pending = 0; }
+                }
+                tc_fence_after();
+                trace_ev(jobs.trace, 0, titer, 1);
+                trace_ev(jobs.trace, 0, titer, 2);
 #pragma unroll
                 for (int ks = 0; ks < NG; ++ks) {
                     // the slab of this group has landed (blocking wait above, or the finish of the previous group)
                     uint32_t ns_ = stage + 1, np_ = phase;
                     if (ns_ == C::STAGES) { ns_ = 0; np_ ^= 1; }
-                    const bool nx_full = ks + 1 < NG || nx_any;          // is there a next group whose slab we may test?
-                    if (nx_full) mbar_test_p0(&full[ns_], np_);
-                    if (ks == NG - 1) {
-                        if (nx_te) mbar_test_p1(&tmem_empty[nbuf], nte_par);
-                        if (nx_a) mbar_test_p2(&a_ready[(it + 1) % C::NBUF], na_par);
-                    }
-                    if (ks == 0) trace_ev(jobs.trace, 0, titer, 2);
+#ifndef DDP_UMMA_WATCHDOG
+                    if (ks + 1 < NG) mbar_test_p0(&full[ns_], np_);
+#endif
                     const uint32_t b_addr = smem_u32(ring + (size_t)stage * C::STAGE_BYTES);
                     const uint32_t b_lo0 = ((b_addr >> 4) & 0x3FFFu) | b_lbo_word;
                     const uint32_t a_k = (uint32_t)(ks * (C::STAGE_K / 8)) * (uint32_t)(TILE_M * 16 >> 4);
@@ -582,35 +702,27 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                         umma_commit(&empty[stage]);
                         if (ks == NG - 1) {
                             umma_commit(&tmem_full[buf]);
-                            // the smem A buffer is free once its last reader has run: GEMM1 (TS) / the last GEMM2 tile (SS)
-                            if (C::TS ? tt < 0 : tt == nt - 1) umma_commit(&a_free[ab]);
+                            if (last_reader) umma_commit(&a_free[ab]);
+                            if (C::DUAL && DDP_UMMA_TOKEN && !(me == 0 && tt == nt - 1)) mbar_arrive(&tok[me]);
                         }
                     }
                     __syncwarp();
-                    if (nx_full) mbar_finish_p0(&full[ns_], np_);
-                    if (ks == NG - 1) {
-                        if (nx_te) { mbar_finish_p1(&tmem_empty[nbuf], nte_par); te_phase ^= 1u << nbuf; }
-                        if (nx_a) mbar_finish_p2(&a_ready[(it + 1) % C::NBUF], na_par);
-                        pre_full = nx_full; pre_te = nx_te; pre_a = nx_a;
-                    }
-                    tc_fence_after();
+#ifndef DDP_UMMA_WATCHDOG
+                    if (ks + 1 < NG) { mbar_finish_p0(&full[ns_], np_); tc_fence_after(); }
+#else
+                    if (ks + 1 < NG) { DDP_WAIT(&full[ns_], np_, 11, it, tt * 16 + (int)ns_); tc_fence_after(); }
+#endif
                     stage = ns_; phase = np_;
                 }
                 trace_ev(jobs.trace, 0, titer, 3);
-#ifdef DDP_UMMA_TRACE
-                if (jobs.trace != nullptr && blockIdx.x == 0 && titer < TRACE_TILES) {
-                    unsigned long long ns_now;
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_now));
-                    jobs.trace[(0 * TRACE_TILES + titer) * TRACE_EVENTS + 4] = (long long)ns_now;
-                }
-#endif
             }
         }
-    } else if (warp >= 6) {
-        // =============================== gather warps: A operand of the NEXT edge tile ==============
-        // [emb | p1 | p2] as bf16 (constant one in slot NS of source 0), two rows per thread, written in UMMA
-        // core-matrix order while the tensor cores still work on the previous tile.
-        const int gt = threadIdx.x - 6 * 32;
+    } else if (warp == 6 || (warp == 7 && !C::DUAL)) {
+        // =============================== gather: A operand of the NEXT edge tile ===================
+        // Two-issuer configurations: warp 6 stages all 128 rows of every edge tile (four per lane) except the CTA's
+        // first one, where warp 7 -- idle as an issuer until the first hidden activations exist -- has taken rows
+        // 64..127 (see above) so that the launch does not start with a single warp's gather latency.  Single-issuer
+        // configurations: warps 6 and 7 stage 64 rows each.  a_ready counts 64 arrivals either way.
         int it = 0;
         for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
             int g, t0, t1, job, et;
@@ -621,64 +733,13 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
             const int ab = it % C::NBUF;
             uint8_t *a_hi = a_base + (size_t)ab * C::A_BYTES * (SPLIT ? 2 : 1);
             uint8_t *a_lo = a_hi + C::A_BYTES;
-            const float *srcs[2][3];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int e = et * TILE_M + gt + h * N_GATHER;
-                const bool valid = e < n_edges;
-                srcs[h][0] = valid ? ed.emb + (size_t)e * NS : nullptr;
-                srcs[h][1] = valid ? ed.p1 + (size_t)__ldg(ed.i1 + e) * ed.ld1 : nullptr;
-                srcs[h][2] = valid ? ed.p2 + (size_t)__ldg(ed.i2 + e) * ed.ld2 : nullptr;
+            const uint32_t fpar = ((uint32_t)(it / C::NBUF) & 1u) ^ 1u;
+            if (C::DUAL && it > 0) {
+                gather_rows<NS, KS, SPLIT, 4>(ed, n_edges, et, 0, lane, a_hi, a_lo, &a_free[ab], fpar);
+                mbar_arrive(&a_ready[ab]);
+            } else {
+                gather_rows<NS, KS, SPLIT, 2>(ed, n_edges, et, (warp - 6) * 64, lane, a_hi, a_lo, &a_free[ab], fpar);
             }
-            mbar_wait(&a_free[ab], ((uint32_t)(it / C::NBUF) & 1u) ^ 1u);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int r = gt + h * N_GATHER;
-                const uint32_t a_row_off = (uint32_t)((r >> 3) * 128 + (r & 7) * 16);
-#pragma unroll
-                for (int s = 0; s < 3; ++s) {
-                    const float *sp = srcs[h][s];
-                    const bool v4 = (s == 0) ? (NS % 4 == 0) : (((s == 1 ? ed.ld1 : ed.ld2) & 3) == 0);
-#pragma unroll
-                    for (int c8 = 0; c8 < KS / 8; ++c8) {
-                        float v[8];
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) v[q] = 0.f;
-                        if (sp != nullptr) {
-                            if (v4 && NS % 4 == 0) {
-                                if (c8 * 8 < NS) {
-                                    const float4 f = __ldg(reinterpret_cast<const float4 *>(sp + c8 * 8));
-                                    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
-                                }
-                                if (c8 * 8 + 4 < NS) {
-                                    const float4 f = __ldg(reinterpret_cast<const float4 *>(sp + c8 * 8 + 4));
-                                    v[4] = f.x; v[5] = f.y; v[6] = f.z; v[7] = f.w;
-                                }
-                            } else {
-#pragma unroll
-                                for (int q = 0; q < 8; ++q)
-                                    if (c8 * 8 + q < NS) v[q] = __ldg(sp + c8 * 8 + q);
-                            }
-                        }
-                        if (s == 0 && NS / 8 == c8) v[NS % 8] = 1.f;
-                        uint4 hi;
-                        hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
-                        hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
-                        const uint32_t off = (uint32_t)((s * (KS / 8) + c8) * (TILE_M * 16)) + a_row_off;
-                        *reinterpret_cast<uint4 *>(a_hi + off) = hi;
-                        if (SPLIT) {
-                            float w[8];
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) w[q] = v[q] - __bfloat162float(__float2bfloat16_rn(v[q]));
-                            uint4 lo;
-                            lo.x = pack_bf16x2(w[0], w[1]); lo.y = pack_bf16x2(w[2], w[3]);
-                            lo.z = pack_bf16x2(w[4], w[5]); lo.w = pack_bf16x2(w[6], w[7]);
-                            *reinterpret_cast<uint4 *>(a_lo + off) = lo;
-                        }
-                    }
-                }
-            }
-            fence_proxy_async();
             mbar_arrive(&a_ready[ab]);
         }
     } else {
@@ -723,7 +784,7 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
             // TS: packed bf16 pairs into tensor memory (column c of the lane = k 2c, 2c + 1); SS (split mode): hi / lo
             // images back into the shared-memory A buffer in core-matrix order.
             if (r == 0) trace_ev(jobs.trace, 1, titer, 0);
-            mbar_wait(&tmem_full[0], tf_phase & 1u);
+            DDP_WAIT(&tmem_full[0], tf_phase & 1u, 8, it, -1);
             tf_phase ^= 1u;
             tc_fence_after();
             if (r == 0) trace_ev(jobs.trace, 1, titer, 1);
@@ -805,7 +866,7 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                         x_prefetch_tile<NS, NV, C::ROWS_S, C::XN>(xg, tdw, f_in, xn);
                     }
                     if (r == 0) trace_ev(jobs.trace, 1, titer, 0);
-                    mbar_wait(&tmem_full[buf], (tf_phase >> buf) & 1u);
+                    DDP_WAIT(&tmem_full[buf], (tf_phase >> buf) & 1u, 9, it, tt);
                     tf_phase ^= 1u << buf;
                     tc_fence_after();
                     if (r == 0) trace_ev(jobs.trace, 1, titer, 1);
@@ -869,7 +930,7 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                         (void)stride;
                         if (pass == 0) {
                             if (r == 0) trace_ev(jobs.trace, 1, titer, 0);
-                            mbar_wait(&tmem_full[buf], (tf_phase >> buf) & 1u);
+                            DDP_WAIT(&tmem_full[buf], (tf_phase >> buf) & 1u, 10, it, tt);
                             tf_phase ^= 1u << buf;
                             tc_fence_after();
                             if (r == 0) trace_ev(jobs.trace, 1, titer, 1);
@@ -1122,7 +1183,7 @@ static long long *g_umma_trace = nullptr;
 extern "C" int ddp_tpconv_umma_set_trace(void *trace_dev) {
 #ifdef DDP_UMMA_TRACE
     g_umma_trace = static_cast<long long *>(trace_dev);
-    return 2 * umma::TRACE_TILES * umma::TRACE_EVENTS;      // int64 slots the buffer must hold
+    return 3 * umma::TRACE_TILES * umma::TRACE_EVENTS;      // int64 slots the buffer must hold (watchdog build: 148 x 8 x 4 of them)
 #else
     (void)trace_dev;
     return DDP_E_UNSUPPORTED;                               // library built without -DDDP_UMMA_TRACE

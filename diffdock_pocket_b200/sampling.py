@@ -192,11 +192,14 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
     flexible_sidechains = model_args.flexible_sidechains if flexible_sidechains is None else flexible_sidechains
     no_sidechains_in_batch = False
     if flexible_sidechains:
-        no_sidechains_in_batch = sum(len(c['flexResidues'].subcomponents) for c in data_list) == 0
+        # (graphs without any 'flexResidues' store count as zero flexible atoms; the reference would raise on them)
+        has_sc = lambda c: 'flexResidues' in c and 'subcomponents' in c['flexResidues']
+        no_sidechains_in_batch = sum(len(c['flexResidues'].subcomponents) for c in data_list if has_sc(c)) == 0
         if no_sidechains_in_batch:
             data_list = copy.deepcopy(data_list)
             for c in data_list:
-                del c['flexResidues']
+                if 'flexResidues' in c:
+                    del c['flexResidues']
     N = len(data_list)
     ma = model_args
     device = torch.device(device) if not isinstance(device, torch.device) else device

@@ -141,6 +141,102 @@ __global__ void __launch_bounds__(128, 1) check_kernel(float *out_ss, float *out
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tb) : "memory");
 }
 
+// ---- 128-byte-swizzled K-major operands (bit 0 of sw: A, bit 1: B) instead of the no-swizzle core-matrix layout ----
+// descriptor high word: SBO (8 rows x 128 B = 1024 B) >> 4 | version 1 << 14 | layout SWIZZLE_128B (2) << 29
+constexpr uint32_t DESC_HI_SW128 = 64u | (1u << 14) | (2u << 29);
+__device__ __forceinline__ void mma_ss2(uint32_t d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\tmov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %6};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}\n" ::"r"(d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(a_hi), "r"(b_hi) : "memory");
+}
+__global__ void __launch_bounds__(128, 1) bench_sw_kernel(int n, int sw, int iters, long long *out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    uint8_t *a = smem;                       // 16 KB: 128 rows x 128 B (K = 64)
+    uint8_t *b = smem + 16384;               // 32 KB: 256 rows x 128 B
+    for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tb = tmem_base_s;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = instr_desc(n);
+        const bool swa = sw & 1, swb = sw & 2;
+        const uint32_t a_lo = ((smem_u32(a) >> 4) & 0x3FFFu) | (swa ? (1u << 16) : (128u << 16));
+        const uint32_t b_lo = ((smem_u32(b) >> 4) & 0x3FFFu) | (swb ? (1u << 16) : ((uint32_t)n << 16));
+        const uint32_t a_hi = swa ? DESC_HI_SW128 : DESC_HI, b_hi = swb ? DESC_HI_SW128 : DESC_HI;
+        const uint32_t a_step = swa ? 2u : 256u, b_step = swb ? 2u : 2u * (uint32_t)n;     // one K = 16 step, in 16-byte units
+        long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            const uint32_t d = tb + ((i & 1) ? 256u : 0u);
+            const int k = i & 3;
+            mma_ss2(d, a_lo + (uint32_t)k * a_step, a_hi, b_lo + (uint32_t)k * b_step, b_hi, idesc, i > 1);
+        }
+        long long t1 = clock64();
+        umma_commit(&bar);
+        mbar_wait(&bar, 0);
+        long long t2 = clock64();
+        if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tb) : "memory");
+}
+
+// Numerical check of the swizzled layout: element (row r, k) at byte r * 128 + ((k / 8) ^ (r % 8)) * 16 + (k % 8) * 2
+__global__ void __launch_bounds__(128, 1) check_sw_kernel(float *out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    __nv_bfloat16 *a = reinterpret_cast<__nv_bfloat16 *>(smem);
+    __nv_bfloat16 *b = reinterpret_cast<__nv_bfloat16 *>(smem + 16384);
+    const int N = 64, K = 64;
+    for (int i = threadIdx.x; i < 128 * K; i += blockDim.x) {
+        const int r = i / K, k = i % K;
+        a[r * 64 + (((k / 8) ^ (r % 8)) * 8) + (k % 8)] = __float2bfloat16(((r * 7 + k * 3) % 13 - 6) / 8.f);
+    }
+    for (int i = threadIdx.x; i < N * K; i += blockDim.x) {
+        const int n = i / K, k = i % K;
+        b[n * 64 + (((k / 8) ^ (n % 8)) * 8) + (k % 8)] = __float2bfloat16(((n * 5 + k) % 11 - 5) / 4.f);
+    }
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tb = tmem_base_s;
+    const int r = threadIdx.x;
+    const uint32_t lane_base = (uint32_t)((r / 32) * 32) << 16;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = instr_desc(N);
+        const uint32_t a_lo = ((smem_u32(a) >> 4) & 0x3FFFu) | (1u << 16);
+        const uint32_t b_lo = ((smem_u32(b) >> 4) & 0x3FFFu) | (1u << 16);
+        for (int k = 0; k < K / 16; ++k) mma_ss2(tb, a_lo + (uint32_t)k * 2u, DESC_HI_SW128, b_lo + (uint32_t)k * 2u, DESC_HI_SW128, idesc, k > 0);
+        umma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int c = 0; c < N; ++c) {
+        uint32_t v;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(tb + lane_base + (uint32_t)c) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        out[r * N + c] = __uint_as_float(v);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tb) : "memory");
+}
+
 int main() {
     long long *out;
     cudaMalloc(&out, 16);
@@ -160,6 +256,35 @@ int main() {
             printf("mode %s %s N=%3d : issue %.1f  complete %.1f  (floor %d)  %s\n", (mode & 2) ? "TS" : "SS", (mode & 1) ? "alt2" : "same",
                    n, (double)h[0] / iters, (double)h[1] / iters, n / 2, cudaGetErrorString(e));
         }
+    }
+    cudaFuncSetAttribute(bench_sw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 49152);
+    cudaFuncSetAttribute(check_sw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 49152);
+    for (int sw = 0; sw < 4; ++sw) {
+        for (int n : ns) {
+            bench_sw_kernel<<<148, 128, 49152>>>(n, sw, iters, out);
+            bench_sw_kernel<<<148, 128, 49152>>>(n, sw, iters, out);
+            cudaError_t e = cudaDeviceSynchronize();
+            long long h[2];
+            cudaMemcpy(h, out, 16, cudaMemcpyDeviceToHost);
+            printf("SS alt2 swizzle128 A=%d B=%d N=%3d : issue %.1f  complete %.1f  (floor %d)  %s\n", sw & 1, (sw >> 1) & 1, n, (double)h[0] / iters,
+                   (double)h[1] / iters, n / 2, cudaGetErrorString(e));
+        }
+    }
+    {
+        float *o;
+        cudaMalloc(&o, 128 * 64 * 4);
+        check_sw_kernel<<<1, 128, 49152>>>(o);
+        cudaError_t e = cudaDeviceSynchronize();
+        static float ho[128 * 64];
+        cudaMemcpy(ho, o, sizeof(ho), cudaMemcpyDeviceToHost);
+        double err = 0;
+        for (int r = 0; r < 128; ++r)
+            for (int n = 0; n < 64; ++n) {
+                double ref = 0;
+                for (int k = 0; k < 64; ++k) ref += (((r * 7 + k * 3) % 13 - 6) / 8.0) * (((n * 5 + k) % 11 - 5) / 4.0);
+                err = fmax(err, fabs(ho[r * 64 + n] - ref));
+            }
+        printf("check swizzle128 (%s): max err %.3g\n", cudaGetErrorString(e), err);
     }
     float *ss, *ts;
     cudaMalloc(&ss, 128 * 64 * 4);

@@ -49,7 +49,7 @@ t = buf.cpu().numpy().reshape(2, -1, 8)
 t0 = t[0, 0, 0]
 print('iter | MMA: wait_empty_start empty_ok first_full issued | EPI: ready_to_wait full_ok released red_done   (cycles rel. to start)')
 n_it = int((t[0, :, 0] != 0).sum())
-print(f'SM clock during the traced tiles: {(t[0, n_it - 1, 3] - t[0, 0, 3]) / max(t[0, n_it - 1, 4] - t[0, 0, 4], 1):.3f} GHz over {n_it} tile iterations')
+print(f'{n_it} tile iterations traced (two MMA issuers: even iterations warp 5, odd iterations warp 7)')
 for i in range(160):
     m, e = t[0, i], t[1, i]
     if m[0] == 0:

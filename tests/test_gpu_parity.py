@@ -288,12 +288,15 @@ def test_rigid_ligand_without_flexible_residues():
     assert T.rel_err(conf, ref_conf) < 1e-2
 
 
-def test_forward_batch64_equals_sub_batches():
-    """BASELINE.json configs[2] shape (64 pocket graphs, big model, t = 1 so every ligand-residue pair is an edge):
-    too large for the oracle, so the check is size-independent -- the 64-graph forward equals four 16-graph forwards."""
+@pytest.mark.parametrize('mode,tol', [('bf16x3', 1e-4), ('bf16', 1e-2)])
+def test_forward_batch64_equals_sub_batches(mode, tol):
+    """BASELINE.json configs[2] shape (64 pocket graphs, big model, t = 1 so nearly every ligand-residue pair is an edge):
+    too large for the oracle, so the check is size-independent -- the 64-graph forward equals four 16-graph forwards
+    within the mode's parity gate (the scatter order differs, and in the bf16 mode a last-bit change of a feature can flip
+    its bf16 rounding in the next layer)."""
     m, c, om, oc, sa, ca = T.models(DEV)
     dl = T.randomized_list(T.graph('3dpf_apo'), 64, sa, seed=9)
-    m.conv_mode = 'bf16'
+    m.conv_mode = mode
     try:
         with torch.no_grad():
             b = T.batch_at(dl, 1.0)
@@ -307,4 +310,5 @@ def test_forward_batch64_equals_sub_batches():
     finally:
         m.conv_mode = 'fp32'
     for i in range(4):
-        assert T.rel_err(full[i], torch.cat([p[i] for p in parts])) < 1e-4, i
+        err = T.rel_err(full[i], torch.cat([p[i] for p in parts]))
+        assert err < tol, (i, err)
