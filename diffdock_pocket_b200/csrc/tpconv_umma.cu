@@ -78,6 +78,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// Waits with slack (the gather warp is a whole edge tile ahead, the TMA producer a ring of slabs): let the hardware park
+// the warp (suspend-time hint) and back off between polls instead of spinning -- in profiles/r1_ncu_umma_v23_summary.txt
+// the plain try_wait loops of these two roles are 22 % of all executed warp instructions, i.e. issue energy under a
+// power cap.  The latency-critical waits (issuers, epilogue) keep the tight loop.
+template <int SLEEP_NS>
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+            : "memory");
+        if (done) break;
+        if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+    }
+}
 // Debug build (-DDDP_UMMA_WATCHDOG, with -DDDP_UMMA_TRACE): a wait that has polled ~2^18 times records
 // (code, a, b, barrier parity asked for) of its warp in the host-visible trace buffer, so a deadlock can be read
 // from the host while the kernel still hangs (scripts/umma_watchdog.py).
@@ -103,6 +122,11 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, lon
 #define DDP_WAIT(bar, par, code, a, b) mbar_wait_wd(bar, par, jobs.trace, code, a, b)
 #else
 #define DDP_WAIT(bar, par, code, a, b) mbar_wait(bar, par)
+#endif
+#if defined(DDP_UMMA_WATCHDOG) || defined(DDP_UMMA_SPIN)
+#define DDP_WAIT_RELAXED(SLEEP, bar, par, code, a, b) DDP_WAIT(bar, par, code, a, b)
+#else
+#define DDP_WAIT_RELAXED(SLEEP, bar, par, code, a, b) mbar_wait_relaxed<SLEEP>(bar, par)
 #endif
 // Split-phase barrier test for the MMA issue loop: mbar_test_pN starts a non-blocking phase test whose predicate
 // lives in a PTX register declared once per kernel (DDP_DECLARE_TEST_PREDS); mbar_finish_pN consumes it later (falling
@@ -435,7 +459,11 @@ __device__ __forceinline__ void gather_rows(const ddp_tpconv_edges_t &ed, int n_
         srcs[h][1] = valid ? ed.p1 + (size_t)__ldg(ed.i1 + e) * ed.ld1 : nullptr;
         srcs[h][2] = valid ? ed.p2 + (size_t)__ldg(ed.i2 + e) * ed.ld2 : nullptr;
     }
+#ifdef DDP_UMMA_SPIN
     mbar_wait(free_bar, free_parity);
+#else
+    mbar_wait_relaxed<500>(free_bar, free_parity);
+#endif
 #pragma unroll
     for (int h = 0; h < ROWS; ++h) {
         const int r = row0 + lane + h * 32;
@@ -597,7 +625,7 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                 const uint32_t bytes = slab_bytes(ncol, C::STAGE_K, SPLIT);
 #pragma unroll 1
                 for (int ks = 0; ks < C::KP / C::STAGE_K; ++ks) {
-                    DDP_WAIT(&empty[stage], phase ^ 1, 1, w, tt * 8 + ks);
+                    DDP_WAIT_RELAXED(0, &empty[stage], phase ^ 1, 1, w, tt * 8 + ks);
                     if (elect_one()) {
                         mbar_expect_tx(&full[stage], bytes);
                         bulk_g2s(ring + (size_t)stage * C::STAGE_BYTES, src, bytes, &full[stage]);

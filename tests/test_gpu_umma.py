@@ -25,7 +25,8 @@ def _seq(ns, nv):
 
 @pytest.mark.parametrize('mode', ['bf16x3', 'bf16'])
 @pytest.mark.parametrize('ns,nv,layer,n_edges', [(60, 10, 3, 1000), (60, 10, 0, 130), (60, 10, 1, 128), (60, 10, 2, 5),
-                                                 (24, 6, 3, 700), (16, 4, 2, 300), (60, 10, 3, 40000)])
+                                                 (24, 6, 3, 700), (16, 4, 2, 300), (60, 10, 3, 40000),
+                                                 (60, 10, 1, 45000), (24, 6, 3, 50000), (16, 4, 2, 30000)])
 def test_conv_operator_tensor_core(mode, ns, nv, layer, n_edges):
     seq = _seq(ns, nv)
     in_ir, out_ir = seq[min(layer, 3)], seq[min(layer + 1, 3)]
