@@ -306,6 +306,60 @@ __global__ void scan_counts_kernel(int32_t *__restrict__ counts, int n, int pref
     }
 }
 
+// C-alpha contact graph of datasets/process_mols.py:661-677, one warp per residue j of its complex: neighbours are
+// the residues closer than r (index order); more than max_nbr of them -> the max_nbr nearest in ascending (distance,
+// index) order instead; none -> the single nearest residue.  Fills slab[j][:counts[j]].  Distances in double from the
+// fp32 coordinates, like the reference's scipy cdist, so that near-ties (ideal 3.8 A neighbours) order the same way.
+__device__ __forceinline__ double calpha_dist(const float *__restrict__ pos, int i, double px, double py, double pz) {
+    const double dx = (double)pos[3 * i] - px, dy = (double)pos[3 * i + 1] - py, dz = (double)pos[3 * i + 2] - pz;
+    return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+}
+__global__ void calpha_scan_kernel(const float *__restrict__ pos, const int32_t *__restrict__ ptr, int num_examples, int n,
+                                   double r, int max_nbr, int32_t *__restrict__ slab, int slab_w, int32_t *__restrict__ counts) {
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (j >= n) return;
+    const int b = ddp_find_segment(ptr, num_examples, j);
+    const int beg = ptr[b], end = ptr[b + 1];
+    const double px = pos[3 * j], py = pos[3 * j + 1], pz = pos[3 * j + 2];
+    const unsigned lt = (1u << lane) - 1u;
+    int cnt = 0;
+    for (int base = beg; base < end; base += 32) {
+        const int i = base + lane;
+        const bool hit = i < end && i != j && calpha_dist(pos, i, px, py, pz) < r;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        const int at = cnt + __popc(m & lt);
+        if (hit && at < max_nbr) slab[(size_t)j * slab_w + at] = i;
+        cnt += __popc(m);
+    }
+    int keep = cnt;
+    if (cnt > max_nbr || cnt == 0) {
+        keep = cnt == 0 ? 1 : max_nbr;
+        if (keep > end - beg - 1) keep = end - beg - 1;
+        double last_d = -1.0;
+        int last_i = -1;
+        for (int k = 0; k < keep; ++k) {
+            double bd = INFINITY;
+            int bi = 0x7fffffff;
+            for (int i = beg + lane; i < end; i += 32) {
+                if (i == j) continue;
+                const double d = calpha_dist(pos, i, px, py, pz);
+                const bool after = d > last_d || (d == last_d && i > last_i);
+                if (after && (d < bd || (d == bd && i < bi))) { bd = d; bi = i; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+            }
+            if (lane == 0) slab[(size_t)j * slab_w + k] = bi;
+            last_d = bd; last_i = bi;
+        }
+    }
+    if (lane == 0) counts[j] = keep;
+}
+
 __global__ void compact_edges_kernel(const int32_t *__restrict__ slab, int slab_w, const int32_t *__restrict__ offs,
                                      int n_y, int swap_rows, int prefix, int32_t *__restrict__ edge, int edge_cap) {
     const int lane = threadIdx.x & 31;
@@ -393,6 +447,26 @@ extern "C" int ddp_knn_graph(const float *x, const int32_t *ptr, int32_t num_exa
     if (n > 0) {
         compact_edges_kernel<<<(n + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, st>>>(
             slab, slab_w, counts, n, 1, 0, edge, edge_cap);
+        DDP_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" int ddp_calpha_graph(const float *pos, const int32_t *ptr, int32_t num_examples, int32_t n, float r, int32_t max_nbr,
+                                int32_t *slab, int32_t slab_w, int32_t *counts, int32_t *edge, int32_t edge_cap,
+                                int32_t *n_edges_dev, void *stream) {
+    if (!pos || !ptr || !slab || !counts || !edge || !n_edges_dev) return DDP_E_ARG;
+    if (num_examples <= 0 || n < 0 || max_nbr <= 0 || slab_w < max_nbr) return DDP_E_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (n > 0) {
+        calpha_scan_kernel<<<grid, kWarpsPerBlock * 32, 0, st>>>(pos, ptr, num_examples, n, (double)r, max_nbr, slab, slab_w, counts);
+        DDP_LAUNCH_CHECK();
+    }
+    scan_counts_kernel<<<1, 1024, 0, st>>>(counts, n, 0, n_edges_dev);
+    DDP_LAUNCH_CHECK();
+    if (n > 0) {
+        compact_edges_kernel<<<grid, kWarpsPerBlock * 32, 0, st>>>(slab, slab_w, counts, n, 0, 0, edge, edge_cap);
         DDP_LAUNCH_CHECK();
     }
     return 0;

@@ -84,3 +84,29 @@ def knn_graph(x, k, batch=None, loop=False, flow='source_to_target'):
                                         _lib.stream_ptr()), 'ddp_knn_graph')
     m = int(n_dev.item())
     return torch.stack([edge[:m], edge[cap:cap + m]]).long()
+
+
+def calpha_graph(pos, receptor_radius=15.0, max_neighbors=24, batch=None):
+    """Residue contact graph of the reference's preprocessing (datasets/process_mols.py:661-677) on the device:
+    ``edge_index[0]`` = residue (repeated), ``edge_index[1]`` = its neighbours -- every residue within
+    ``receptor_radius`` in index order, the ``max_neighbors`` nearest (ascending distance) when there are more, the
+    single nearest when there are none.  ``batch`` separates complexes as in radius_graph."""
+    dev = pos.device
+    if dev.type != 'cuda':
+        raise RuntimeError('ddp_b200 graph ops run on CUDA only (no CPU fallback)')
+    x = pos.float().contiguous()
+    n = x.shape[0]
+    if n == 0:
+        return torch.zeros(2, 0, dtype=torch.long, device=dev)
+    nb = _num_examples(batch, batch)
+    p = _ptr_from_batch(batch, n, nb, dev)
+    k = int(max_neighbors)
+    slab = torch.empty(n * k, dtype=torch.int32, device=dev)
+    counts = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+    cap = n * k
+    edge = torch.empty(2 * cap, dtype=torch.int32, device=dev)
+    n_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(_lib.lib().ddp_calpha_graph(ptr(x), ptr(p), nb, n, float(receptor_radius), k, ptr(slab), k, ptr(counts), ptr(edge), cap,
+                                           ptr(n_dev), _lib.stream_ptr()), 'ddp_calpha_graph')
+    m = int(n_dev.item())
+    return torch.stack([edge[:m], edge[cap:cap + m]]).long()

@@ -59,6 +59,14 @@ int ddp_knn_graph(const float *x, const int32_t *ptr, int32_t num_examples, int3
                   int32_t *slab, int32_t slab_w, int32_t *counts, int32_t *edge, int32_t edge_cap,
                   int32_t *n_edges_dev, void *stream);
 
+/* ddp_calpha_graph: the receptor's residue contact graph, built once per complex by the reference's preprocessing
+ * (datasets/process_mols.py:661-677): for every residue i of its complex the residues closer than r, in index order;
+ * if there are more than max_nbr, the max_nbr nearest in ascending distance instead; if there are none, the nearest
+ * one.  edge[0] = i (repeated), edge[1] = neighbour.  Same workspace contract as ddp_radius, slab_w >= max_nbr. */
+int ddp_calpha_graph(const float *pos, const int32_t *ptr, int32_t num_examples, int32_t n, float r, int32_t max_nbr,
+                     int32_t *slab, int32_t slab_w, int32_t *counts, int32_t *edge, int32_t edge_cap,
+                     int32_t *n_edges_dev, void *stream);
+
 /* In-degree of every node on one side of an edge list (the `count` of torch_scatter's mean,
  * models/score_model.py:117): deg[idx[e]] += 1 for e < *n_edges_dev.  deg must be zeroed by the caller. */
 int ddp_degree(const int32_t *idx, const int32_t *n_edges_dev, int32_t edge_cap, int32_t *deg, void *stream);

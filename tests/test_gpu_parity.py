@@ -312,3 +312,43 @@ def test_forward_batch64_equals_sub_batches(mode, tol):
     for i in range(4):
         err = T.rel_err(full[i], torch.cat([p[i] for p in parts]))
         assert err < tol, (i, err)
+
+
+def _calpha_ref(pos, r, k):
+    """datasets/process_mols.py:661-677 restated with numpy (float64 distances, as the reference's cdist)."""
+    pos = pos.double().numpy()
+    dist = np.linalg.norm(pos[:, None] - pos[None], axis=-1)
+    src, dst = [], []
+    for i in range(len(pos)):
+        nb = [j for j in np.where(dist[i] < r)[0] if j != i]
+        if len(nb) > k:
+            nb = [j for j in np.argsort(dist[i], kind='stable') if j != i][:k]
+        if len(nb) == 0:
+            nb = [j for j in np.argsort(dist[i], kind='stable') if j != i][:1]
+        src += [i] * len(nb)
+        dst += [int(j) for j in nb]
+    return torch.tensor([src, dst], dtype=torch.long)
+
+
+def test_calpha_graph_matches_reference_preprocessing():
+    """SURVEY 8(f) rank 1 (static per-complex preprocessing on the device): the residue contact graph is bit-exact with
+    the host restatement on the 3dpf pockets (cap of 24 active for most residues), on a batch of pockets, and on the
+    corner cases (isolated residue -> nearest one; tiny cap; single-residue complex)."""
+    for name in ('3dpf_holo', '3dpf_apo'):
+        g = T.graph(name)
+        got = ops.calpha_graph(g['receptor'].pos.to(DEV), 15.0, 24).cpu()
+        assert torch.equal(got, g['receptor', 'receptor'].edge_index), name           # what inputs.py built on the host
+        assert torch.equal(got, _calpha_ref(g['receptor'].pos, 15.0, 24)), name
+    graphs = [inputs.synthetic_complex(30 + i, n_lig=8, n_res=n, flexible_residues=0) for i, n in enumerate((25, 61, 33))]
+    pos = torch.cat([g['receptor'].pos for g in graphs])
+    batch = torch.repeat_interleave(torch.arange(3), torch.tensor([g['receptor'].pos.shape[0] for g in graphs]))
+    for r, k in ((15.0, 24), (9.0, 5), (4.5, 3)):
+        got = ops.calpha_graph(pos.to(DEV), r, k, batch=batch.to(DEV)).cpu()
+        off, want = 0, []
+        for g in graphs:
+            want.append(_calpha_ref(g['receptor'].pos, r, k) + off)
+            off += g['receptor'].pos.shape[0]
+        assert torch.equal(got, torch.cat(want, 1)), (r, k)
+    far = torch.cat([graphs[0]['receptor'].pos, torch.tensor([[400.0, 0.0, 0.0]])])   # one residue with nobody within r
+    assert torch.equal(ops.calpha_graph(far.to(DEV), 15.0, 24).cpu(), _calpha_ref(far, 15.0, 24))
+    assert ops.calpha_graph(torch.zeros(1, 3, device=DEV), 15.0, 24).shape == (2, 0)
