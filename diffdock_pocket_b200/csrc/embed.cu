@@ -289,36 +289,66 @@ __global__ void __launch_bounds__(256) node_update_vec_kernel(const float *__res
 // Up to three node types (ligand / atom / receptor) of one interaction layer in one launch: blockIdx.y selects the job.
 constexpr int kMaxNodeJobs = 3;
 struct NodeJobs { ddp_node_update_job_t j[kMaxNodeJobs]; };
+constexpr int kNodesPerThread = 4;
 __global__ void __launch_bounds__(256) node_update_multi_kernel(NodeJobs jobs) {
+    // one thread = one channel pair of kNodesPerThread consecutive nodes: the per-channel scale / shift and the live
+    // flags are loaded once, the node rows (old features, sums) are issued together before the arithmetic
     const ddp_node_update_job_t &J = jobs.j[blockIdx.y];
     const int h = J.f_new >> 1;
-    const int total = J.n * h;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const int node = idx / h, c = 2 * (idx - node * h);
-        float2 v = make_float2(0.f, 0.f);
-        if (J.old_x != nullptr && c < J.f_old) v = *reinterpret_cast<const float2 *>(J.old_x + (size_t)node * J.ld_old + c);
+    const int groups = (J.n + kNodesPerThread - 1) / kNodesPerThread;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= groups * h) return;
+    const int g = idx / h, c = 2 * (idx - g * h);
+    float2 sc[4], shift = make_float2(0.f, 0.f);
+    bool has_sum[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (k < J.n_updates && __ldg(J.updates[k].n_edges_dev) > 0) {
-                const ddp_update_t &u = J.updates[k];
-                float2 m = make_float2(0.f, 0.f);
-                if (u.sum != nullptr) {
-                    m = *reinterpret_cast<const float2 *>(u.sum + (size_t)node * J.f_new + c);
-                    if (u.deg != nullptr) {
-                        const int dg = __ldg(u.deg + node);
-                        const float cnt = (float)(dg < 1 ? 1 : dg);
-                        m.x = __fdiv_rn(m.x, cnt);
-                        m.y = __fdiv_rn(m.y, cnt);
-                    }
-                }
-                float2 sc = make_float2(1.f, 1.f), sf = make_float2(0.f, 0.f);
-                if (u.scale != nullptr && u.deg != nullptr) sc = __ldg(reinterpret_cast<const float2 *>(u.scale + c));
-                if (u.shift != nullptr) sf = __ldg(reinterpret_cast<const float2 *>(u.shift + c));
-                v.x += fmaf(m.x, sc.x, sf.x);
-                v.y += fmaf(m.y, sc.y, sf.y);
+    for (int k = 0; k < 4; ++k) {
+        has_sum[k] = false;
+        sc[k] = make_float2(1.f, 1.f);
+        if (k < J.n_updates && __ldg(J.updates[k].n_edges_dev) > 0) {
+            const ddp_update_t &u = J.updates[k];
+            has_sum[k] = u.sum != nullptr;
+            if (u.scale != nullptr && u.deg != nullptr) sc[k] = __ldg(reinterpret_cast<const float2 *>(u.scale + c));
+            if (u.shift != nullptr) {
+                const float2 sf = __ldg(reinterpret_cast<const float2 *>(u.shift + c));
+                shift.x += sf.x; shift.y += sf.y;
             }
         }
-        *reinterpret_cast<float2 *>(J.new_x + (size_t)node * J.ld_new + c) = v;
+    }
+    const int node0 = g * kNodesPerThread;
+    float2 v[kNodesPerThread], m[4][kNodesPerThread];
+#pragma unroll
+    for (int i = 0; i < kNodesPerThread; ++i) {
+        const int node = node0 + i;
+        v[i] = make_float2(0.f, 0.f);
+        if (node < J.n && J.old_x != nullptr && c < J.f_old) v[i] = *reinterpret_cast<const float2 *>(J.old_x + (size_t)node * J.ld_old + c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            m[k][i] = make_float2(0.f, 0.f);
+            if (has_sum[k] && node < J.n) m[k][i] = *reinterpret_cast<const float2 *>(J.updates[k].sum + (size_t)node * J.f_new + c);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kNodesPerThread; ++i) {
+        const int node = node0 + i;
+        if (node >= J.n) break;
+        float2 r = v[i];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (has_sum[k]) {
+                float2 mm = m[k][i];
+                if (J.updates[k].deg != nullptr) {
+                    const int dg = __ldg(J.updates[k].deg + node);
+                    const float cnt = (float)(dg < 1 ? 1 : dg);
+                    mm.x = __fdiv_rn(mm.x, cnt);
+                    mm.y = __fdiv_rn(mm.y, cnt);
+                }
+                r.x = fmaf(mm.x, sc[k].x, r.x);
+                r.y = fmaf(mm.y, sc[k].y, r.y);
+            }
+        }
+        r.x += shift.x; r.y += shift.y;
+        *reinterpret_cast<float2 *>(J.new_x + (size_t)node * J.ld_new + c) = r;
     }
 }
 
@@ -613,7 +643,7 @@ extern "C" int ddp_node_update_multi(const ddp_node_update_job_t *jobs_host, int
                  (reinterpret_cast<uintptr_t>(J.updates[k].scale) % 8 == 0) && (reinterpret_cast<uintptr_t>(J.updates[k].shift) % 8 == 0);
         if (!ok) return DDP_E_UNSUPPORTED;
         jobs.j[m++] = J;
-        const size_t tot = (size_t)J.n * (J.f_new / 2);
+        const size_t tot = (size_t)((J.n + kNodesPerThread - 1) / kNodesPerThread) * (J.f_new / 2);
         most = tot > most ? tot : most;
     }
     if (m == 0) return 0;
