@@ -352,3 +352,26 @@ def test_calpha_graph_matches_reference_preprocessing():
     far = torch.cat([graphs[0]['receptor'].pos, torch.tensor([[400.0, 0.0, 0.0]])])   # one residue with nobody within r
     assert torch.equal(ops.calpha_graph(far.to(DEV), 15.0, 24).cpu(), _calpha_ref(far, 15.0, 24))
     assert ops.calpha_graph(torch.zeros(1, 3, device=DEV), 15.0, 24).shape == (2, 0)
+
+
+def test_sampler_schedules_agree():
+    """The sampler's execution strategies are bookkeeping only: mini-batches on two streams vs one, captured CUDA graphs vs
+    eager launches -- same poses and confidences (noise off, fp32 mode; the only freedom left is the order of the scatter
+    atomics)."""
+    m, c, om, oc, sa, ca = T.models(DEV, small=True)
+    g = inputs.synthetic_complex(41, n_lig=16, n_res=34, flexible_residues=3)
+    dl = T.randomized_list(g, 7, sa, seed=6)
+    steps = 5
+    sch = du.get_t_schedule('expbeta', steps)
+    kw = dict(temp_sampling=[0.9766, 6.0774, 6.7616, 1.4488], temp_psi=[1.5103, 0.8141, 0.7662, 1.3396], temp_sigma_data=0.48884,
+              no_random=True, confidence_model=c, filtering_model_args=ca, batch_size=3)
+    m.conv_mode = 'fp32'
+    run = lambda **o: ps.sampling(copy.deepcopy(dl), m, steps, sch, sch, sch, sch, DEV, partial(du.t_to_sigma, args=sa), sa, **kw, **o)
+    base, conf0 = run(concurrent_batches=False, use_graph=False)
+    for opts in (dict(concurrent_batches=True, use_graph=False), dict(concurrent_batches=True, use_graph=True),
+                 dict(concurrent_batches=False, use_graph=True)):
+        out, conf = run(**opts)
+        for a, b in zip(out, base):
+            assert float((a['ligand'].pos - b['ligand'].pos).abs().max()) < 2e-3, opts
+            assert float((a['atom'].pos - b['atom'].pos).abs().max()) < 2e-3, opts
+        assert T.rel_err(conf, conf0) < 1e-3, opts
