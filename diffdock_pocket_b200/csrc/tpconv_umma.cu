@@ -278,6 +278,23 @@ __device__ __forceinline__ void red_row(float *dst, const float (&acc)[NA]) {
     }
 }
 
+// Warp-level segmented inclusive scan of the output block over runs of consecutive edges with the same aggregation
+// node (off = position of the lane inside its run): afterwards the last lane of every run holds the run's sum and is
+// the only one that issues the atomics.  Edge lists whose aggregation side is sorted (receptor graph, ligand side of
+// the cross edges, residue side of the atom-residue edges) have runs of 8 - 100 edges: 32 lanes adding to the SAME
+// address serialise in the L2 atomic unit, the scan replaces them with log2(run) shuffle steps and one vector atomic.
+template <int N, int NA>
+__device__ __forceinline__ void seg_scan(float (&acc)[NA], int off, int nsteps) {
+#pragma unroll 1
+    for (int st = 0, d = 1; st < nsteps; ++st, d <<= 1) {
+#pragma unroll
+        for (int o = 0; o < N; ++o) {
+            const float v = __shfl_up_sync(0xffffffffu, acc[o], d);
+            if (off >= d) acc[o] += v;
+        }
+    }
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&t);
@@ -306,6 +323,9 @@ __host__ __device__ constexpr int stage_k_of(int ks, bool split) { return ks == 
 #endif
 #ifndef DDP_UMMA_TOKEN
 #define DDP_UMMA_TOKEN 1
+#endif
+#ifndef DDP_UMMA_SEGSCAN
+#define DDP_UMMA_SEGSCAN 1
 #endif
 __host__ __device__ constexpr bool use_ts(bool split) { return DDP_UMMA_TS != 0 && !split; }
 __host__ __device__ constexpr int rows_scalar(int ns, bool ts) { return (ts ? 192 : 240) / ns; }
@@ -803,6 +823,19 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                 s0 = sh4.x * inv_deg; s1x = sh4.y * inv_deg; s1y = sh4.z * inv_deg; s1z = sh4.w * inv_deg;
                 xg = ed.x + (size_t)__ldg(ed.gather + e) * ed.ldx;
             }
+            // runs of equal aggregation nodes inside this warp's 32 edges: seg = off | steps << 8 | is_tail << 16
+            // (steps = 0: no pre-reduction, e.g. fewer than half of the lanes would merge)
+            int seg = 0;
+            {
+                const int lane_ = r & 31;
+                const int key = valid ? agg : -1 - r;
+                const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+                const unsigned heads = __ballot_sync(0xffffffffu, lane_ == 0 || prev != key);
+                const int off = lane_ - (31 - __clz((int)(heads & (0xffffffffu >> (31 - lane_)))));
+                const int maxoff = __reduce_max_sync(0xffffffffu, off);
+                if (DDP_UMMA_SEGSCAN && __popc(heads) <= 16)
+                    seg = off | ((32 - __clz(maxoff)) << 8) | ((lane_ == 31 || ((heads >> (lane_ + 1)) & 1u)) ? 1 << 16 : 0);
+            }
             // node features of weight tile 0 (registers; every tile prefetches the next one's)
             float xn[C::XN];
             uint4 tdw = *reinterpret_cast<const uint4 *>(&tiles[t0]);
@@ -913,8 +946,8 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                     tc_fence_before();
                     mbar_arrive(&tmem_empty[buf]);
                     if (r == 0) trace_ev(jobs.trace, 1, titer, 2);
-                    if ((flags & 4) && valid) {
-                        if (ed.out_scale != nullptr) {                       // block offsets and widths are even: 8-byte loads
+                    if (flags & 4) {
+                        if (valid && ed.out_scale != nullptr) {              // block offsets and widths are even: 8-byte loads
                             const float2 *sc2 = reinterpret_cast<const float2 *>(ed.out_scale + out_off);
 #pragma unroll
                             for (int o = 0; o < NS; o += 2) {
@@ -923,7 +956,9 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                                 acc[o + 1] *= v.y;
                             }
                         }
-                        red_row<NS>(sum + (size_t)agg * f_out + out_off, acc);
+                        const int steps = (seg >> 8) & 0xff;
+                        if (steps) seg_scan<NS>(acc, seg & 0xff, steps);
+                        if (valid && (steps == 0 || (seg >> 16))) red_row<NS>(sum + (size_t)agg * f_out + out_off, acc);
                     }
                     if (r == 0) trace_ev(jobs.trace, 1, titer, 3);
                 } else {
@@ -995,8 +1030,8 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                     tc_fence_before();
                     mbar_arrive(&tmem_empty[buf]);
                     if (r == 0) trace_ev(jobs.trace, 1, titer, 2);
-                    if ((flags & 4) && valid) {
-                        if (ed.out_scale != nullptr) {
+                    if (flags & 4) {
+                        if (valid && ed.out_scale != nullptr) {
                             const float2 *sc2 = reinterpret_cast<const float2 *>(ed.out_scale + out_off);
 #pragma unroll
                             for (int o = 0; o < 3 * NV; o += 2) {
@@ -1005,7 +1040,9 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                                 acc[o + 1] *= v.y;
                             }
                         }
-                        red_row<3 * NV>(sum + (size_t)agg * f_out + out_off, acc);
+                        const int steps = (seg >> 8) & 0xff;
+                        if (steps) seg_scan<3 * NV>(acc, seg & 0xff, steps);
+                        if (valid && (steps == 0 || (seg >> 16))) red_row<3 * NV>(sum + (size_t)agg * f_out + out_off, acc);
                     }
                     if (r == 0) trace_ev(jobs.trace, 1, titer, 3);
                 }

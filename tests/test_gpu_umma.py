@@ -54,6 +54,33 @@ def test_conv_operator_tensor_core(mode, ns, nv, layer, n_edges):
 
 
 @pytest.mark.parametrize('mode', ['bf16x3', 'bf16'])
+@pytest.mark.parametrize('run', [3, 8, 24, 100])
+def test_conv_operator_sorted_aggregation(mode, run):
+    """Edge lists sorted by aggregation node (receptor graph: runs of 24; ligand side of the cross edges: ~100): the epilogue
+    pre-reduces each run inside the warp before the atomics.  Runs of random length around `run`, plus a ragged tail."""
+    ns, nv = 60, 10
+    seq = _seq(ns, nv)
+    torch.manual_seed(1)
+    prod = TensorProductConvLayer(seq[3], '1x0e+1x1o', seq[3], 3 * ns, residual=False, batch_norm=True, faster=True)
+    ref = RefConv(seq[3], '1x0e+1x1o', seq[3], 3 * ns, residual=False, batch_norm=True, faster=True)
+    ref.load_state_dict(prod.state_dict())
+    prod, ref = prod.to(DEV).eval(), ref.eval()
+    n = 200
+    lens = torch.randint(max(run // 2, 1), run * 3 // 2 + 2, (n,))
+    agg = torch.repeat_interleave(torch.arange(n), lens)[:4001]
+    n_edges = agg.numel()
+    ei = torch.stack([agg, torch.randint(0, n, (n_edges,))])
+    x = torch.randn(n, E.Irreps(seq[3]).dim)
+    ea = torch.randn(n_edges, 3 * ns)
+    sh = E.spherical_harmonics('1x0e+1x1o', torch.randn(n_edges, 3))
+    with torch.no_grad():
+        want = ref(x, ei, ea, sh, out_nodes=n)
+        prod.conv_mode = mode
+        got = prod(x.to(DEV), ei.to(DEV), ea.to(DEV), sh.to(DEV), out_nodes=n)
+    assert T.rel_err(got, want) < TOL[mode], (mode, run, T.rel_err(got, want))
+
+
+@pytest.mark.parametrize('mode', ['bf16x3', 'bf16'])
 def test_score_model_forward_tensor_core(mode):
     m, c, om, oc, sa, ca = T.models(DEV)
     dl = T.randomized_list(T.graph(), 3, sa, seed=0)
