@@ -81,7 +81,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 // Waits with slack (the gather warp is a whole edge tile ahead, the TMA producer a ring of slabs): let the hardware park
 // the warp (suspend-time hint) and back off between polls instead of spinning -- in profiles/r1_ncu_umma_v23_summary.txt
 // the plain try_wait loops of these two roles are 22 % of all executed warp instructions, i.e. issue energy under a
-// power cap.  The latency-critical waits (issuers, epilogue) keep the tight loop.
+// power cap.  The latency-critical waits (issuers, epilogue) use the hint without the back-off (-DDDP_UMMA_SPIN restores
+// the plain loops).
 template <int SLEEP_NS>
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
     uint32_t done;
@@ -121,7 +122,11 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, lon
 }
 #define DDP_WAIT(bar, par, code, a, b) mbar_wait_wd(bar, par, jobs.trace, code, a, b)
 #else
+#ifdef DDP_UMMA_SPIN
 #define DDP_WAIT(bar, par, code, a, b) mbar_wait(bar, par)
+#else
+#define DDP_WAIT(bar, par, code, a, b) mbar_wait_relaxed<0>(bar, par)   // suspend-time hint, no back-off: wakes on completion
+#endif
 #endif
 #if defined(DDP_UMMA_WATCHDOG) || defined(DDP_UMMA_SPIN)
 #define DDP_WAIT_RELAXED(SLEEP, bar, par, code, a, b) DDP_WAIT(bar, par, code, a, b)
