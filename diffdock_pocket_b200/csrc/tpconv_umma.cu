@@ -399,6 +399,12 @@ struct Cfg {
     static_assert(XN % 2 == 0, "x prefetch registers are loaded in pairs");
 };
 
+// TMEM accumulator of slot tt of an item with nt weight tiles (tt = -1: GEMM1, always accumulator 0).  The weight tiles
+// alternate such that the LAST one sits in accumulator 1: accumulator 0 is then free one tile earlier, and the next
+// item's GEMM1 runs under the last tile's MMAs / epilogue instead of after them.  For even nt that puts GEMM1 and
+// tile 0 back to back in accumulator 0 (tile 0 has to wait for the hidden activations anyway).
+__device__ __forceinline__ uint32_t acc_of(int tt, int nt) { return tt < 0 ? 0u : (uint32_t)(tt + nt) & 1u; }
+
 // Map the g-th 128-edge tile of the launch to (job, tile inside the job); pref = exclusive prefix of tile counts.
 __device__ __forceinline__ void locate(const int *pref, int n_jobs, int g, int &job, int &et) {
     int j = 0;
@@ -693,7 +699,7 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
             const uint32_t a_hi_lo = ((a_hi_addr >> 4) & 0x3FFFu) | ((uint32_t)(TILE_M * 16 >> 4) << 16);
             const uint32_t a_lo_lo = (((a_hi_addr + C::A_BYTES) >> 4) & 0x3FFFu) | ((uint32_t)(TILE_M * 16 >> 4) << 16);
             for (int tt = -1; tt < nt; ++tt, ++titer) {
-                const uint32_t buf = (uint32_t)(tt + 1) & 1u;
+                const uint32_t buf = acc_of(tt, nt);
                 if (C::DUAL && buf != me) {                              // the other issuer's tile: only the ring position moves
 #pragma unroll
                     for (int ks = 0; ks < NG; ++ks)
@@ -713,15 +719,17 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                 const bool last_reader = C::TS ? tt < 0 : tt + (C::DUAL ? 2 : 1) >= nt;
                 trace_ev(jobs.trace, 0, titer, 0);
                 if (tt < 0) DDP_WAIT(&a_ready[ab], (uint32_t)(it / C::NBUF) & 1u, 2, it, tt);
-                if (tt == 0) { DDP_WAIT(h_ready, hr_phase, 3, it, tt); hr_phase ^= 1; }
+                // the first GEMM2 tile this warp issues in the item needs the hidden activations (tile 0, and tile 1 where
+                // it belongs to the other issuer); every warp toggles its phase once per item
+                if (tt == 0 || (C::DUAL && tt == 1)) DDP_WAIT(h_ready, hr_phase, 3, it, tt);
                 DDP_WAIT(&tmem_empty[buf], ((te_phase >> buf) & 1u) ^ 1u, 4, it, tt);
                 te_phase ^= 1u << buf;
                 DDP_WAIT(&full[stage], phase, 5, it, tt * 16 + (int)stage);
                 if (C::DUAL && DDP_UMMA_TOKEN) {
                     // tiles are issued in tile order: everything above overlapped the other issuer's tile, only the
                     // first tcgen05.mma waits for its last one
-                    // (one token per run of the other issuer's tiles: warp 5 owns the last tile of an even-length item and
-                    // the next item's GEMM1 back to back and signals only after the second)
+                    // (one token per run of the other issuer's tiles: warp 5 owns GEMM1 and tile 0 of an even-length item
+                    // back to back and signals only after the second)
                     if (tok_pending > 0) { DDP_WAIT(&tok[me ^ 1u], tok_phase, 6, it, tt); tok_phase ^= 1u; tok_pending = 0; }
                 }
                 tc_fence_after();
@@ -756,7 +764,7 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                         if (ks == NG - 1) {
                             umma_commit(&tmem_full[buf]);
                             if (last_reader) umma_commit(&a_free[ab]);
-                            if (C::DUAL && DDP_UMMA_TOKEN && !(me == 0 && tt == nt - 1)) mbar_arrive(&tok[me]);
+                            if (C::DUAL && DDP_UMMA_TOKEN && !(tt < 0 && acc_of(0, nt) == 0u)) mbar_arrive(&tok[me]);
                         }
                     }
                     __syncwarp();
@@ -769,6 +777,7 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                 }
                 trace_ev(jobs.trace, 0, titer, 3);
             }
+            hr_phase ^= 1u;
         }
     } else if (warp == 6 || (warp == 7 && !C::DUAL)) {
         // =============================== gather: A operand of the NEXT edge tile ===================
@@ -910,7 +919,7 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                 const int out_off = (int)(tdw.y & 0xffffu);
                 // a split item starts / ends inside a block: its partial sums are zeroed / flushed at the item bounds
                 const int flags = (int)((tdw.y >> 16) & 0xffu) | (tt == 0 ? 1 : 0) | (tt == nt - 1 ? 4 : 0);
-                const uint32_t buf = (uint32_t)(tt + 1) & 1u;
+                const uint32_t buf = acc_of(tt, nt);
                 const uint32_t taddr = tmem_base + lane_base + buf * (uint32_t)C::ACC_STRIDE;
                 if (flags & 1) {
 #pragma unroll
