@@ -812,6 +812,62 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
         const uint32_t a_row_off = (uint32_t)((r >> 3) * 128 + (r & 7) * 16);
         int it = 0;
         int titer = 0;
+        // GEMM1 result -> ReLU -> hidden activations become the A operand of GEMM2 (TS: packed bf16 pairs into tensor memory,
+        // column c of the lane = k 2c, 2c + 1; SS: hi (/ lo) images back into the shared-memory A buffer in core-matrix
+        // order).  Needs nothing per edge, so at an item boundary it runs BEFORE the previous item's last flush and the
+        // next item's per-edge set-up (dependent global loads): tiles 0 and 1 of the next item are already on the tensor
+        // pipe while the epilogue does those.
+        auto convert_hidden = [&](uint8_t *a_hi_, uint8_t *a_lo_, int it_) {
+            if (r == 0) trace_ev(jobs.trace, 1, titer, 0);
+            DDP_WAIT(&tmem_full[0], tf_phase & 1u, 8, it_, -1);
+            tf_phase ^= 1u;
+            tc_fence_after();
+            if (r == 0) trace_ev(jobs.trace, 1, titer, 1);
+            {
+                uint32_t w[2][16];
+                tmem_ld16_async(tmem_base + lane_base, w[0]);
+#pragma unroll
+                for (int c16 = 0; c16 < C::N1 / 16; ++c16) {
+                    tmem_wait16(w[c16 & 1]);
+                    if (c16 + 1 < C::N1 / 16) tmem_ld16_async(tmem_base + lane_base + (uint32_t)((c16 + 1) * 16), w[(c16 + 1) & 1]);
+                    float v[16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) v[q] = fmaxf(__uint_as_float(w[c16 & 1][q]), 0.f);
+                    if (C::TS) {
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) pk[q] = pack_bf16x2(v[2 * q], v[2 * q + 1]);
+                        tmem_st8(tmem_base + lane_base + (uint32_t)(C::H_COL + c16 * 8), pk);
+                    } else {
+#pragma unroll
+                        for (int h8 = 0; h8 < 2; ++h8) {
+                            uint4 hi;
+                            hi.x = pack_bf16x2(v[8 * h8 + 0], v[8 * h8 + 1]); hi.y = pack_bf16x2(v[8 * h8 + 2], v[8 * h8 + 3]);
+                            hi.z = pack_bf16x2(v[8 * h8 + 4], v[8 * h8 + 5]); hi.w = pack_bf16x2(v[8 * h8 + 6], v[8 * h8 + 7]);
+                            const uint32_t off = (uint32_t)((c16 * 2 + h8) * (TILE_M * 16)) + a_row_off;
+                            *reinterpret_cast<uint4 *>(a_hi_ + off) = hi;
+                            if (SPLIT) {
+                                float u[8];
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) u[q] = v[8 * h8 + q] - __bfloat162float(__float2bfloat16_rn(v[8 * h8 + q]));
+                                uint4 lo;
+                                lo.x = pack_bf16x2(u[0], u[1]); lo.y = pack_bf16x2(u[2], u[3]);
+                                lo.z = pack_bf16x2(u[4], u[5]); lo.w = pack_bf16x2(u[6], u[7]);
+                                *reinterpret_cast<uint4 *>(a_lo_ + off) = lo;
+                            }
+                        }
+                    }
+                }
+            }
+            if (C::TS) tmem_wait_st();
+            tc_fence_before();
+            if (!C::TS) fence_proxy_async();
+            mbar_arrive(h_ready);
+            mbar_arrive(&tmem_empty[0]);
+            if (r == 0) trace_ev(jobs.trace, 1, titer, 2);
+
+        };
+        bool h_done = false;                             // the current item's hidden activations were written at the previous boundary
         for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
             int g, t0, t1, job, et;
             work_item(wk, w, n_tiles, g, t0, t1);
@@ -855,57 +911,11 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
             uint4 tdw = *reinterpret_cast<const uint4 *>(&tiles[t0]);
             x_prefetch_tile<NS, NV, C::ROWS_S, C::XN>(xg, tdw, f_in, xn);
 
-            // ---- GEMM1 result -> ReLU -> hidden activations become the A operand of GEMM2 ----
-            // TS: packed bf16 pairs into tensor memory (column c of the lane = k 2c, 2c + 1); SS (split mode): hi / lo
-            // images back into the shared-memory A buffer in core-matrix order.
-            if (r == 0) trace_ev(jobs.trace, 1, titer, 0);
-            DDP_WAIT(&tmem_full[0], tf_phase & 1u, 8, it, -1);
-            tf_phase ^= 1u;
-            tc_fence_after();
-            if (r == 0) trace_ev(jobs.trace, 1, titer, 1);
-            {
-                uint32_t w[2][16];
-                tmem_ld16_async(tmem_base + lane_base, w[0]);
-#pragma unroll
-                for (int c16 = 0; c16 < C::N1 / 16; ++c16) {
-                    tmem_wait16(w[c16 & 1]);
-                    if (c16 + 1 < C::N1 / 16) tmem_ld16_async(tmem_base + lane_base + (uint32_t)((c16 + 1) * 16), w[(c16 + 1) & 1]);
-                    float v[16];
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) v[q] = fmaxf(__uint_as_float(w[c16 & 1][q]), 0.f);
-                    if (C::TS) {
-                        uint32_t pk[8];
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) pk[q] = pack_bf16x2(v[2 * q], v[2 * q + 1]);
-                        tmem_st8(tmem_base + lane_base + (uint32_t)(C::H_COL + c16 * 8), pk);
-                    } else {
-#pragma unroll
-                        for (int h8 = 0; h8 < 2; ++h8) {
-                            uint4 hi;
-                            hi.x = pack_bf16x2(v[8 * h8 + 0], v[8 * h8 + 1]); hi.y = pack_bf16x2(v[8 * h8 + 2], v[8 * h8 + 3]);
-                            hi.z = pack_bf16x2(v[8 * h8 + 4], v[8 * h8 + 5]); hi.w = pack_bf16x2(v[8 * h8 + 6], v[8 * h8 + 7]);
-                            const uint32_t off = (uint32_t)((c16 * 2 + h8) * (TILE_M * 16)) + a_row_off;
-                            *reinterpret_cast<uint4 *>(a_hi + off) = hi;
-                            if (SPLIT) {
-                                float u[8];
-#pragma unroll
-                                for (int q = 0; q < 8; ++q) u[q] = v[8 * h8 + q] - __bfloat162float(__float2bfloat16_rn(v[8 * h8 + q]));
-                                uint4 lo;
-                                lo.x = pack_bf16x2(u[0], u[1]); lo.y = pack_bf16x2(u[2], u[3]);
-                                lo.z = pack_bf16x2(u[4], u[5]); lo.w = pack_bf16x2(u[6], u[7]);
-                                *reinterpret_cast<uint4 *>(a_lo + off) = lo;
-                            }
-                        }
-                    }
-                }
-            }
-            if (C::TS) tmem_wait_st();
-            tc_fence_before();
-            if (!C::TS) fence_proxy_async();
-            mbar_arrive(h_ready);
-            mbar_arrive(&tmem_empty[0]);
-            if (r == 0) trace_ev(jobs.trace, 1, titer, 2);
+            if (!h_done) convert_hidden(a_hi, a_lo, it);
+            h_done = false;
             ++titer;
+            const bool has_next = w + (int)gridDim.x < n_items;
+            uint8_t *a_hi_next = a_base + (size_t)((it + 1) % C::NBUF) * C::A_BYTES * (SPLIT ? 2 : 1);
 
             // ---- weight tiles: TMEM accumulator x tensor-product basis -> per-edge output registers ----
             // Every tile has one basis kind; its node features arrive in registers (prefetched during the previous
@@ -960,6 +970,7 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                     tc_fence_before();
                     mbar_arrive(&tmem_empty[buf]);
                     if (r == 0) trace_ev(jobs.trace, 1, titer, 2);
+                    if (tt == nt - 1 && has_next) { convert_hidden(a_hi_next, a_hi_next + C::A_BYTES, it + 1); h_done = true; }
                     if (flags & 4) {
                         if (valid && ed.out_scale != nullptr) {              // block offsets and widths are even: 8-byte loads
                             const float2 *sc2 = reinterpret_cast<const float2 *>(ed.out_scale + out_off);
@@ -1044,6 +1055,7 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                     tc_fence_before();
                     mbar_arrive(&tmem_empty[buf]);
                     if (r == 0) trace_ev(jobs.trace, 1, titer, 2);
+                    if (tt == nt - 1 && has_next) { convert_hidden(a_hi_next, a_hi_next + C::A_BYTES, it + 1); h_done = true; }
                     if (flags & 4) {
                         if (valid && ed.out_scale != nullptr) {
                             const float2 *sc2 = reinterpret_cast<const float2 *>(ed.out_scale + out_off);
