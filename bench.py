@@ -321,9 +321,9 @@ def main():
         model.profile = None
         ach = tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
         # DRAM bytes of one conv launch (dram__bytes_read + write, ncu --set full of the grouped layer-3 launch of this
-        # same batch: profiles/r1_ncu_umma_v23_summary.txt); far below the algorithmic 1.2 kB/edge because gathered
+        # same batch: profiles/r1_ncu_umma_v27_summary.txt); far below the algorithmic 1.2 kB/edge because gathered
         # node rows and the weight image are served by L2
-        traffic = 220.3e6 if (args.mode == 'bf16' and args.workload == '3dpf_apo' and args.batch_size == 20) else None
+        traffic = 224.1e6 if (args.mode == 'bf16' and args.workload == '3dpf_apo' and args.batch_size == 20) else None
         roof = {'bound': 'tensor', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'traffic': traffic,
                 'kernel': 'tpconv_umma_kernel' if args.mode != 'fp32' else 'tpconv_fp32_kernel', 'launches_measured': n_l,
                 'peak_source': peak_src, 'conv_share_of_forward_ms': tot_ms}
