@@ -9,7 +9,9 @@
 //   warps 0-3  epilogue: after GEMM1 apply ReLU and write the hidden activations back as the A operand of GEMM2;
 //              then, per weight tile, tcgen05.ld the [128 x N] accumulator, multiply with the tensor-product basis
 //              (node features fetched from global memory into registers one tile ahead) and accumulate the edge's
-//              output in registers; vector red.global.add into the aggregation node at the end of each output block.
+//              output in registers; at the end of each output block a warp-level segmented pre-reduction over runs of
+//              equal aggregation nodes, then vector red.global.add.  At an edge-tile boundary the next tile's hidden
+//              activations are written before the last flush and the next tile's per-edge set-up.
 //   warp 4     TMA producer: streams the pre-packed weight image (already in UMMA core-matrix order and in
 //              consumption order) slab by slab.
 //   warps 5, 7 MMA issuers (one elected lane each), one per TMEM accumulator, so that one of them is always parked on
