@@ -47,8 +47,8 @@ def parse():
     p.add_argument('--batch-size', type=int, default=20)
     p.add_argument('--inference-steps', type=int, default=20)
     p.add_argument('--workload', default='3dpf_apo')
-    p.add_argument('--cpu-samples', type=int, default=2)
-    p.add_argument('--cpu-steps', type=int, default=2)
+    p.add_argument('--cpu-samples', type=int, default=4)
+    p.add_argument('--cpu-steps', type=int, default=3)
     p.add_argument('--no-cpu-baseline', action='store_true')
     p.add_argument('--single-stream', action='store_true', help='run the mini-batches back to back on one stream (A/B of the two-stream overlap)')
     p.add_argument('--no-graph', action='store_true', help='launch kernels eagerly instead of replaying the captured step graph')
