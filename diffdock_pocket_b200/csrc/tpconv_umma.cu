@@ -328,6 +328,9 @@ __host__ __device__ constexpr int stage_k_of(int ks, bool split) { return ks == 
 #ifndef DDP_UMMA_DUAL
 #define DDP_UMMA_DUAL 1
 #endif
+// DDP_UMMA_TOKEN = 1: the two issuers hand an issue-order token back and forth, so tiles reach the tensor pipe in tile
+// order.  Without it (0) the big grouped launches failed on B200 ("unspecified launch failure" / hangs, cause not
+// found: every barrier hazard checked out on paper and the watchdog build ran clean) -- debug switch only.
 #ifndef DDP_UMMA_TOKEN
 #define DDP_UMMA_TOKEN 1
 #endif
