@@ -225,6 +225,13 @@ def test_fixture_graph_shapes_and_collate():
     assert int(b['ligand', 'ligand'].edge_index.max()) == 110 and int(b['atom', 'receptor'].edge_index[1].max()) == 3 * 139 - 1
     assert int(b['flexResidues'].edge_idx.max()) < 1111 and b['flexResidues'].batch.tolist() == [0] * 17 + [1] * 17 + [2] * 17
     assert len(list(DataLoader([g] * 5, batch_size=2))) == 3
+    # a graph without flexible residues: look-ups like len(data['flexResidues']) leave an empty store behind (as in PyG),
+    # which must not break collation; the rigid case also goes through the oracle sampler
+    from diffdock_pocket_b200 import inputs
+    r = inputs.synthetic_complex(21, n_lig=3, n_res=12, flexible_residues=0)
+    assert 'flexResidues' not in r and len(r['flexResidues']) == 0 and 'flexResidues' in r
+    rb = Batch.from_data_list([copy.deepcopy(r), copy.deepcopy(r)])
+    assert rb.num_graphs == 2 and 'flexResidues' not in rb.node_types and rb['ligand'].pos.shape == (6, 3)
 
 
 def test_oracle_reproduces_golden_forward():
