@@ -208,6 +208,9 @@ class PackedConv:
             host = torch.empty(size, dtype=torch.uint8)
             _lib.check(L.ddp_tpconv_pack(*args, ptr(host)), 'ddp_tpconv_pack')
             self.umma[mode] = host.to(device)
+            # one-time upload from pageable memory: other streams (the sampler's second mini-batch stream) may launch on
+            # this image right away, so make sure the DMA has landed before anybody can
+            torch.cuda.current_stream(device).synchronize()
         return self.umma[mode]
 
 
