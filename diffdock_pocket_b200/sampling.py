@@ -186,7 +186,8 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
              t_schedule=None, batch_size=32, no_final_step_noise=False, pivot=None, return_full_trajectory=False,
              svgd_weight=0.0, svgd_repulsive_weight=1.0, svgd_only=False, svgd_rot_rel_weight=1.0, svgd_tor_rel_weight=1.0,
              svgd_sidechain_tor_rel_weight=1.0, temp_sampling=1.0, temp_psi=0.0, temp_sigma_data=0.5,
-             flexible_sidechains=None, max_steps=None, trace=None, use_graph=False, concurrent_batches=True):
+             flexible_sidechains=None, max_steps=None, trace=None, use_graph=False, concurrent_batches=True,
+             loader_seed_draws=True):
     if svgd_weight > 0 or pivot is not None or asyncronous_noise_schedule:
         raise NotImplementedError('SVGD / pivot / asynchronous schedules are outside the accelerated path')
     flexible_sidechains = model_args.flexible_sidechains if flexible_sidechains is None else flexible_sidechains
@@ -226,9 +227,14 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
     # Noise for all steps is drawn up front, in the reference's order (per step: tr_z, rot_z, tor_z,
     # sidechain_tor_z; utils/sampling.py:136-163) -- nothing else consumes the CPU generator in between, so the
     # stream is identical; each step's slice travels to the device inside that step's single H2D copy.
+    # The reference also builds a torch DataLoader every step (utils/sampling.py:100) whose iterator draws its
+    # ``_base_seed`` (one int64 ``random_()``) from the same default generator before the step's noise; the draw is
+    # repeated here so that a seeded run consumes the identical stream (``loader_seed_draws=False`` skips it).
     noise_host = torch.zeros(max(n_steps, 1), M)
-    if not ode:
-        for t_idx in range(n_steps):
+    for t_idx in range(n_steps):
+        if loader_seed_draws:
+            torch.empty((), dtype=torch.int64).random_()
+        if not ode:
             zero_noise = no_random or (no_final_step_noise and t_idx == inference_steps - 1)
             draw = (lambda shape: torch.zeros(shape)) if zero_noise else (lambda shape: torch.normal(mean=0, std=1, size=shape))
             noise_host[t_idx, :3 * N] = draw((N, 3)).reshape(-1)
@@ -237,6 +243,9 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
                 noise_host[t_idx, 6 * N:6 * N + T_tot] = draw((T_tot,))
             if flexible_sidechains:
                 noise_host[t_idx, 6 * N + T_tot:] = draw((S_tot,))
+    if loader_seed_draws and confidence_model is not None and n_steps == inference_steps:
+        for _ in range(2):                                            # the two loaders of utils/sampling.py:265-266
+            torch.empty((), dtype=torch.int64).random_()
 
     conf_plans = None
 

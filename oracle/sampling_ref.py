@@ -6,9 +6,10 @@
   inference path and the reference raises NotImplementedError for it with flexible side chains)
 
 Random draws use the same generators in the same order as the reference (numpy global RNG for the
-initial torsions, scipy ``Rotation.random``, ``torch.normal`` on the CPU default generator for
-tr_z, rot_z, tor_z, sidechain_tor_z per step) so a seeded product run consumes identical streams
-(SURVEY.md App. D.14).
+initial torsions, scipy ``Rotation.random``, and on the torch CPU default generator per step: the
+``_base_seed`` of the step's DataLoader iterator (utils/sampling.py:100,112), then ``torch.normal`` for
+tr_z, rot_z, tor_z, sidechain_tor_z) so a seeded run consumes identical streams.
+Graphs are collated by ``oracle.pyg_mini`` (not by the product's ``hetero`` module).
 """
 import copy
 
@@ -16,7 +17,7 @@ import numpy as np
 import torch
 from scipy.spatial.transform import Rotation as R
 
-from diffdock_pocket_b200.hetero import DataLoader
+from .pyg_mini import DataLoader
 from .diffusion_ref import (modify_conformer, modify_conformer_torsion_angles, modify_sidechains, set_time)
 
 
@@ -129,7 +130,9 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
     if confidence_model is not None:                                   # utils/sampling.py:263-281
         conf = []
         with torch.no_grad():
-            for batch in DataLoader(data_list, batch_size=batch_size):
+            loader = DataLoader(data_list, batch_size=batch_size)
+            iter(DataLoader(None, batch_size=batch_size))             # filtering_loader (:266): its iterator is created even without filtering data
+            for batch in loader:
                 set_time(batch, 0, 0, 0, 0, N)
                 conf.append(confidence_model(batch))
         confidence = torch.cat(conf, 0)
