@@ -216,6 +216,33 @@ class TensorProductScoreModel(nn.Module):
         self._packed = None
         return super()._load_from_state_dict(*a, **k)
 
+    @staticmethod
+    def _is_e3nn_constant(key, value):
+        """Keys an e3nn 0.5.1 module contributes to a reference checkpoint that carry no learned state: the persistent
+        buffers of ``o3.TensorProduct`` (``output_mask``, the Wigner-3j constants ``_w3j_*`` inside the TorchScript-compiled
+        ``_compiled_main_*`` sub-modules) and the EMPTY ``weight`` buffer it registers when ``internal_weights`` is off.
+        They belong to ``conv.tp`` of the non-``faster`` convs, ``tor_bond_conv.tp`` / ``sc_tor_bond_conv.tp`` and
+        ``final_tp_tor`` / ``final_tp_sc_tor`` (models/all_atom_score_model.py:193-228, models/score_model.py:98)."""
+        parts = key.split('.')
+        owner_is_tp = 'tp' in parts[:-1] or any(p.startswith('final_tp') for p in parts[:-1])
+        if not owner_is_tp:
+            return False
+        last = parts[-1]
+        if last == 'output_mask' or last.startswith('_w3j') or any(p.startswith('_compiled_main') for p in parts[:-1]):
+            return True
+        return last == 'weight' and torch.is_tensor(value) and value.numel() == 0
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        """``strict=True`` like the reference (inference.py:434-435,447-448) on everything learned; the constant e3nn
+        buffers listed in ``_is_e3nn_constant`` are the ONLY keys that are dropped.  A ``module.``-prefixed checkpoint
+        (saved from ``DataParallel``, utils/utils.py:110-111) is accepted as the reference's wrapped model would."""
+        sd = state_dict
+        if sd and all(k.startswith('module.') for k in sd):
+            sd = {k[len('module.'):]: v for k, v in sd.items()}
+        sd = type(sd)((k, v) for k, v in sd.items() if not self._is_e3nn_constant(k, v)) if not isinstance(sd, dict) \
+            else {k: v for k, v in sd.items() if not self._is_e3nn_constant(k, v)}
+        return super().load_state_dict(sd, strict=strict, **kw)
+
     def _edge_mlp_pack(self, seq, rbf, dev, layout):
         """layout: tuple of ('pre', n) / ('sig', n) / ('rbf', n) giving the column order of Linear 0."""
         W, b1 = seq[0].weight.detach(), seq[0].bias.detach()
@@ -768,11 +795,12 @@ class TensorProductScoreModel(nn.Module):
         """Drop-in ``model(data)`` on a collated batch (uploads the batch, runs, returns device tensors)."""
         pl = self.make_plan(data)
         out = self.run_plan(pl, data.complex_t)
-        # side effects the reference's forward leaves on ``data`` (all_atom_score_model.py:373,530)
-        try:
-            data['atom', 'atom'].edge_index = pl.es['aa'].edge_index()
-            data.graph_sigma_emb = pl.sig
-        except Exception:
-            pass
+        # side effects the reference's forward leaves on ``data`` (all_atom_score_model.py:373,453,495,520,530)
+        data['atom', 'atom'].edge_index = pl.es['aa'].edge_index()
+        data.graph_sigma_emb = pl.sig
+        for key in ('ligand', 'receptor', 'atom'):
+            node_t = getattr(data[key], 'node_t', None)
+            if node_t is not None:
+                data[key].node_sigma_emb = self.timestep_emb_func(torch.as_tensor(node_t['tr'], dtype=torch.float32).to(pl.device))
         self._last_plan = pl
         return out

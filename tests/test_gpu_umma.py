@@ -90,13 +90,13 @@ def test_score_model_forward_tensor_core(mode):
         with torch.no_grad():
             pl = m.make_plan(copy.deepcopy(b))
             got = m.run_plan(pl, b.complex_t, return_layers=True)
-            want = om(copy.deepcopy(b))
+            want = om(T.oracle_batch_at(dl, 0.3))
     finally:
         m.conv_mode = 'fp32'
     for l, ((gl, ga, gr), (wl, wa, wr)) in enumerate(zip(pl.last_layers, om._debug['layers'])):
         assert T.rel_err(gl, wl) < TOL[mode] and T.rel_err(ga[:, :wa.shape[1]], wa) < TOL[mode], (l, T.rel_err(gl, wl))
     for g_, w_ in zip(got, want):
-        assert T.rel_err(g_, w_) < 3 * TOL[mode], T.rel_err(g_, w_)
+        assert T.rel_err(g_, w_) < TOL[mode], T.rel_err(g_, w_)
 
 
 @pytest.mark.parametrize('mode', ['bf16x3', 'bf16'])
@@ -110,7 +110,7 @@ def test_sampling_tensor_core_pose_rmsd(mode):
     sch = D.get_t_schedule(steps)
     kw = dict(temp_sampling=[0.9766, 6.0774, 6.7616, 1.4488], temp_psi=[1.5103, 0.8141, 0.7662, 1.3396], temp_sigma_data=0.48884)
     torch.manual_seed(11)
-    ref, _ = S.sampling(copy.deepcopy(dl), om, steps, sch, sch, sch, sch, partial(D.t_to_sigma, args=sa), sa, batch_size=4, **kw)
+    ref, _ = S.sampling(T.oracle_list(dl), om, steps, sch, sch, sch, sch, partial(D.t_to_sigma, args=sa), sa, batch_size=4, **kw)
     torch.manual_seed(11)
     m.conv_mode = mode
     try:

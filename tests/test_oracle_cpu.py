@@ -234,22 +234,6 @@ def test_fixture_graph_shapes_and_collate():
     assert rb.num_graphs == 2 and 'flexResidues' not in rb.node_types and rb['ligand'].pos.shape == (6, 3)
 
 
-def test_oracle_reproduces_golden_forward():
-    """Seeded weights + seeded poses -> the committed oracle outputs (small-t slice to keep the CPU suite short)."""
-    torch.set_num_threads(os.cpu_count())
-    gold = np.load(os.path.join(T.GOLD, 'golden_forward.npz'))
-    m, c, om, oc, sa, ca = T.models(torch.device('cpu'))
-    g = T.graph('3dpf_holo')
-    dl = T.randomized_list(g, 3, sa, seed=0)
-    assert np.allclose(torch.stack([d['ligand'].pos for d in dl]).numpy(), gold['lig_pos'], atol=1e-5)
-    b = T.batch_at(dl, 0.05)
-    with torch.no_grad():
-        tr, rot, tor, sc = om(b)
-    assert om._debug['lr'].shape[1] == int(gold['t05_n_lr']) and om._debug['ll'].shape[1] == int(gold['t05_n_ll'])
-    for got, key in ((tr, 't05_tr'), (rot, 't05_rot'), (tor, 't05_tor'), (sc, 't05_sc')):
-        assert T.rel_err(got, gold[key]) < 1e-4, key
-
-
 def test_oracle_sampler_two_steps_runs_and_moves_poses():
     m, c, om, oc, sa, ca = T.models(torch.device('cpu'), small=True)
     g = inputs.synthetic_complex(3, n_lig=12, n_res=20, flexible_residues=2)
@@ -290,3 +274,35 @@ def test_no_oracle_import_in_product():
         if f.endswith('.py'):
             src = open(os.path.join(pkg, f)).read()
             assert not re.search(r'^\s*(from|import)\s+\.*oracle', src, flags=re.M), f
+
+
+# ------------------------------------------------------------------------------------------- checkpoint loading
+def test_strict_load_of_a_reference_style_checkpoint():
+    """inference.py:434-435 loads with strict=True.  A reference checkpoint also carries the constant buffers of its e3nn
+    modules (output_mask, _w3j_* of the compiled sub-modules, an empty ``weight``): those -- and only those -- are dropped."""
+    sa = utils.score_model_args(ns=16, nv=4, num_conv_layers=2, sigma_embed_dim=32, distance_embed_dim=32, cross_distance_embed_dim=32)
+    m, _, sa, _ = utils.build_models(torch.device('cpu'), score_args=sa, with_confidence=False, seed=1)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    extra = {}
+    for owner in ('tor_bond_conv.tp', 'sc_tor_bond_conv.tp', 'final_tp_tor', 'final_tp_sc_tor'):
+        extra[f'{owner}.output_mask'] = torch.ones(7)
+        extra[f'{owner}.weight'] = torch.Tensor()
+        extra[f'{owner}._compiled_main_left_right._w3j_1_1_0'] = torch.randn(3, 3, 1)
+        extra[f'{owner}._compiled_main_right._w3j_1_1_1'] = torch.randn(3, 3, 3)
+    ckpt = dict(sd, **extra)
+    m2, _, _, _ = utils.build_models(torch.device('cpu'), score_args=sa, with_confidence=False, seed=2)
+    res = m2.load_state_dict(ckpt, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    for k, v in m2.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    m2.load_state_dict({'module.' + k: v for k, v in ckpt.items()}, strict=True)          # saved from DataParallel
+    with pytest.raises(RuntimeError):                                                     # anything else stays strict
+        m2.load_state_dict(dict(ckpt, **{'conv_layers.0.fc.0.extra': torch.zeros(1)}), strict=True)
+    with pytest.raises(RuntimeError):
+        m2.load_state_dict(dict(ckpt, **{'lig_node_embedding.output_mask': torch.zeros(1)}), strict=True)
+    missing = dict(ckpt)
+    del missing['conv_layers.0.fc.0.weight']
+    with pytest.raises(RuntimeError):
+        m2.load_state_dict(missing, strict=True)
+    with pytest.raises(RuntimeError):                                                     # a non-empty tp.weight is learned state
+        m2.load_state_dict(dict(ckpt, **{'tor_bond_conv.tp.weight': torch.zeros(5)}), strict=True)
