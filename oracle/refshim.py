@@ -19,8 +19,8 @@ so3 / torus tables) against ``oracle/*_ref.py``.  What it cannot pin: the third-
 which stays a restatement (``oracle/e3nn_mini.py``, ``oracle/cluster_c.c``) checked by algebraic identities.
 
 ``utils/so3.py`` and ``utils/torus.py`` compute their tables at import time (6 + 2.5 minutes here) and
-cache them as ``.npy`` in the CWD; ``load()`` imports them with the CWD set to ``oracle/_ref/cache`` (git- and
-gpurun-ignored) so the reference's own caching applies.  numpy's global RNG is seeded (``torus_seed``) around the
+cache them as ``.npy`` in the CWD; ``load()`` imports them with the CWD set to ``CACHE`` (``.git/ddp_ref_cache``: outside
+history and outside the gpurun snapshot) so the reference's own caching applies.  numpy's global RNG is seeded (``torus_seed``) around the
 import of ``utils/torus.py`` because its ``score_norm_`` table is a Monte-Carlo estimate from the unseeded global
 RNG.
 
@@ -41,7 +41,11 @@ import torch
 from . import cluster, e3nn_mini, pyg_mini
 
 REF_ROOT = os.environ.get('DDP_REFERENCE_ROOT', '/root/reference')
-CACHE = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref', 'cache')
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# 430 MB of .npy tables the reference caches in its CWD: kept under .git/ (never part of a commit, and outside the snapshot
+# that travels to the GPU box) when the checkout has one, else under oracle/_ref/cache (git-ignored)
+CACHE = os.environ.get('DDP_REF_CACHE') or (os.path.join(_ROOT, '.git', 'ddp_ref_cache') if os.path.isdir(os.path.join(_ROOT, '.git'))
+                                            else os.path.join(_ROOT, 'oracle', '_ref', 'cache'))
 _LOADED = None
 
 

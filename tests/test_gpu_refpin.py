@@ -120,10 +120,11 @@ def test_big_confidence_and_forward_side_effects_vs_reference():
     with torch.no_grad():
         m(b)
     # what forward() leaves on the batch (all_atom_score_model.py:373,453,495,520,530)
-    assert T.rel_err(b['ligand'].node_sigma_emb, z['side_lig_node_sigma_emb']) < 1e-5
-    assert T.rel_err(b['receptor'].node_sigma_emb[:4], z['side_rec_node_sigma_emb']) < 1e-5
-    assert T.rel_err(b['atom'].node_sigma_emb[:4], z['side_atom_node_sigma_emb']) < 1e-5
-    assert T.rel_err(b.graph_sigma_emb, z['side_graph_sigma_emb']) < 1e-5
+    # (fp32 sin / cos of arguments up to embedding_scale * t = 300: the device's and the host's libm differ by ~1e-5)
+    assert T.rel_err(b['ligand'].node_sigma_emb, z['side_lig_node_sigma_emb']) < 1e-4
+    assert T.rel_err(b['receptor'].node_sigma_emb[:4], z['side_rec_node_sigma_emb']) < 1e-4
+    assert T.rel_err(b['atom'].node_sigma_emb[:4], z['side_atom_node_sigma_emb']) < 1e-4
+    assert T.rel_err(b.graph_sigma_emb, z['side_graph_sigma_emb']) < 1e-4
     assert np.array_equal(b['atom', 'atom'].edge_index.cpu().numpy().astype(np.int32), z['side_aa_edge_index'])
 
 
