@@ -329,8 +329,18 @@ __host__ __device__ constexpr int stage_k_of(int ks, bool split) { return ks == 
 #define DDP_UMMA_DUAL 1
 #endif
 // DDP_UMMA_TOKEN = 1: the two issuers hand an issue-order token back and forth, so tiles reach the tensor pipe in tile
-// order.  Without it (0) the big grouped launches failed on B200 ("unspecified launch failure" / hangs, cause not
-// found: every barrier hazard checked out on paper and the watchdog build ran clean) -- debug switch only.
+// order.  The token is REQUIRED for correctness with a ring shorter than two tiles' slabs (4 slots, 3 slabs per tile in the
+// big-model configuration), not only an ordering nicety: an issuer that skips the other issuer's tile tests slot s for
+// fill F while fill F-1 of s is one of the OTHER issuer's slabs, and bulk copies that are in flight together may land out
+// of order (one misses in L2, a later one hits).  If that foreign slab is still in the air the parity test passes on the
+// stale phase; the MMAs read a slot that is being written, their commit frees it early and the producer's
+// mbarrier.arrive.expect_tx hits a barrier whose previous phase is still pending -> "Warp Illegal Instruction" at that
+// SYNCS.ARRIVE.TRANS64 (cuda-gdb, profiles/r2_token0_rootcause.txt; seen only with two conv kernels in flight on two
+// streams, where L2 contention reorders the copies; compute-sanitizer memcheck / synccheck / racecheck are clean for both
+// builds).  The token is released after an issuer has ISSUED its tile -- so after it has seen every slab of that tile
+// land -- and awaited before the first non-blocking parity test of the next tile, which closes the hole.
+// tests/test_umma_protocol_model.py reproduces both the failure (no token, out-of-order landing) and the fix.
+// 0 is a debug switch only.
 #ifndef DDP_UMMA_TOKEN
 #define DDP_UMMA_TOKEN 1
 #endif

@@ -1,9 +1,10 @@
 """Discrete-event model of the mbarrier protocol of ``tpconv_umma_kernel`` (csrc/tpconv_umma.cu), run on the CPU.
 
 The kernel's five roles (TMA producer, two MMA issuers, gather warp, epilogue warps) synchronise only through
-mbarrier phase-parity waits, tcgen05.commit arrivals and an issue-order token.  Two bugs of that protocol were found
-the hard way on the GPU during round 1 (a token that was lapped when one issuer owned two slots in a row; a ring
-shorter than a tile's slabs + 1 letting an issuer wait on a slot two fills behind), so this file restates the
+mbarrier phase-parity waits, tcgen05.commit arrivals and an issue-order token.  Three bugs of that protocol were found
+the hard way on the GPU (a token that was lapped when one issuer owned two slots in a row; a ring shorter than a tile's
+slabs + 1 letting an issuer wait on a slot two fills behind; and, without the token, a parity test that aliases when bulk
+copies land out of order -- test_no_token_aliases_when_bulk_copies_land_out_of_order), so this file restates the
 protocol -- loop for loop, same parities, same barrier counts -- and runs it under many random interleavings,
 checking what the hardware cannot tell us:
 
@@ -47,8 +48,9 @@ def acc_of(tt, nt):                       # tpconv_umma.cu: acc_of()
 
 
 class Model:
-    def __init__(self, items, ng, stages, nbuf, dual, rng, mutate=None):
+    def __init__(self, items, ng, stages, nbuf, dual, rng, mutate=None, in_order_tma=False):
         self.items, self.ng, self.stages, self.nbuf, self.dual, self.rng = items, ng, stages, nbuf, dual, rng
+        self.in_order_tma = in_order_tma
         self.mutate = mutate                  # None, or a deliberately broken / disabled piece of the protocol
         B = Barrier
         self.full = [B(f'full[{s}]', 1) for s in range(stages)]
@@ -79,7 +81,9 @@ class Model:
 
     def fire(self, kind):
         if kind == 'fill':
-            stage, tag = self.fills.pop(0)
+            # bulk copies that are in flight at the same time may land in ANY order (nothing orders their completion;
+            # one slab can miss in L2 while a later one hits) unless the model is told otherwise
+            stage, tag = self.fills.pop(0 if self.in_order_tma else self.rng.randrange(len(self.fills)))
             assert self.slab[stage] is None and self.slab_readers[stage] == 0, 'TMA wrote a slab that is still being read'
             self.slab[stage] = tag
             self.full[stage].arrive()
@@ -279,9 +283,23 @@ def test_model_catches_a_lapped_token():
             Model([rng.choice([2, 4, 6])] * 3, 3, 4, 2, True, random.Random(rng.random()), mutate='token_every_tile').run()
 
 
-def test_protocol_without_the_token_is_still_consistent_in_the_model():
-    """Without the issue-order token the model finds nothing wrong either -- the failures seen on the GPU with
-    -DDDP_UMMA_TOKEN=0 are not a barrier-protocol error this model can express (tpconv_umma.cu keeps the token on)."""
+def test_no_token_aliases_when_bulk_copies_land_out_of_order():
+    """Root cause of the -DDDP_UMMA_TOKEN=0 failures on the GPU (cuda-gdb: "Warp Illegal Instruction" at the producer's
+    ``mbarrier.arrive.expect_tx``, i.e. an arrival on a ``full`` barrier whose previous phase is still pending; only with two
+    conv kernels in flight on two streams, profiles/r2_token0_rootcause.txt).  With a 4-slot ring and 3 slabs per tile
+    an issuer that skips the other issuer's tile tests slot s for fill F while fill F-1 of s is one of the OTHER issuer's
+    slabs.  Nothing orders the completion of bulk copies that are in flight together, so that slab can still be in the
+    air when a later one has landed: the parity test then passes on the stale phase (aliasing), the MMAs read a slot
+    that is being written, their commit frees it early and the producer re-arms a barrier that has not completed.
+    With in-order completion the model (like most runs on the GPU) sees nothing; with out-of-order completion it must.
+    The token closes the hole: it is released after the other issuer has ISSUED its tile, i.e. after it has seen all of that
+    tile's slabs land, and it is awaited before the first non-blocking parity test of the own tile
+    (test_protocol_has_no_deadlock_aliasing_or_hazard runs with out-of-order landing).  Letting the skipping issuer merely
+    look at the foreign slabs' barriers instead does not work: it is not counted in ``empty``, so the slot can be recycled
+    twice before it looks (lapped waiter)."""
     rng = random.Random(5)
-    for _ in range(60):
-        Model([rng.randint(1, 7) for _ in range(4)], 3, 4, 2, True, random.Random(rng.random()), mutate='no_token').run()
+    for _ in range(60):                                                       # in-order landing: consistent
+        Model([rng.randint(1, 7) for _ in range(4)], 3, 4, 2, True, random.Random(rng.random()), mutate='no_token', in_order_tma=True).run()
+    with pytest.raises(AssertionError, match='aliasing|holding|lapped|still being read|more arrivals'):
+        for _ in range(400):
+            Model([rng.randint(2, 7) for _ in range(4)], 3, 4, 2, True, random.Random(rng.random()), mutate='no_token').run()
