@@ -97,12 +97,13 @@ _SIGS = {
     'ddp_row_mlp': (i32, [vp, i32, i32, C.POINTER(MlpLayer), i32, vp, vp, i32, vp]),
     'ddp_tr_rot_head': (i32, [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
     'ddp_pose_update': (i32, [C.POINTER(Pose), C.POINTER(StepCoef), vp]),
+    'ddp_pose_max_ligand_atoms': (i32, []),
     'ddp_pose_update_dev': (i32, [C.POINTER(Pose), vp, vp]),
 }
 EXPORTS = sorted(_SIGS)
 _LIB = None
 # kernels launched per C-ABI call (for the bench's gpu_launches claim)
-KERNELS_PER_CALL = {'ddp_radius': 3, 'ddp_knn_graph': 3, 'ddp_calpha_graph': 3, 'ddp_version': 0, 'ddp_tpconv_pack': 0, 'ddp_tpconv_umma_set_trace': 0}
+KERNELS_PER_CALL = {'ddp_radius': 3, 'ddp_knn_graph': 3, 'ddp_calpha_graph': 3, 'ddp_version': 0, 'ddp_pose_max_ligand_atoms': 0, 'ddp_tpconv_pack': 0, 'ddp_tpconv_umma_set_trace': 0}
 COUNTS = {}
 
 

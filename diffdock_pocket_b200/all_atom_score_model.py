@@ -548,7 +548,7 @@ class TensorProductScoreModel(nn.Module):
         if prof is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        tc = self.conv_mode != 'fp32' and all(it[1].spec.tc_eligible and it[5] is not None and it[7] is not None for it in items)
+        tc = self.conv_mode != 'fp32' and all(tpmod.umma_supported(it[1].spec, self.ns) and it[5] is not None and it[7] is not None for it in items)
         eds = [self._edges_desc(*it[2:9], *it[10:12]) for it in items]
         if tc:
             mode = 0 if self.conv_mode == 'bf16' else 1

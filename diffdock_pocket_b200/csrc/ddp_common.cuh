@@ -10,15 +10,33 @@
         if (e__ != cudaSuccess) return (int)e__;            \
     } while (0)
 
+// Per-device caches: cudaFuncSetAttribute and the SM count belong to a DEVICE, not to the process -- a process that
+// drives several GPUs through this library must opt in / count on each of them.
+constexpr int DDP_MAX_DEVICES = 64;
+static inline int ddp_current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev >= 0 && dev < DDP_MAX_DEVICES ? dev : 0;
+}
 static inline int ddp_num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
+    static int n[DDP_MAX_DEVICES] = {0};
+    const int dev = ddp_current_device();
+    if (n[dev] == 0) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        n[dev] = v > 0 ? v : 148;
     }
-    return n;
+    return n[dev];
+}
+// Opt a kernel in to `bytes` of dynamic shared memory once per device.  `done` is a caller-owned static
+// bool[DDP_MAX_DEVICES] (one per kernel instantiation).
+template <typename K>
+static inline cudaError_t ddp_smem_opt_in(K kernel, size_t bytes, bool *done) {
+    const int dev = ddp_current_device();
+    if (done[dev]) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) done[dev] = true;
+    return e;
 }
 
 __device__ __forceinline__ int ddp_find_segment(const int32_t *__restrict__ ptr, int n_seg, int i) {

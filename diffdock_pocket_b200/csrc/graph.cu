@@ -425,13 +425,10 @@ extern "C" int ddp_knn_graph(const float *x, const int32_t *ptr, int32_t num_exa
         const int qpb = kKnnThreads / kKnnSub;
         const int grid_sub = (n + qpb - 1) / qpb, grid = (n + kKnnThreads - 1) / kKnnThreads;
         const size_t fsm = (size_t)kKnnStage * 3 * sizeof(float) + (size_t)(kKnnFilterCap + 1) * kKnnFC * sizeof(int);
-        static bool configured = false;
-        if (!configured) {
-            cudaError_t e1 = cudaFuncSetAttribute(knn_scan_filter_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
-            cudaError_t e2 = cudaFuncSetAttribute(knn_scan_filter_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
-            if (e1 != cudaSuccess || e2 != cudaSuccess) return (int)(e1 != cudaSuccess ? e1 : e2);
-            configured = true;
-        }
+        static bool configured9[DDP_MAX_DEVICES] = {false}, configured13[DDP_MAX_DEVICES] = {false};
+        cudaError_t e1 = ddp_smem_opt_in(knn_scan_filter_kernel<9>, fsm, configured9);
+        cudaError_t e2 = ddp_smem_opt_in(knn_scan_filter_kernel<13>, fsm, configured13);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) return (int)(e1 != cudaSuccess ? e1 : e2);
         const bool filt = kp == 9 || kp == 13;
         const int fgrid = (n + kKnnFC - 1) / kKnnFC + num_examples;
         if (filt && kp == 9) knn_scan_filter_kernel<9><<<fgrid, kKnnFC * kKnnFSub, fsm, st>>>(x, ptr, num_examples, n, slab, slab_w, counts);

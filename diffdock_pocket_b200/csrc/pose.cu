@@ -122,7 +122,8 @@ pose_update_kernel(ddp_pose_t P, ddp_step_coef_t C_host, const ddp_step_coef_t *
 
     // ---------------- ligand (utils/diffusion_utils.py:37-60) -----------------------------------------
     const int a0 = P.lig_ptr[s], na = P.lig_ptr[s + 1] - a0;
-    if (na <= 0 || na > kMaxLigAtoms) return;
+    if (na <= 0) return;
+    if (na > kMaxLigAtoms) __trap();             // the host checks ddp_pose_max_ligand_atoms(); never skip a ligand silently
     float *pos = P.lig_pos + 3 * (size_t)a0;
     if (tid == 0) {
         float cx = 0.f, cy = 0.f, cz = 0.f;
@@ -211,6 +212,8 @@ pose_update_kernel(ddp_pose_t P, ddp_step_coef_t C_host, const ddp_step_coef_t *
 }
 
 }  // namespace
+
+extern "C" int ddp_pose_max_ligand_atoms(void) { return kMaxLigAtoms; }
 
 extern "C" int ddp_pose_update(const ddp_pose_t *pose, const ddp_step_coef_t *coef, void *stream) {
     if (!pose || !coef) return DDP_E_ARG;

@@ -188,12 +188,13 @@ extern "C" int ddp_tpconv_fp32(const ddp_tpconv_t *conv, const ddp_tpconv_edges_
     const int TE = small ? 8 : 32;
     const size_t smem = ((size_t)(c.k1 + c.hid + c.f_in + c.sh_dim + c.f_out) * (TE + 4) + ctab_len) * sizeof(float) + TE * sizeof(int);
     if (smem > 200 * 1024) return DDP_E_SHAPE;
-    static size_t configured[2] = {0, 0};
-    if (smem > configured[small]) {
+    static size_t configured[DDP_MAX_DEVICES][2] = {{0, 0}};      // largest opt-in so far, per device and tile size
+    size_t &cfg = configured[ddp_current_device()][small];
+    if (smem > cfg) {
         cudaError_t err = small ? cudaFuncSetAttribute(tpconv_fp32_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                                 : cudaFuncSetAttribute(tpconv_fp32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;
-        configured[small] = smem;
+        cfg = smem;
     }
     int tiles = (e.edge_cap + TE - 1) / TE;
     int grid = tiles < 2 * ddp_num_sms() ? tiles : 2 * ddp_num_sms();

@@ -1273,12 +1273,9 @@ template <int NS, int NV, int KS, bool SPLIT>
 static int launch_umma(const umma::Jobs &jobs, int tiles_cap, cudaStream_t st) {
     using C = umma::Cfg<NS, NV, KS, SPLIT>;
     auto kern = umma::tpconv_umma_kernel<NS, NV, KS, SPLIT>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        if (err != cudaSuccess) return (int)err;
-        configured = true;
-    }
+    static bool configured[DDP_MAX_DEVICES] = {false};
+    cudaError_t err = ddp_smem_opt_in(kern, C::SMEM, configured);
+    if (err != cudaSuccess) return (int)err;
     const int grid = tiles_cap < ddp_num_sms() ? tiles_cap : ddp_num_sms();
     kern<<<grid, umma::N_THREADS, C::SMEM, st>>>(jobs);
     DDP_LAUNCH_CHECK();

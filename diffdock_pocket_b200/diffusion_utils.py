@@ -76,6 +76,9 @@ class PoseState:
         n = len(data_list)
         self.n, self.device = n, device
         nl = [g['ligand'].pos.shape[0] for g in data_list]
+        cap = int(_lib.lib().ddp_pose_max_ligand_atoms())
+        if max(nl) > cap:
+            raise ValueError(f'ligand with {max(nl)} atoms: the fused pose update handles at most {cap} atoms per sample')
         na = [g['atom'].pos.shape[0] for g in data_list]
         lo = np.concatenate([[0], np.cumsum(nl)])
         ao = np.concatenate([[0], np.cumsum(na)])

@@ -164,14 +164,23 @@ class Batch(HeteroData):
                     node_types.append(t)
         offsets: Dict[str, List[int]] = {}
         for t in node_types:
-            if any(t not in d._nodes or len(d._nodes[t]) == 0 for d in data_list):
+            has = [t in d._nodes and len(d._nodes[t]) > 0 for d in data_list]
+            if not any(has):
                 continue                                   # absent, or an empty store left behind by data[t] look-ups
+            if not all(has):
+                # PyG cannot collate such a list.  The only optional node type of the path is 'flexResidues' (complexes
+                # without flexible residues in a cross-complex batch): those graphs contribute zero entries.  Anything
+                # else is a malformed input and is reported instead of being dropped silently.
+                if t != 'flexResidues':
+                    missing = [i for i, h in enumerate(has) if not h]
+                    raise ValueError(f"node type {t!r} is missing or empty in graphs {missing} of the batch")
             st = Store()
-            counts = [d._nodes[t].num_nodes for d in data_list]
+            present = [d for d, h in zip(data_list, has) if h]
+            counts = [d._nodes[t].num_nodes if h else 0 for d, h in zip(data_list, has)]
             off = np.concatenate([[0], np.cumsum(counts)])
             offsets[t] = off
-            for k in data_list[0]._nodes[t].keys():
-                vals = [d._nodes[t]._d[k] for d in data_list]
+            for k in present[0]._nodes[t].keys():
+                vals = [d._nodes[t]._d[k] for d in present]
                 if k == 'num_nodes':
                     st._d[k] = int(sum(vals))
                 elif torch.is_tensor(vals[0]):

@@ -268,7 +268,7 @@ class TensorProductConvLayer(nn.Module):
             ew = edge_weight.float().reshape(-1).contiguous()
         n_dev = torch.tensor([E], dtype=torch.int32, device=dev)
         k1 = self.fc[0].in_features
-        use_tc = self.conv_mode != 'fp32' and self.tp.spec.tc_eligible and k1 % 3 == 0 and ew is None
+        use_tc = self.conv_mode != 'fp32' and k1 % 3 == 0 and ew is None and tpmod.umma_supported(self.tp.spec, k1 // 3)
         if use_tc:
             ns = k1 // 3
             pk = self.packed(dev, ns, ns)

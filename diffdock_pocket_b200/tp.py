@@ -84,6 +84,21 @@ def wigner_3j(l1, l2, l3):
     return C / np.linalg.norm(C)
 
 
+# widths the tensor-core kernel is instantiated for (csrc/tpconv_umma.cu pick_cfg): ns -> nv
+UMMA_WIDTHS = {60: 10, 24: 6, 16: 4}
+
+
+def umma_supported(spec, ns):
+    """True if ``ddp_tpconv_pack`` accepts this product: an l <= 1 row-group spec whose scalar / vector output
+    multiplicities are one of the instantiated (ns, nv) pairs.  Anything else runs on the fp32 CUDA-core kernel."""
+    if not spec.tc_eligible or ns not in UMMA_WIDTHS:
+        return False
+    for m, l, _ in spec.out_irreps:
+        if m != (ns if l == 0 else UMMA_WIDTHS[ns]):
+            return False
+    return True
+
+
 # ------------------------------------------------------------------------------------------- groups
 class TpSpec:
     """Row-group description of one tensor product."""

@@ -295,6 +295,10 @@ typedef struct {
     const float *tr_z, *rot_z, *tor_z, *sc_z;
 } ddp_pose_t;
 int ddp_pose_update(const ddp_pose_t *pose, const ddp_step_coef_t *coef, void *stream);
+/* Largest ligand (atoms of one sample) the fused kernel handles: its flexible / rigid copies live in shared memory.
+ * The caller must check its per-sample atom counts against this (the kernel traps on a larger ligand instead of
+ * leaving it unmoved). */
+int ddp_pose_max_ligand_atoms(void);
 /* Same, with the step coefficients read from DEVICE memory (8 floats): lets the whole step be replayed as a
  * CUDA graph while the per-step scalars change. */
 int ddp_pose_update_dev(const ddp_pose_t *pose, const ddp_step_coef_t *coef_dev, void *stream);

@@ -215,6 +215,7 @@ def test_mixed_complex_batch_equals_per_complex_calls():
     from diffdock_pocket_b200 import diffusion_utils as du, inputs as inp, sampling as ps
     m, c, om, oc, sa, ca = T.models(DEV, small=True)
     graphs = [inp.synthetic_complex(11, n_lig=12, n_res=30, flexible_residues=2), inp.synthetic_complex(12, n_lig=25, n_res=45, flexible_residues=3),
+              inp.synthetic_complex(14, n_lig=10, n_res=24, flexible_residues=0),         # no flexResidues store at all
               inp.synthetic_complex(13, n_lig=9, n_res=26, flexible_residues=1)]
     lists = [T.randomized_list(g, 3, sa, seed=20 + i) for i, g in enumerate(graphs)]
     steps = 5

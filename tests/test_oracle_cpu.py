@@ -232,6 +232,15 @@ def test_fixture_graph_shapes_and_collate():
     assert 'flexResidues' not in r and len(r['flexResidues']) == 0 and 'flexResidues' in r
     rb = Batch.from_data_list([copy.deepcopy(r), copy.deepcopy(r)])
     assert rb.num_graphs == 2 and 'flexResidues' not in rb.node_types and rb['ligand'].pos.shape == (6, 3)
+    # cross-complex batch where only some complexes have flexible residues: the others contribute zero entries
+    f = inputs.synthetic_complex(22, n_lig=5, n_res=14, flexible_residues=2)
+    mb = Batch.from_data_list([copy.deepcopy(r), copy.deepcopy(f), copy.deepcopy(r), copy.deepcopy(f)])
+    nf = f['flexResidues'].edge_idx.shape[0]
+    assert mb['flexResidues'].edge_idx.shape[0] == 2 * nf and mb['flexResidues'].batch.tolist() == [1] * nf + [3] * nf
+    bad = copy.deepcopy(f)
+    del bad['atom']
+    with pytest.raises(ValueError, match="node type 'atom' is missing"):
+        Batch.from_data_list([copy.deepcopy(f), bad])
 
 
 def test_oracle_sampler_two_steps_runs_and_moves_poses():
