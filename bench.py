@@ -46,7 +46,15 @@ def parse():
     p.add_argument('--samples', type=int, default=40)
     p.add_argument('--batch-size', type=int, default=20)
     p.add_argument('--inference-steps', type=int, default=20)
-    p.add_argument('--workload', default='3dpf_apo')
+    p.add_argument('--workload', default='3dpf_apo', choices=['3dpf_apo', '3dpf_holo', 'forward64', 'pdbbind_synth', 'screen'],
+                   help='3dpf_apo: BASELINE configs[1] (default, the headline); forward64: configs[2] score-model forward microbench; '
+                        'pdbbind_synth: configs[3] complex-sharded set; screen: configs[4] one pocket x many ligands, ligand-sharded')
+    p.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                   help='3dpf workloads under torchrun: weak = every rank docks its own --samples; strong = --samples split over the ranks')
+    p.add_argument('--complexes', type=int, default=None, help='pdbbind_synth: complexes (default 48; 363 = the whole test-set law); '
+                                                               'screen: ligands (default 192; configs[4] names 10000)')
+    p.add_argument('--no-pipeline', action='store_true', help='pdbbind_synth / screen: serial loop over the complexes (A/B of the software pipeline)')
+    p.add_argument('--no-fp32-grade', action='store_true', help='skip the additional bf16x3 (fp32-grade) resident measurement')
     p.add_argument('--cpu-samples', type=int, default=4)
     p.add_argument('--cpu-steps', type=int, default=3)
     p.add_argument('--no-cpu-baseline', action='store_true')
@@ -108,6 +116,24 @@ def conv_flops(ns, w_numel):
     return 2.0 * ((3 * ns) * (3 * ns) + (3 * ns) * w_numel + w_numel)
 
 
+def conv_bytes(ns, f_in, n_edges):
+    """SURVEY 8(d) minimal fused traffic of one conv: per edge 4 * (ns edge embedding + 2 * ns scalar blocks + f_in gathered
+    features + 3 edge vector + 2 indices)."""
+    return 4.0 * (3 * ns + f_in + 3 + 2) * n_edges
+
+
+def ncu_traffic(args):
+    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the committed ncu --set full capture of
+    THIS command (profiles/r2_ncu_traffic.json, written by scripts/ncu_summary.py); None when there is no capture."""
+    path = os.path.join(ROOT, 'profiles', 'r2_ncu_traffic.json')
+    key = f'{args.workload}:{args.mode}:b{args.batch_size}'
+    if os.path.exists(path):
+        d = json.load(open(path))
+        if key in d:
+            return float(d[key]['dram_bytes_per_launch']), d[key].get('source', path)
+    return None, None
+
+
 def cpu_arm(args, n_samples, n_steps, threads):
     """Oracle port (pure PyTorch fp32 on the host cores) on a bounded sample, scaled to poses/s of the full workload."""
     from diffdock_pocket_b200 import so3, torus, utils
@@ -151,6 +177,133 @@ def run_reference(args):
         'e2e': {'value': value, 'unit': 'poses/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
 
+def _reduce_max(x, dev, world, dist):
+    if world == 1:
+        return x
+    t = torch.tensor([x], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def bench_forward64(args, model, sa, dev, world, rank, local, dist):
+    """BASELINE.json configs[2]: score-model forward microbench, batch of 64 pocket graphs (the 3dpf pocket: receptor_radius 15,
+    atom_max_neighbors 8, c_alpha_max_neighbors 24; README big model), at t = 1.0 (every ligand-residue pair is an edge) and
+    t = 0.05.  A step = one forward of the resident batch; value = graph-forwards / s at t = 1.0."""
+    from diffdock_pocket_b200.hetero import Batch
+    args.samples = 64
+    g, dl = workload(argparse.Namespace(**{**vars(args), 'workload': '3dpf_apo'}), rank)
+    with torch.no_grad():
+        pl = model.make_plan(Batch.from_data_list(dl), graphs=dl)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = {}
+    sampler = ClockSampler(local)
+    sampler.start()
+    for tag, t in (('t1.0', 1.0), ('t0.05', 0.05)):
+        ct = {k: torch.full((64,), t) for k in ('tr', 'rot', 'tor', 'sc_tor')}
+        with torch.no_grad():
+            for _ in range(max(args.warmup, 3)):
+                model.run_plan(pl, ct)
+            torch.cuda.synchronize()
+            ms = []
+            for _ in range(max(args.steps, 3)):
+                flush.fill_(0)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                model.run_plan(pl, ct)
+                e1.record()
+                torch.cuda.synchronize()
+                ms.append(e0.elapsed_time(e1))
+            model.profile = []
+            model.run_plan(pl, ct)
+            torch.cuda.synchronize()
+            conv_ms = sum(a.elapsed_time(b) for a, b, _ in model.profile)
+            conv_fl = sum(conv_flops(ns, w) * int(es.n_dev.item()) for _, _, convs in model.profile for (w, es, ns) in convs)
+            model.profile = None
+        m = _reduce_max(float(np.median(ms)), dev, world, dist)
+        out[tag] = {'ms_per_forward': m, 'graph_forwards_per_s': world * 64 / (m / 1000.0), 'conv_ms': conv_ms,
+                    'conv_tflops': conv_fl / (conv_ms * 1e-3) / 1e12, 'edges': {k: int(pl.es[k].n_dev.item()) for k in ('ll', 'lr', 'la', 'aa', 'rr', 'ar')}}
+    sampler.stop_flag = True
+    if rank == 0:
+        peak_tf, hbm, peak_src = peaks()
+        print(json.dumps({
+            'metric': 'score-model graph-forwards/sec (batch 64 forward microbench)', 'value': out['t1.0']['graph_forwards_per_s'], 'unit': 'graph-forwards/s',
+            'n_gpus': world, 'steps': max(args.steps, 3), 'warmup': max(args.warmup, 3), 'ms_per_step': out['t1.0']['ms_per_forward'], 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': args.mode, 'data': 'synthetic',
+            'config': {'workload': 'forward64: 64 x 3dpf pocket graph (BASELINE.json configs[2]), README big model, resident batch, t = 1.0 (value) and t = 0.05',
+                       'conv_mode': args.mode, 'l2': '256 MiB flush before every timed forward'},
+            'clocks': sampler.summary(), 'detail': out,
+            'roofline': {'bound': 'tensor', 'achieved': out['t1.0']['conv_tflops'], 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': out['t1.0']['conv_tflops'] / peak_tf,
+                         'traffic': None, 'peak_source': peak_src}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_set(args, model, conf, sa, ca, dev, world, rank, local, dist):
+    """BASELINE.json configs[3] (``pdbbind_synth``: complexes whose ligand sizes follow the PDBBind test set, 40 samples each,
+    complexes split over the ranks like np.array_split) and configs[4] (``screen``: one pocket x many procedural ligands x 10
+    samples, ligands split over the ranks, final all-gather of the best confidences + global top-k).  The whole job goes
+    through the host mirror of inference.py (graphs on the host in, ranked poses on the host out): value == e2e."""
+    from diffdock_pocket_b200 import inference, inputs
+    screen = args.workload == 'screen'
+    n = args.complexes or (192 if screen else 48)
+    t_gen = time.time()
+    if screen:
+        pocket = inputs.synthetic_complex(0, n_lig=30, n_res=139, flexible_residues=7, name='pocket')
+        sizes = inputs.pdbbind_test_sizes()
+        graphs = [inputs.with_ligand(pocket, 1000 + i, sizes[i % len(sizes)], name=f'ligand{i}') for i in range(n)]
+        spc = 10
+    else:
+        graphs = inputs.pdbbind_synth_set(n)
+        spc = args.samples
+    t_gen = time.time() - t_gen
+    rows = [dict(complex_name=g.name, complex_graph=g) for g in graphs]
+    iargs = inference.default_args(samples_per_complex=spc, batch_size=args.batch_size, inference_steps=args.inference_steps)
+    sampler = ClockSampler(local)
+
+    def one_pass(sub):
+        np.random.seed(1 + rank)
+        torch.manual_seed(1 + rank)
+        return inference.infer_sharded(sub, model, iargs, sa, dev, filtering_model=conf, filtering_model_args=ca,
+                                       batch_complexes=screen, pipeline=not args.no_pipeline)
+    for _ in range(max(1, min(args.warmup, 2))):                       # warm-up on a small prefix (lazy init, allocator, weight images)
+        one_pass(rows[:max(2 * world, 2)])
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    res, best, ok = one_pass(rows)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.time() - t0
+    if world > 1:
+        dist.barrier()
+    sampler.stop_flag = True
+    ms = _reduce_max(e0.elapsed_time(e1), dev, world, dist)
+    wall = _reduce_max(wall, dev, world, dist)
+    poses = n * spc
+    if rank == 0:
+        order = torch.argsort(best, descending=True)
+        print(json.dumps({
+            'metric': 'docked poses/sec (20-step reverse diffusion)', 'value': poses / (ms / 1000.0), 'unit': 'poses/s', 'n_gpus': world,
+            'steps': 1, 'warmup': max(1, min(args.warmup, 2)), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': args.mode, 'data': 'synthetic',
+            'config': {'workload': (f'screen: one synthetic pocket (139 residues, 7 flexible) x {n} procedural ligands (PDBBind size law) x {spc} samples, '
+                                    f'{args.inference_steps} steps + confidence, ligands split over the ranks, 2 ligands per sampler call (BASELINE.json configs[4]; it names 10000 ligands)'
+                                    if screen else
+                                    f'pdbbind_synth: {n} synthetic complexes (ligand sizes of the PDBBind test set; 363 = the whole set) x {spc} samples, batch {args.batch_size}, '
+                                    f'{args.inference_steps} steps + confidence, complexes split over the ranks (BASELINE.json configs[3])'),
+                       'pipeline': not args.no_pipeline, 'conv_mode': args.mode, 'generation_s': t_gen,
+                       'l2': 'every complex brings new activations; weights (> 400 MB over the layers) exceed L2'},
+            'clocks': sampler.summary(), 'wall_s': wall, 'succeeded_on_rank0': ok,
+            'top3': [(int(i), round(float(best[i]), 4)) for i in order[:3]],
+            'e2e': {'value': poses / (wall * 1000.0 / 1000.0), 'unit': 'poses/s', 'h2d_bytes_per_step': int(model.static_h2d_bytes), 'd2h_bytes_per_step': None}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == 'reference':
@@ -178,7 +331,21 @@ def main():
             os.close(saved)
     model, conf, sa, ca = utils.build_models(dev, seed=0)
     model.conv_mode = conf.conv_mode = args.mode
-    g, dl0 = workload(args, rank)
+    if args.workload == 'forward64':
+        return bench_forward64(args, model, sa, dev, world, rank, local, dist)
+    if args.workload in ('pdbbind_synth', 'screen'):
+        return bench_set(args, model, conf, sa, ca, dev, world, rank, local, dist)
+    total_samples = args.samples * (world if args.scaling == 'weak' else 1)
+    if args.scaling == 'strong':
+        # one complex's samples split over the ranks (np.array_split rule); every rank still draws the same initial poses
+        from diffdock_pocket_b200.parallel import shard_range
+        g, dl_all = workload(args, 0)
+        lo, hi = shard_range(args.samples, rank, world)
+        dl0 = dl_all[lo:hi]
+        args.samples = hi - lo
+        assert args.samples > 0, 'more ranks than samples'
+    else:
+        g, dl0 = workload(args, rank)
     sch = du.get_t_schedule('expbeta', args.inference_steps)
     t2s = partial(du.t_to_sigma, args=sa)
     kw = dict(confidence_model=conf, filtering_model_args=ca, batch_size=args.batch_size, **TEMP)
@@ -191,13 +358,8 @@ def main():
 
     def gather_rank(poses, confidence):
         """The single collective of the path: all-gather final poses + confidences, rank by confidence."""
-        if world == 1:
-            return torch.argsort(confidence, descending=True)
-        pg = [torch.empty_like(poses) for _ in range(world)]
-        cg = [torch.empty_like(confidence) for _ in range(world)]
-        dist.all_gather(pg, poses)
-        dist.all_gather(cg, confidence)
-        return torch.argsort(torch.cat(cg), descending=True)
+        from diffdock_pocket_b200.parallel import gather_and_rank
+        return gather_and_rank(poses, confidence)[2]
 
     # ---- e2e pass through the public API (host graphs in, host poses out) --------------------------------
     def e2e_step(dl):
@@ -210,19 +372,21 @@ def main():
     chunks = [list(range(i, min(i + args.batch_size, args.samples))) for i in range(0, args.samples, args.batch_size)]
     # independent mini-batches alternate between two streams, exactly as sampling() runs them
     streams = [torch.cuda.Stream(device=dev) for _ in range(2)] if len(chunks) > 1 and not args.single_stream else [None]
-    with torch.no_grad():
-        runners = [ps.StepRunner(model, [dl0[i] for i in idx], True, False, use_graph=not args.no_graph, stream=streams[k % len(streams)])
-                   for k, idx in enumerate(chunks)]
-        cplans = [conf.make_plan(Batch.from_data_list([dl0[i] for i in idx])) for idx in chunks]
-    plans = [r.pl for r in runners]
-    init = [(pl.lig_pos.clone(), pl.atom_pos.clone()) for pl in plans]
+    def build_resident():
+        with torch.no_grad():
+            rs = [ps.StepRunner(model, [dl0[i] for i in idx], True, False, use_graph=not args.no_graph, stream=streams[k % len(streams)])
+                  for k, idx in enumerate(chunks)]
+            cps = [conf.make_plan(Batch.from_data_list([dl0[i] for i in idx])) for idx in chunks]
+        return rs, cps, [r.pl for r in rs], [(r.pl.lig_pos.clone(), r.pl.atom_pos.clone()) for r in rs]
+    runners, cplans, plans, init = build_resident()
     N = args.samples
     T_tot, S_tot = sum(r.T for r in runners), sum(r.S for r in runners)
     noise = torch.randn(args.inference_steps, 6 * N + T_tot + S_tot, generator=torch.Generator().manual_seed(3))
     coefs = [ps.step_coefficients(t_idx, args.inference_steps, (sch,) * 4, t2s, sa, False, TEMP['temp_sampling'], TEMP['temp_psi'],
                                   TEMP['temp_sigma_data'], True) for t_idx in range(args.inference_steps)]
 
-    def resident_step():
+    def resident_step(runners=None, cplans=None, plans=None, init=None):
+        runners, cplans, plans, init = runners or R0[0], cplans or R0[1], plans or R0[2], init or R0[3]
         with torch.no_grad():
             for pl, (lp, ap) in zip(plans, init):
                 pl.lig_pos.copy_(lp)
@@ -249,6 +413,8 @@ def main():
             for r in runners:
                 r.sync_out()
             return gather_rank(torch.cat([pl.lig_pos for pl in plans]).reshape(N, -1, 3), torch.cat(cs))
+
+    R0 = (runners, cplans, plans, init)
 
     # gpu_launches: kernels of ONE bench step, counted on an eager (non-graph) pass of identical work
     eager = [ps.StepRunner(model, [dl0[i] for i in idx], True, False, use_graph=False) for idx in chunks[:1]]
@@ -282,7 +448,33 @@ def main():
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    value = world * args.samples / (ms / 1000.0)
+    value = total_samples / (ms / 1000.0)
+
+    # ---- fp32-grade leg: the same resident step with the bf16x3 tensor-core conv (hi/lo split operands, fp32-grade products:
+    # the mode that meets the 1e-4 per-layer gate), so that the driver's record carries both numbers
+    fp32_grade = None
+    if args.mode == 'bf16' and not args.no_fp32_grade:
+        model.conv_mode = conf.conv_mode = 'bf16x3'
+        R3 = build_resident()
+        for _ in range(max(1, min(args.warmup, 2))):
+            resident_step(*R3)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n3 = max(1, min(args.steps, 3))
+        e0.record()
+        for _ in range(n3):
+            resident_step(*R3)
+            flush.fill_(0)
+        e1.record()
+        barrier()
+        ms3 = e0.elapsed_time(e1) / n3
+        if world > 1:
+            t = torch.tensor([ms3], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms3 = float(t.item())
+        fp32_grade = {'value': total_samples / (ms3 / 1000.0), 'unit': 'poses/s', 'ms_per_step': ms3, 'conv_mode': 'bf16x3', 'steps': n3}
+        del R3
+        model.conv_mode = conf.conv_mode = args.mode
 
     # e2e: same metric through sampling() with host buffers
     n_e2e = max(1, min(args.steps, 3))
@@ -290,17 +482,22 @@ def main():
     for _ in range(2):                                               # untimed: lazy initialisation, allocator, page cache
         e2e_step(e2e_inputs.pop())
     barrier()
+    b0 = model.static_h2d_bytes + conf.static_h2d_bytes
     t0 = time.time()
     for _ in range(n_e2e):
         e2e_step(e2e_inputs.pop())
     barrier()
     e2e_ms = (time.time() - t0) * 1000.0 / n_e2e
+    static_bytes_per_call = (model.static_h2d_bytes + conf.static_h2d_bytes - b0) / n_e2e
     if world > 1:
         t = torch.tensor([e2e_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
-    h2d = sum(t.numel() * t.element_size() for pl in plans for t in (pl.lig_pos, pl.atom_pos, pl.rec_pos, pl.lig_static, pl.atom_static, pl.rec_static))
-    h2d += sum(pl.NR * 1281 * 4 for pl in plans) + noise.numel() * 4 + sum(pl.step_in.numel() * 4 for pl in plans) * args.inference_steps
+    # bytes sampling() copies host->device per call: positions + index / edge tensors of every plan, the static node features
+    # as counted by the model (once per complex, not per sample), the per-step scalar / noise rows
+    h2d = sum(t.numel() * t.element_size() for pl in plans for t in (pl.lig_pos, pl.atom_pos, pl.rec_pos, pl.bond_attr, pl.lig_batch, pl.rec_batch,
+                                                                      pl.atom_batch, pl.es['rr'].edge, pl.es['ar'].edge, pl.es['ll'].edge[:pl.Eb]))
+    h2d += static_bytes_per_call + sum(pl.step_in.numel() * 4 for pl in plans) * args.inference_steps
     d2h = sum((pl.NL + pl.NA) * 12 for pl in plans) + N * 4
 
     # ---- roofline of the dominant kernel: instrumented forward (events around every fused conv launch) -----
@@ -313,20 +510,27 @@ def main():
         with torch.no_grad():
             model.run_plan(pl, ct)
         torch.cuda.synchronize()
-        tot_ms, tot_fl, n_l = 0.0, 0.0, 0
+        tot_ms, tot_fl, tot_bytes, n_l, li = 0.0, 0.0, 0.0, 0, 0
+        from diffdock_pocket_b200 import tp as tpmod
+        dims = [tpmod.irreps_dim(tpmod.parse_irreps(q)) for q in model.irrep_seq]
         for (e0, e1, convs) in model.profile:
             tot_ms += e0.elapsed_time(e1)
             tot_fl += sum(conv_flops(ns, w_numel) * int(es.n_dev.item()) for (w_numel, es, ns) in convs)
+            tot_bytes += sum(conv_bytes(ns, dims[min(li, 3)], int(es.n_dev.item())) for (w_numel, es, ns) in convs)
+            li += 1
             n_l += 1
         model.profile = None
         ach = tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
         # DRAM bytes of one conv launch (dram__bytes_read + write, ncu --set full of the grouped layer-3 launch of this
         # same batch: profiles/r1_ncu_umma_v27_summary.txt); far below the algorithmic 1.2 kB/edge because gathered
         # node rows and the weight image are served by L2
-        traffic = 224.1e6 if (args.mode == 'bf16' and args.workload == '3dpf_apo' and args.batch_size == 20) else None
+        traffic, traffic_src = ncu_traffic(args)
         roof = {'bound': 'tensor', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'traffic': traffic,
                 'kernel': 'tpconv_umma_kernel' if args.mode != 'fp32' else 'tpconv_fp32_kernel', 'launches_measured': n_l,
-                'peak_source': peak_src, 'conv_share_of_forward_ms': tot_ms}
+                'peak_source': peak_src, 'conv_share_of_forward_ms': tot_ms, 'traffic_source': traffic_src,
+                # BASELINE.json's metric also names "TP-conv GB/s": the fused kernel's ALGORITHMIC bytes (edge
+                # embedding + two scalar blocks + gathered features + indices per edge, output rows once) over its time
+                'algorithmic_gbs': tot_bytes / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0, 'hbm_peak_gbs': hbm}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, dt = cpu_arm(args, args.cpu_samples, args.cpu_steps, os.cpu_count())
@@ -335,13 +539,16 @@ def main():
     if rank == 0:
         print(json.dumps({
             'metric': 'docked poses/sec (20-step reverse diffusion)', 'value': value, 'unit': 'poses/s', 'n_gpus': world,
-            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': args.scaling,
             'vs_baseline': None, 'dtype': {'bf16': 'bf16', 'bf16x3': 'bf16x3 (fp32-grade)', 'fp32': 'f32'}[args.mode], 'data': 'synthetic',
-            'config': {'workload': f'{args.workload}: {args.samples} samples, batch {args.batch_size}, {args.inference_steps} reverse-diffusion steps + confidence pass, per GPU (BASELINE.json configs[1])',
+            'config': {'workload': (f'{args.workload}: {args.samples} samples, batch {args.batch_size}, {args.inference_steps} reverse-diffusion steps + confidence pass, per GPU (BASELINE.json configs[1])'
+                                    if args.scaling == 'weak' else
+                                    f'{args.workload}: {total_samples} samples of ONE complex split over {world} GPU(s) ({args.samples} on rank 0), batch {args.batch_size}, {args.inference_steps} steps + confidence pass (BASELINE.json configs[1], strong scaling)'),
                        'weights': 'random init of the README big score model (ns=60 nv=10 6 layers lmax=1) + confidence model (no checkpoint offline)', 'conv_mode': args.mode, 'streams': len(streams),
                        'l2': 'weights + activations (>400 MB) exceed L2; 256 MiB flush between timed iterations'},
             'clocks': sampler.summary(), 'gpu_launches': launches,
-            'e2e': {'value': world * args.samples / (e2e_ms / 1000.0), 'unit': 'poses/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
+            'fp32_grade': fp32_grade,
+            'e2e': {'value': total_samples / (e2e_ms / 1000.0), 'unit': 'poses/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
             'roofline': roof, 'cpu_baseline': cpu}))
     if world > 1:
         dist.destroy_process_group()

@@ -82,6 +82,7 @@ _SIGS = {
     'ddp_edge_embed': (i32, [vp, vp, vp, i32, vp, vp, vp, i32, vp, C.POINTER(EdgeMlp), vp, vp, vp]),
     'ddp_graph_sigma_proj': (i32, [vp, i32, f32, vp, i32, vp, vp, i32, i32, vp, vp, vp]),
     'ddp_node_init': (i32, [vp, vp, vp, i32, i32, vp, i32, vp]),
+    'ddp_node_static_embed': (i32, [vp, i32, i32, vp, vp, vp, i32, vp, vp, i32, vp, vp]),
     'ddp_tpconv_fp32': (i32, [C.POINTER(TpConv), C.POINTER(TpEdges), vp, vp]),
     'ddp_tpconv_pack': (C.c_int64, [C.POINTER(TpConv), C.POINTER(TpGroup), vp, vp, vp, vp, vp, i32, vp]),
     'ddp_tpconv_umma': (i32, [C.POINTER(TpConv), vp, i32, C.POINTER(TpEdges), vp, vp]),

@@ -22,7 +22,10 @@ from torch import nn
 
 from . import _lib, so3, torus, tp as tpmod
 from ._lib import ptr
-from .score_model import (FEATURE_DIMS, AtomEncoder, GaussianSmearing, OldAtomEncoder, TensorProductConvLayer, _TP)
+from .score_model import (FEATURE_DIMS, AtomEncoder, GaussianSmearing, OldAtomEncoder, TensorProductConvLayer, _TP, static_embed)
+
+
+STATIC_KEYS = (('ligand', 'x'), ('receptor', 'x'), ('atom', 'x'))      # collate skips these when the plan gets ``graphs``
 
 
 def _mlp(i, h, o, dropout):
@@ -302,6 +305,9 @@ class TensorProductScoreModel(nn.Module):
             if self.flexible_sidechains:
                 em['sc'] = self._edge_mlp_pack(self.sidechain_final_edge_embedding, self.lig_distance_expansion, dev, (('rbf', dd),))
         P['em'], P['proj_names'] = em, proj_names
+        P['static'] = {k: enc.static_pack(dev) for k, enc in (('lig', self.lig_node_embedding), ('rec', self.rec_node_embedding),
+                                                               ('atom', self.atom_node_embedding))}
+        self._static_cache = {}
         P['proj_w'], P['proj_b'] = torch.stack(ws).contiguous(), torch.stack(bs).contiguous()
         half = sd // 2
         P['freq'] = torch.exp(torch.arange(half, dtype=torch.float32) * -(np.log(10000) / (half - 1))).to(dev)
@@ -338,8 +344,55 @@ class TensorProductScoreModel(nn.Module):
         return P
 
     # ------------------------------------------------------------------------------------------ plan
-    def make_plan(self, data, extra_step_floats=0):
-        """Upload one collated batch and allocate all workspaces (no per-step allocation afterwards)."""
+    STATIC_CACHE_SIZE = 256
+
+    def static_for(self, graph):
+        """Time-independent node embeddings of ONE complex (``ddp_node_static_embed``: AtomEncoder sums + the part of its
+        Linear that does not see sigma, incl. the 1280-wide ESM product) on the device: (ligand, atom, receptor) parts, each
+        cached on its own -- a screening run re-uses the pocket's atom / residue embeddings across all ligands."""
+        P = self.packed()
+        rx = graph['receptor'].x
+        return (self._static_one('lig', graph['ligand'].x, lambda x: (x, None)),
+                self._static_one('atom', graph['atom'].x, lambda x: (x, None)),
+                self._static_one('rec', rx, lambda x: ((x * 0 if self.no_aminoacid_identities else x)[:, :1],
+                                                      (x * 0 if self.no_aminoacid_identities else x)[:, 1:] if self.lm_embedding_type else None)))
+
+    static_h2d_bytes = 0          # bytes of static node features uploaded so far (bench.py's e2e accounting)
+
+    def _static_one(self, kind, x, split):
+        """Cache levels: (1) identity of the feature tensor (samples made by ``hetero.sample_copies`` share it; the entry
+        keeps the tensor alive, so its address cannot be reused by another complex while it is cached); (2) content --
+        deep-copied samples (the reference's inference.py:135) have equal values in different storage: same shape and
+        fingerprint, then verified exactly with ``torch.equal`` (host reads instead of an upload + embedding per sample)."""
+        P = self.packed()
+        cache = self._static_cache.setdefault(kind, {})
+        key = (x.data_ptr(), tuple(x.shape), x._version)
+        hit = cache.get(key)
+        if hit is not None:
+            cache[key] = cache.pop(key)                                # most recently used last
+            return hit[0]
+        f = x.reshape(-1)
+        fp = (tuple(x.shape), tuple(f[::max(1, f.numel() // 61)][:64].tolist()))
+        out = None
+        for out2, keep2, fp2 in reversed(list(cache.values())):
+            if fp2 == fp and torch.equal(keep2, x):
+                out = out2
+                break
+        if out is None:
+            cat, lm = split(x)
+            with torch.no_grad():
+                out = static_embed(P['static'][kind], cat, lm, P['device'])
+            self.static_h2d_bytes += 8 * cat.numel() + (4 * lm.numel() if lm is not None else 0)
+        cache[key] = (out, x, fp)
+        while len(cache) > self.STATIC_CACHE_SIZE:
+            cache.pop(next(iter(cache)))
+        return out
+
+    def make_plan(self, data, extra_step_floats=0, graphs=None):
+        """Upload one collated batch and allocate all workspaces (no per-step allocation afterwards).
+        ``graphs``: the per-sample graphs ``data`` was collated from -- their static node features are then taken per
+        complex from ``static_for`` (uploaded and embedded once per complex, not once per sample) and ``data`` may have
+        been collated without the ``x`` matrices (``Batch.from_data_list(..., skip=STATIC_KEYS)``)."""
         P = self.packed()
         dev = P['device']
         ns, sh_dim = self.ns, self.sh_dim
@@ -368,12 +421,21 @@ class TensorProductScoreModel(nn.Module):
         pl.atom_pos = atom.pos.to(**f32).contiguous().clone()
         # static node-embedding parts (time independent, once per complex)
         with torch.no_grad():
-            rx = rec.x.to(dev)
-            if self.no_aminoacid_identities:
-                rx = rx * 0
-            pl.lig_static = self.lig_node_embedding.static_part(lig.x.to(dev)).float().contiguous()
-            pl.atom_static = self.atom_node_embedding.static_part(atom.x.to(dev)).float().contiguous()
-            pl.rec_static = self.rec_node_embedding.static_part(rx[:, :1], rx[:, 1:].float() if self.lm_embedding_type else None).float().contiguous()
+            if graphs is not None:
+                assert len(graphs) == B
+                parts = [self.static_for(g) for g in graphs]
+                pl.lig_static, pl.atom_static, pl.rec_static = (torch.cat([q[i] for q in parts], 0) if B > 1 else parts[0][i] for i in range(3))
+                pl.static_h2d_bytes = 0
+            else:
+                rx = rec.x
+                if self.no_aminoacid_identities:
+                    rx = rx * 0
+                pl.lig_static = static_embed(P['static']['lig'], lig.x, None, dev)
+                pl.atom_static = static_embed(P['static']['atom'], atom.x, None, dev)
+                pl.rec_static = static_embed(P['static']['rec'], rx[:, :1], rx[:, 1:] if self.lm_embedding_type else None, dev)
+                pl.static_h2d_bytes = 8 * (lig.x.numel() + atom.x.numel() + rx.shape[0]) + 4 * rx.shape[0] * (rx.shape[1] - 1)
+                self.static_h2d_bytes += pl.static_h2d_bytes
+            assert pl.lig_static.shape[0] == pl.NL and pl.atom_static.shape[0] == pl.NA and pl.rec_static.shape[0] == pl.NR
         F = tpmod.irreps_dim(tpmod.parse_irreps(self.irrep_seq[3]))
         pl.F = F
         pl.x = {k: [torch.zeros(n, F, **f32), torch.zeros(n, F, **f32)] for k, n in (('l', pl.NL), ('r', pl.NR), ('a', pl.NA))}

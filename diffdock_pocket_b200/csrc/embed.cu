@@ -40,6 +40,44 @@ __global__ void node_init_kernel(const float *__restrict__ sp, const float *__re
 }
 
 // ---------------------------------------------------------------------------------------------
+// Static (time-independent) part of AtomEncoder (models/score_model.py:74-82), once per complex:
+//   out[n][:] = (sum_k Emb_k[cat[n][k]]) W_emb + lm[n][:] W_lm
+// One block per node: the summed embedding row and the language-model row (1280 floats) are staged in shared memory,
+// thread o accumulates output channel o over K with weight reads coalesced across the block.
+constexpr int kStaticThreads = 64;
+__global__ void __launch_bounds__(kStaticThreads)
+node_static_embed_kernel(const int64_t *__restrict__ cat, int n_cat, const float *__restrict__ table,
+                         const int32_t *__restrict__ table_off, const float *__restrict__ lm, int n_lm,
+                         const float *__restrict__ w_emb_t, const float *__restrict__ w_lm_t, int ns,
+                         float *__restrict__ out) {
+    extern __shared__ float s_row[];               // [ns | n_lm]
+    const int node = blockIdx.x, tid = threadIdx.x;
+    for (int c = tid; c < ns; c += kStaticThreads) {
+        float h = 0.f;
+        for (int k = 0; k < n_cat; ++k)            // same summation order as the reference loop over the embedding tables
+            h += table[((size_t)table_off[k] + (size_t)cat[(size_t)node * n_cat + k]) * ns + c];
+        s_row[c] = h;
+    }
+    for (int k = tid; k < n_lm; k += kStaticThreads) s_row[ns + k] = lm[(size_t)node * n_lm + k];
+    __syncthreads();
+    for (int o = tid; o < ns; o += kStaticThreads) {
+        float a0 = 0.f, a1 = 0.f;
+        if (w_emb_t != nullptr) {
+            for (int k = 0; k < ns; ++k) a0 = fmaf(s_row[k], __ldg(w_emb_t + (size_t)k * ns + o), a0);
+        } else {
+            a0 = s_row[o];                         // no Linear over the embedding sum (OldAtomEncoder without LM features)
+        }
+        int k = 0;
+        for (; k + 1 < n_lm; k += 2) {             // two chains: 1280 dependent FMAs would be latency bound
+            a0 = fmaf(s_row[ns + k], __ldg(w_lm_t + (size_t)k * ns + o), a0);
+            a1 = fmaf(s_row[ns + k + 1], __ldg(w_lm_t + (size_t)(k + 1) * ns + o), a1);
+        }
+        if (k < n_lm) a0 = fmaf(s_row[ns + k], __ldg(w_lm_t + (size_t)k * ns + o), a0);
+        out[(size_t)node * ns + o] = a0 + a1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Edge geometry + embedding: 32 edges per block, 128 threads = 2 edge halves x 64 output lanes.
 constexpr int kEE = 32;
 constexpr int kEEThreads = 128;
@@ -579,6 +617,19 @@ extern "C" int ddp_node_init(const float *static_part, const float *u, const int
     if (!static_part || !u || !graph_of || !out) return DDP_E_ARG;
     if (n <= 0) return 0;
     node_init_kernel<<<grid_for((size_t)n * ns, 256), 256, 0, (cudaStream_t)stream>>>(static_part, u, graph_of, n, ns, out, ld_out);
+    DDP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ddp_node_static_embed(const int64_t *cat, int32_t n, int32_t n_cat, const float *table, const int32_t *table_off,
+                                     const float *lm, int32_t n_lm, const float *w_emb_t, const float *w_lm_t, int32_t ns,
+                                     float *out, void *stream) {
+    if (!cat || !table || !table_off || !out || n_cat <= 0 || ns <= 0) return DDP_E_ARG;
+    if (n_lm > 0 && (!lm || !w_lm_t)) return DDP_E_ARG;
+    if (n_lm < 0 || (size_t)(ns + n_lm) * sizeof(float) > 40 * 1024) return DDP_E_SHAPE;
+    if (n <= 0) return 0;
+    node_static_embed_kernel<<<n, kStaticThreads, (size_t)(ns + n_lm) * sizeof(float), (cudaStream_t)stream>>>(
+        cat, n_cat, table, table_off, lm, n_lm, w_emb_t, w_lm_t, ns, out);
     DDP_LAUNCH_CHECK();
     return 0;
 }

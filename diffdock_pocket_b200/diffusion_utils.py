@@ -151,8 +151,16 @@ class PoseState:
         cf = _lib.StepCoef(*[float(v) for v in coef])
         _lib.check(_lib.lib().ddp_pose_update(C.byref(P), C.byref(cf), _lib.stream_ptr()), 'ddp_pose_update')
 
+    def stage_to_host(self):
+        """Enqueue asynchronous copies of the poses into pinned host buffers (``write_back`` then reads those; the caller
+        synchronises with an event recorded after this call)."""
+        self._host = (torch.empty(self.lig_pos.shape, dtype=self.lig_pos.dtype, pin_memory=True),
+                      torch.empty(self.atom_pos.shape, dtype=self.atom_pos.dtype, pin_memory=True))
+        self._host[0].copy_(self.lig_pos, non_blocking=True)
+        self._host[1].copy_(self.atom_pos, non_blocking=True)
+
     def write_back(self, data_list):
-        lp, apos = self.lig_pos.cpu(), self.atom_pos.cpu()
+        lp, apos = getattr(self, '_host', None) or (self.lig_pos.cpu(), self.atom_pos.cpu())
         for s, g in enumerate(data_list):
             g['ligand'].pos = lp[self.lig_off[s]:self.lig_off[s + 1]].clone()
             g['atom'].pos = apos[self.atom_off[s]:self.atom_off[s + 1]].clone()

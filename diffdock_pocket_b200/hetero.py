@@ -153,7 +153,9 @@ class Batch(HeteroData):
     the last dim and are incremented by the cumulative node count; per node type ``batch``/``ptr``."""
 
     @staticmethod
-    def from_data_list(data_list: List[HeteroData]) -> 'Batch':
+    def from_data_list(data_list: List[HeteroData], skip=()) -> 'Batch':
+        """``skip``: (node type, attribute) pairs that are NOT concatenated (the sampler passes the static feature
+        matrices -- 1281 floats per residue -- to the model per complex instead of per sample)."""
         b = Batch()
         n = len(data_list)
         b._glob['num_graphs'] = n
@@ -180,6 +182,8 @@ class Batch(HeteroData):
             off = np.concatenate([[0], np.cumsum(counts)])
             offsets[t] = off
             for k in present[0]._nodes[t].keys():
+                if (t, k) in skip:
+                    continue
                 vals = [d._nodes[t]._d[k] for d in present]
                 if k == 'num_nodes':
                     st._d[k] = int(sum(vals))
@@ -224,3 +228,26 @@ class DataLoader:
 
     def __len__(self):
         return (len(self.data_list) + self.batch_size - 1) // self.batch_size
+
+
+def sample_copies(graph, n):
+    """``n`` graphs for ``n`` samples of one complex: everything is shared with ``graph`` (same tensor objects) except the
+    coordinates the sampler moves (``ligand.pos``, ``atom.pos``), which are cloned.  The reference deep-copies the whole
+    graph per sample (inference.py:135), ESM features included; sharing is what lets ``sampling()`` recognise samples of
+    one complex and upload / embed its static part once."""
+    out = []
+    for _ in range(n):
+        g = HeteroData()
+        for k, st in graph._nodes.items():
+            ns = Store()
+            ns._d.update(st._d)
+            if k in ('ligand', 'atom') and 'pos' in st._d:
+                ns._d['pos'] = st._d['pos'].clone()
+            g._nodes[k] = ns
+        for k, st in graph._edges.items():
+            es = Store()
+            es._d.update(st._d)
+            g._edges[k] = es
+        g._glob.update(graph._glob)
+        out.append(g)
+    return out

@@ -22,6 +22,7 @@ import torch.distributed as dist
 
 from .diffusion_utils import get_t_schedule, t_to_sigma as t_to_sigma_compl
 from .parallel import shard_range
+from .hetero import sample_copies
 from .sampling import randomize_position, sampling
 
 
@@ -40,23 +41,32 @@ def default_args(**over):
 
 def infer_single_complex(idx, protein_ligand_info_row, model, args, score_model_args, filtering_args=None,
                          filtering_model=None, filtering_model_args=None, filtering_complex_dict=None, t_schedule=None,
-                         tr_schedule=None, device=None):
+                         tr_schedule=None, device=None, defer=False):
     """-> dict(name, ligand_pos [spc, N_l, 3], atom_pos [spc, N_a, 3], confidence [spc] or None), poses in the original
-    frame and sorted by confidence (descending); ``None`` if the complex failed (the reference returns 0 and goes on)."""
+    frame and sorted by confidence (descending); ``None`` if the complex failed (the reference returns 0 and goes on).
+    ``defer=True`` returns a zero-argument callable producing that result instead: all GPU work is enqueued, nothing has
+    been waited for, so the caller can prepare the next complex meanwhile (``infer_multiple_complexes`` does)."""
     orig = protein_ligand_info_row['complex_graph']
     spc = args.samples_per_complex
     t_to_sigma = partial(t_to_sigma_compl, args=score_model_args)
     flex = False if args.rigid else score_model_args.flexible_sidechains
+
+    def failed(e):                                                  # inference.py:282-287
+        print('Failed on', getattr(orig, 'name', idx), e)
+        traceback.print_exc()
+        return None
     try:
-        data_list = [copy.deepcopy(orig) for _ in range(spc)]
+        # inference.py:135 deep-copies the graph per sample; here the samples share the static tensors of the complex
+        # (features, receptor graph) and own only the coordinates the sampler moves
+        data_list = sample_copies(orig, spc)
         randomize_position(data_list, score_model_args.no_torsion, args.no_random, score_model_args.tr_sigma_max,
                            flexible_sidechains=flex)
         filtering_data_list = None
         if filtering_model is not None and filtering_complex_dict is not None and not (
                 getattr(filtering_args, 'use_original_model_cache', True) or getattr(filtering_args, 'transfer_weights', False)):
-            filtering_data_list = [copy.deepcopy(filtering_complex_dict[orig.name]) for _ in range(spc)]
+            filtering_data_list = sample_copies(filtering_complex_dict[orig.name], spc)
         steps = args.actual_steps if args.actual_steps is not None else args.inference_steps
-        data_list, confidence = sampling(
+        pending = sampling(
             data_list=data_list, model=model, inference_steps=steps, tr_schedule=tr_schedule, rot_schedule=tr_schedule,
             tor_schedule=tr_schedule, sidechain_tor_schedule=tr_schedule, t_schedule=t_schedule, t_to_sigma=t_to_sigma,
             model_args=score_model_args, confidence_model=filtering_model, device=device, no_random=args.no_random,
@@ -65,13 +75,19 @@ def infer_single_complex(idx, protein_ligand_info_row, model, args, score_model_
             batch_size=args.batch_size, no_final_step_noise=args.no_final_step_noise,
             temp_sampling=[args.temp_sampling_tr, args.temp_sampling_rot, args.temp_sampling_tor, args.temp_sampling_sc_tor],
             temp_psi=[args.temp_psi_tr, args.temp_psi_rot, args.temp_psi_tor, args.temp_psi_sc_tor],
-            flexible_sidechains=flex)     # reference quirk kept: --temp_sigma_data is parsed (:101) but never passed
-        #                                   to sampling() (:177-196), so its default 0.5 applies
-        return _rank(orig, idx, data_list, confidence)                  # inference.py:198-219
-    except Exception as e:                                          # inference.py:282-287
-        print('Failed on', getattr(orig, 'name', idx), e)
-        traceback.print_exc()
-        return None
+            flexible_sidechains=flex, defer=True)     # reference quirk kept: --temp_sigma_data is parsed (:101) but never
+        #                                               passed to sampling() (:177-196), so its default 0.5 applies
+    except Exception as e:
+        failed(e)
+        return (lambda: None) if defer else None
+
+    def finish():
+        try:
+            graphs, confidence = pending()
+            return _rank(orig, idx, graphs, confidence)             # inference.py:198-219
+        except Exception as e:
+            return failed(e)
+    return finish if defer else finish()
 
 
 def _rank(orig, idx, graphs, confidence):
@@ -88,54 +104,81 @@ def _rank(orig, idx, graphs, confidence):
 
 
 def infer_complex_group(group, model, args, score_model_args, filtering_model=None, filtering_model_args=None,
-                        tr_schedule=None, t_schedule=None, device=None):
+                        tr_schedule=None, t_schedule=None, device=None, defer=False):
     """Cross-complex batching (the reference's sampler assumes one complex per call, F9): the samples
     of several complexes share one ``sampling()`` call, so that small ``samples_per_complex`` still fill the mini-batch
-    (virtual screening).  ``group``: [(idx, row), ...].  Falls back to one call per complex if the joint call fails."""
+    (virtual screening).  ``group``: [(idx, row), ...].  Falls back to one call per complex if the joint call fails.
+    ``defer`` as in ``infer_single_complex`` (the callable returns the list of per-complex results)."""
     spc = args.samples_per_complex
     flex = False if args.rigid else score_model_args.flexible_sidechains
+
+    def one_by_one(e):
+        print('Joint call failed for', [row['complex_graph'].name for _, row in group], e, '- retrying one complex at a time')
+        return [infer_single_complex(idx, row, model, args, score_model_args, filtering_model=filtering_model,
+                                     filtering_model_args=filtering_model_args, tr_schedule=tr_schedule, t_schedule=t_schedule,
+                                     device=device) for idx, row in group]
     try:
         data_list = []
         for _, row in group:
-            dl = [copy.deepcopy(row['complex_graph']) for _ in range(spc)]
+            dl = sample_copies(row['complex_graph'], spc)
             randomize_position(dl, score_model_args.no_torsion, args.no_random, score_model_args.tr_sigma_max, flexible_sidechains=flex)
             data_list += dl
         steps = args.actual_steps if args.actual_steps is not None else args.inference_steps
-        data_list, confidence = sampling(
+        pending = sampling(
             data_list=data_list, model=model, inference_steps=steps, tr_schedule=tr_schedule, rot_schedule=tr_schedule,
             tor_schedule=tr_schedule, sidechain_tor_schedule=tr_schedule, t_schedule=t_schedule,
             t_to_sigma=partial(t_to_sigma_compl, args=score_model_args), model_args=score_model_args,
             confidence_model=filtering_model, device=device, no_random=args.no_random, ode=args.ode,
             filtering_model_args=filtering_model_args, batch_size=args.batch_size, no_final_step_noise=args.no_final_step_noise,
             temp_sampling=[args.temp_sampling_tr, args.temp_sampling_rot, args.temp_sampling_tor, args.temp_sampling_sc_tor],
-            temp_psi=[args.temp_psi_tr, args.temp_psi_rot, args.temp_psi_tor, args.temp_psi_sc_tor], flexible_sidechains=flex)
-        return [_rank(row['complex_graph'], idx, data_list[k * spc:(k + 1) * spc],
-                      confidence[k * spc:(k + 1) * spc] if confidence is not None else None) for k, (idx, row) in enumerate(group)]
+            temp_psi=[args.temp_psi_tr, args.temp_psi_rot, args.temp_psi_tor, args.temp_psi_sc_tor], flexible_sidechains=flex,
+            defer=True)
     except Exception as e:
-        print('Joint call failed for', [row['complex_graph'].name for _, row in group], e, '- retrying one complex at a time')
-        return [infer_single_complex(idx, row, model, args, score_model_args, filtering_model=filtering_model,
-                                     filtering_model_args=filtering_model_args, tr_schedule=tr_schedule, t_schedule=t_schedule,
-                                     device=device) for idx, row in group]
+        res = one_by_one(e)
+        return (lambda: res) if defer else res
+
+    def finish():
+        try:
+            graphs, confidence = pending()
+            return [_rank(row['complex_graph'], idx, graphs[k * spc:(k + 1) * spc],
+                          confidence[k * spc:(k + 1) * spc] if confidence is not None else None) for k, (idx, row) in enumerate(group)]
+        except Exception as e:
+            return one_by_one(e)
+    return finish if defer else finish()
 
 
-def infer_multiple_complexes(rows, *a, batch_complexes=False, **kw):
+def infer_multiple_complexes(rows, *a, batch_complexes=False, pipeline=True, **kw):
     """inference.py:294-304 over a list of (idx, row) (rows: dicts with 'complex_graph'); -> (results, count_succeeded).
-    ``batch_complexes``: pack floor(batch_size / samples_per_complex) complexes into each sampler call."""
+    ``batch_complexes``: pack floor(batch_size / samples_per_complex) complexes into each sampler call.
+    ``pipeline``: software pipeline of depth 2 -- the host prepares and enqueues call k + 1 (graph copies,
+    ``randomize_position``, collation, plan upload, kernel launches) while the GPU still runs call k, and only then
+    collects call k's poses; without it the GPU idles during every complex's host work (the reference's loop is serial)."""
     args = a[1] if len(a) > 1 else kw['args']
     per_call = max(1, args.batch_size // args.samples_per_complex) if batch_complexes else 1
     if per_call == 1:
-        results = [infer_single_complex(i, row, *a, **kw) for i, row in rows]
+        launch = lambda item: infer_single_complex(item[0], item[1], *a, defer=True, **kw)
+        items, wrap = list(rows), (lambda r: [r])
     else:
         model, score_model_args = (a[0] if a else kw['model']), (a[2] if len(a) > 2 else kw['score_model_args'])
         passthrough = {k: kw[k] for k in ('filtering_model', 'filtering_model_args', 'tr_schedule', 't_schedule', 'device') if k in kw}
-        results = []
-        for j in range(0, len(rows), per_call):
-            results += infer_complex_group(rows[j:j + per_call], model, args, score_model_args, **passthrough)
+        launch = lambda grp: infer_complex_group(grp, model, args, score_model_args, defer=True, **passthrough)
+        items, wrap = [rows[j:j + per_call] for j in range(0, len(rows), per_call)], (lambda r: r)
+    results, pending = [], None
+    for item in items:
+        fin = launch(item)
+        if not pipeline:
+            results += wrap(fin())
+            continue
+        if pending is not None:
+            results += wrap(pending())
+        pending = fin
+    if pending is not None:
+        results += wrap(pending())
     return results, sum(r is not None for r in results)
 
 
 def infer_sharded(rows, model, args, score_model_args, device, filtering_model=None, filtering_model_args=None, group=None,
-                  batch_complexes=False):
+                  batch_complexes=False, pipeline=True):
     """Complexes split over the ranks like ``np.array_split`` (inference.py:468); every rank docks its shard with no
     communication; one all-gather of (complex index, best confidence) at the end -> global ranking on every rank."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -144,7 +187,7 @@ def infer_sharded(rows, model, args, score_model_args, device, filtering_model=N
     sched = get_t_schedule('expbeta', args.inference_steps, inf_sched_alpha=args.inf_sched_alpha, inf_sched_beta=args.inf_sched_beta)   # inference.py:457-459
     local, ok = infer_multiple_complexes([(i, rows[i]) for i in range(lo, hi)], model, args, score_model_args,
                                          filtering_model=filtering_model, filtering_model_args=filtering_model_args,
-                                         tr_schedule=sched, device=device, batch_complexes=batch_complexes)
+                                         tr_schedule=sched, device=device, batch_complexes=batch_complexes, pipeline=pipeline)
     # the single collective of the path: all-gather of the shards' best confidences (padded to the largest shard)
     width = -(-len(rows) // world) if len(rows) else 1
     mine = torch.full((width,), float('-inf'), device=device)

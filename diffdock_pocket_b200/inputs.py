@@ -354,6 +354,61 @@ def load_graph_npz(path, esm_seed=1234, name='complex'):
 
 
 # --------------------------------------------------------------------------------------- synthetic
+def _random_tree_ligand(rng, n_lig):
+    """Random-tree ligand with 1.5 A bonds -> (x, pos, edge_index, edge_attr)."""
+    pos = [np.zeros(3)]
+    bonds = []
+    while len(pos) < n_lig:
+        a = rng.randint(len(pos))
+        d = rng.randn(3)
+        p = pos[a] + d * 1.5 / np.linalg.norm(d)
+        if np.min(np.linalg.norm(np.array(pos) - p, axis=1)) < 1.2:
+            continue
+        bonds.append((a, len(pos), 1))
+        pos.append(p)
+    atoms = [(p[0], p[1], p[2], 'C' if rng.rand() < 0.7 else ('N' if rng.rand() < 0.5 else 'O'), 0) for p in pos]
+    return ligand_graph_from_sdf(atoms, bonds)
+
+
+def with_ligand(pocket_graph, seed, n_lig, name=None):
+    """A complex made of ``pocket_graph``'s receptor (its stores are SHARED, not copied) and a new procedural ligand:
+    the virtual-screening shape of BASELINE.json configs[4] (one pocket, many ligands)."""
+    lig_x, lig_pos, lig_ei, lig_ea = _random_tree_ligand(np.random.RandomState(seed), n_lig)
+    g = HeteroData()
+    for k, st in pocket_graph._nodes.items():
+        if k != 'ligand':
+            g._nodes[k] = st
+    for k, st in pocket_graph._edges.items():
+        if k[0] != 'ligand':
+            g._edges[k] = st
+    g._glob.update(pocket_graph._glob)
+    g['name'] = name or f'lig{seed}'
+    g['ligand'].x = lig_x
+    g['ligand'].pos = (lig_pos - lig_pos.mean(0, keepdim=True)).float()
+    g['ligand', 'lig_bond', 'ligand'].edge_index = lig_ei
+    g['ligand', 'lig_bond', 'ligand'].edge_attr = lig_ea
+    em, mr = rotatable_bond_masks(lig_x.shape[0], lig_ei)
+    g['ligand'].edge_mask, g['ligand'].mask_rotate = torch.tensor(em), mr
+    return g
+
+
+def pdbbind_test_sizes():
+    """Heavy-atom counts of the 363 PDBBind test ligands (tests/golden/pdbbind_test_ligand_sizes.txt, written by
+    scripts/make_size_law.py from the reference's data/test_ligands_smiles.txt): min 7, median 29, mean 35.9, max 147."""
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden', 'pdbbind_test_ligand_sizes.txt')
+    return [int(l) for l in open(path) if l.strip()]
+
+
+def pdbbind_synth_set(n=None, seed=0, flexible_residues=5):
+    """BASELINE.json configs[3]: synthetic complexes whose ligand sizes follow the PDBBind test set; the pocket grows with
+    the ligand (the reference cuts it at ligand radius + 10 A, datasets/pdbbind.py:597)."""
+    sizes = pdbbind_test_sizes()
+    sizes = sizes if n is None else [sizes[i % len(sizes)] for i in range(n)]
+    return [synthetic_complex(seed + i, n_lig=int(k), n_res=int(min(200, 70 + 2 * k)), flexible_residues=flexible_residues, name=f'pdbbind_synth{i}')
+            for i, k in enumerate(sizes)]
+
+
 def synthetic_complex(seed, n_lig=37, n_res=139, flexible_residues=7, name=None):
     """Procedural pocket + ligand of reference shape: a random-walk C-alpha trace folded into a ball
     around the origin (3.8 A steps), ~8 heavy atoms per residue with real residue templates, and a
@@ -384,18 +439,7 @@ def synthetic_complex(seed, n_lig=37, n_res=139, flexible_residues=7, name=None)
             if an not in ('N', 'C', 'O'):
                 prev = xyz
         residues.append(dict(name=rn, chain='A', resseq=str(i + 1), atoms=atoms))
-    pos = [np.zeros(3)]
-    bonds = []
-    while len(pos) < n_lig:
-        a = rng.randint(len(pos))
-        d = rng.randn(3)
-        p = pos[a] + d * 1.5 / np.linalg.norm(d)
-        if np.min(np.linalg.norm(np.array(pos) - p, axis=1)) < 1.2:
-            continue
-        bonds.append((a, len(pos), 1))
-        pos.append(p)
-    atoms = [(p[0], p[1], p[2], 'C' if rng.rand() < 0.7 else ('N' if rng.rand() < 0.5 else 'O'), 0) for p in pos]
-    lig = ligand_graph_from_sdf(atoms, bonds)
+    lig = _random_tree_ligand(rng, n_lig)
     flex = None
     if flexible_residues:
         cand = [r for r in residues if r['name'] not in NO_TORSION_RES]

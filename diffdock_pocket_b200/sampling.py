@@ -26,6 +26,7 @@ import torch
 from scipy.spatial.transform import Rotation as R
 
 from .diffusion_utils import PoseState, modify_conformer, modify_sidechains
+from .all_atom_score_model import STATIC_KEYS
 from .hetero import Batch
 
 
@@ -113,7 +114,7 @@ class StepRunner:
         n_sc = sum(int(g['flexResidues'].edge_idx.shape[0]) for g in data_sub
                    if flexible_sidechains and 'flexResidues' in g and 'edge_idx' in g['flexResidues'])
         self.n_extra = 8 + 6 * b + n_tor + n_sc
-        self.pl = model.make_plan(Batch.from_data_list(data_sub), extra_step_floats=self.n_extra)
+        self.pl = model.make_plan(Batch.from_data_list(data_sub, skip=STATIC_KEYS), extra_step_floats=self.n_extra, graphs=data_sub)
         pl = self.pl
         self.ps = PoseState(data_sub, pl.device, lig_pos=pl.lig_pos, atom_pos=pl.atom_pos,
                             flexible_sidechains=flexible_sidechains, no_torsion=no_torsion)
@@ -187,7 +188,7 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
              svgd_weight=0.0, svgd_repulsive_weight=1.0, svgd_only=False, svgd_rot_rel_weight=1.0, svgd_tor_rel_weight=1.0,
              svgd_sidechain_tor_rel_weight=1.0, temp_sampling=1.0, temp_psi=0.0, temp_sigma_data=0.5,
              flexible_sidechains=None, max_steps=None, trace=None, use_graph=False, concurrent_batches=True,
-             loader_seed_draws=True):
+             loader_seed_draws=True, defer=False):
     if svgd_weight > 0 or pivot is not None or asyncronous_noise_schedule:
         raise NotImplementedError('SVGD / pivot / asynchronous schedules are outside the accelerated path')
     flexible_sidechains = model_args.flexible_sidechains if flexible_sidechains is None else flexible_sidechains
@@ -249,6 +250,10 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
 
     conf_plans = None
 
+    def conf_plan(idx):
+        sub = [(filtering_data_list if filtering_data_list is not None else data_list)[i] for i in idx]
+        return confidence_model.make_plan(Batch.from_data_list(sub, skip=STATIC_KEYS), graphs=sub)
+
     def write_back_all():
         for idx, r in zip(chunks, runners):
             if r is not None:
@@ -285,8 +290,7 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
             if conf_plans is None and confidence_model is not None:
                 # confidence plans (static tensors, workspaces) are collated and uploaded while the GPU runs step 0;
                 # the final poses reach them by device-to-device copies after the last step
-                conf_plans = [confidence_model.make_plan(Batch.from_data_list(
-                    [(filtering_data_list if filtering_data_list is not None else data_list)[i] for i in idx])) for idx in chunks]
+                conf_plans = [conf_plan(idx) for idx in chunks]
             if visualization_list is not None or sidechain_visualization_list is not None:
                 write_back_all()
                 if visualization_list is not None:
@@ -299,8 +303,7 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
         confidence = None
         if confidence_model is not None:                              # utils/sampling.py:263-281
             if conf_plans is None:                                    # n_steps == 0
-                conf_plans = [confidence_model.make_plan(Batch.from_data_list(
-                    [(filtering_data_list if filtering_data_list is not None else data_list)[i] for i in idx])) for idx in chunks]
+                conf_plans = [conf_plan(idx) for idx in chunks]
             conf = []
             cur = torch.cuda.current_stream()
             for idx, r, cpl in zip(chunks, runners, conf_plans):
@@ -322,10 +325,34 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
         for r in runners:
             if r is not None:
                 r.sync_out()
+        staged = None
+        if defer:
+            # asynchronous device->host copies into pinned buffers + one event: finish() waits for THIS call's work only,
+            # not for whatever the caller has enqueued behind it in the meantime
+            for r in runners:
+                if r is not None:
+                    r.ps.stage_to_host()
+            conf_host = None
+            if confidence is not None:
+                conf_host = torch.empty(confidence.shape, dtype=confidence.dtype, pin_memory=True)
+                conf_host.copy_(confidence, non_blocking=True)
+            staged = (torch.cuda.Event(), conf_host)
+            staged[0].record()
+
+    def finish():
+        nonlocal confidence
+        if staged is not None:
+            staged[0].synchronize()
+            confidence = staged[1]
         write_back_all()                                              # the one device->host read of the poses
         if filtering_data_list is not None:
             for i, g in enumerate(filtering_data_list):
                 g['ligand'].pos = data_list[i]['ligand'].pos
-    if return_full_trajectory:
-        return data_list, confidence, trajectory, sidechain_trajectory
-    return data_list, confidence
+        if return_full_trajectory:
+            return data_list, confidence, trajectory, sidechain_trajectory
+        return data_list, confidence
+    if defer:
+        # everything is enqueued; nothing has been waited for.  The caller overlaps its next complex's host work (graph
+        # copies, randomize_position, collation, plan upload) with this one's GPU work and calls finish() later.
+        return finish
+    return finish()

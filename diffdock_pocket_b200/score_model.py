@@ -29,6 +29,29 @@ class GaussianSmearing(nn.Module):
         self.register_buffer('offset', offset)
 
 
+def _static_pack(enc, device, w_emb_t, w_lm_t):
+    f32 = dict(dtype=torch.float32, device=device)
+    tabs = [e.weight.detach().float() for e in enc.atom_embedding_list]
+    off = np.concatenate([[0], np.cumsum([t.shape[0] for t in tabs])[:-1]])
+    return dict(table=torch.cat(tabs, 0).to(**f32).contiguous(), table_off=torch.as_tensor(off, dtype=torch.int32, device=device),
+                n_cat=len(tabs), ns=enc.emb_dim,
+                w_emb_t=None if w_emb_t is None else w_emb_t.to(**f32).contiguous(),
+                w_lm_t=None if w_lm_t is None else w_lm_t.to(**f32).contiguous(),
+                n_lm=0 if w_lm_t is None else int(w_lm_t.shape[0]))
+
+
+def static_embed(pack, cat, lm, device):
+    """``ddp_node_static_embed`` on one complex: cat [n, n_cat] integer features, lm [n, n_lm] float or None -> [n, ns]."""
+    n = cat.shape[0]
+    cat_d = cat.to(device=device, dtype=torch.int64).contiguous()
+    lm_d = lm.to(device=device, dtype=torch.float32).contiguous() if pack['n_lm'] else None
+    out = torch.empty(n, pack['ns'], dtype=torch.float32, device=device)
+    _lib.check(_lib.lib().ddp_node_static_embed(ptr(cat_d), n, pack['n_cat'], ptr(pack['table']), ptr(pack['table_off']), ptr(lm_d),
+                                                 pack['n_lm'], ptr(pack['w_emb_t']), ptr(pack['w_lm_t']), pack['ns'], ptr(out),
+                                                 _lib.stream_ptr()), 'ddp_node_static_embed')
+    return out
+
+
 class AtomEncoder(nn.Module):
     """Parameter holder; the encoder is evaluated as static part (once per complex) + per-graph sigma
     projection (``ddp_graph_sigma_proj`` / ``ddp_node_init``)."""
@@ -69,6 +92,12 @@ class AtomEncoder(nn.Module):
         W = self.additional_features_embedder.weight
         return W[:, -self.sigma_embed_dim:].T.contiguous(), self.additional_features_embedder.bias
 
+    def static_pack(self, device):
+        """Operands of ``ddp_node_static_embed`` (the kernel form of ``static_part``)."""
+        W = self.additional_features_embedder.weight.detach().double()
+        ns, L = self.emb_dim, self.lm_embedding_dim
+        return _static_pack(self, device, W[:, :ns].T, W[:, ns:ns + L].T if L else None)
+
 
 class OldAtomEncoder(nn.Module):
     def __init__(self, emb_dim, feature_dims, sigma_embed_dim, lm_embedding_type=None):
@@ -105,6 +134,17 @@ class OldAtomEncoder(nn.Module):
         Wl = self.lm_embedding_layer.weight
         h = self._emb_sum(cat) + lm[:, :sd] @ self.linear.weight.T
         return (h @ Wl[:, :ns].T + lm[:, sd:] @ Wl[:, ns:ns + self.lm_embedding_dim - sd].T).contiguous()
+
+    def static_pack(self, device):
+        """Operands of ``ddp_node_static_embed``: the two Linears of ``static_part`` folded (in float64) into one pair
+        (W_emb, W_lm) so that the same kernel serves both encoders."""
+        ns, sd = self.emb_dim, self.sigma_embed_dim
+        if self.lm_embedding_type is None:
+            return _static_pack(self, device, None, None)
+        Wl = self.lm_embedding_layer.weight.detach().double()
+        A = Wl[:, :ns].T                                                        # [ns, ns]
+        w_lm = torch.cat([self.linear.weight.detach().double().T @ A, Wl[:, ns:ns + self.lm_embedding_dim - sd].T], 0)
+        return _static_pack(self, device, A, w_lm)
 
     def sigma_proj(self):
         ns, sd = self.emb_dim, self.sigma_embed_dim

@@ -6,13 +6,26 @@ the diffusion loop; inside the loop the same rotations are done by the ``ddp_pos
 """
 import numpy as np
 import torch
-from scipy.spatial.transform import Rotation as R
+
+
+def _rotvec_matrix(rot_vec):
+    """float64 rotation matrix of a rotation vector (what ``scipy Rotation.from_rotvec(v).as_matrix()`` returns, to
+    rounding): Rodrigues' formula, R = I + sin(t) K + (1 - cos(t)) K^2 with K the cross-product matrix of the unit axis."""
+    t = float(np.sqrt(rot_vec[0] * rot_vec[0] + rot_vec[1] * rot_vec[1] + rot_vec[2] * rot_vec[2]))
+    if t < 1e-12:
+        return np.eye(3)
+    x, y, z = rot_vec[0] / t, rot_vec[1] / t, rot_vec[2] / t
+    c, s_ = np.cos(t), np.sin(t)
+    C = 1.0 - c
+    return np.array([[c + x * x * C, x * y * C - z * s_, x * z * C + y * s_],
+                     [y * x * C + z * s_, c + y * y * C, y * z * C - x * s_],
+                     [z * x * C - y * s_, z * y * C + x * s_, c + z * z * C]])
 
 
 def _rotate(pos, u, v, idx, angle):
-    axis = pos[u] - pos[v]
+    axis = (pos[u] - pos[v]).astype(np.float64)
     rot_vec = axis * angle / np.linalg.norm(axis)
-    pos[idx] = (pos[idx] - pos[v]) @ R.from_rotvec(rot_vec).as_matrix().T + pos[v]
+    pos[idx] = (pos[idx] - pos[v]) @ _rotvec_matrix(rot_vec).T + pos[v]
 
 
 def modify_conformer_torsion_angles(pos, edge_index, mask_rotate, torsion_updates, as_numpy=False):
@@ -31,13 +44,12 @@ def modify_conformer_torsion_angles(pos, edge_index, mask_rotate, torsion_update
 
 def modify_sidechains_host(data, torsion_updates):
     fr = data['flexResidues']
-    p = data['atom'].pos.detach().cpu().numpy().copy()
+    p = data['atom'].pos.detach().cpu().numpy().astype(np.float32, copy=True)
     sub = fr.subcomponents.cpu().numpy()
+    bonds = fr.edge_idx.cpu().numpy().reshape(-1, 2)
+    mapping = fr.subcomponentsMapping.cpu().numpy().reshape(-1, 2)
     for k, upd in enumerate(torsion_updates):
         if upd == 0:
             continue
-        u, v = int(fr.edge_idx[k][0]), int(fr.edge_idx[k][1])
-        m0, m1 = int(fr.subcomponentsMapping[k][0]), int(fr.subcomponentsMapping[k][1])
-        _rotate(p, u, v, sub[m0:m1], upd)
-        p = p.astype(np.float32)
-    data['atom'].pos = torch.from_numpy(p.astype(np.float32)).to(data['atom'].pos.device)
+        _rotate(p, int(bonds[k, 0]), int(bonds[k, 1]), sub[int(mapping[k, 0]):int(mapping[k, 1])], upd)     # fp64 rotation, fp32 positions
+    data['atom'].pos = torch.from_numpy(p).to(data['atom'].pos.device)

@@ -114,6 +114,15 @@ int ddp_graph_sigma_proj(const float *t, int32_t n_graphs, float scale, const fl
                          const float *w, const float *b, int32_t n_proj, int32_t ns, float *sig, float *out,
                          void *stream);
 
+/* Static (time-independent) part of AtomEncoder.forward (models/score_model.py:74-82; OldAtomEncoder :38-52 after
+ * folding its two Linears on the host), computed ONCE per complex and cached (the receptor's Linear runs
+ * over 1280 ESM dims):  out[n][:] = (sum_k table[table_off[k] + cat[n][k]][:]) W_emb + lm[n][:] W_lm.
+ * cat: [n][n_cat] int64 categorical features; table: all embedding tables stacked, [rows][ns]; lm: [n][n_lm] or NULL;
+ * w_emb_t: [ns][ns] input-major or NULL (identity); w_lm_t: [n_lm][ns] input-major; out: [n][ns]. */
+int ddp_node_static_embed(const int64_t *cat, int32_t n, int32_t n_cat, const float *table, const int32_t *table_off,
+                          const float *lm, int32_t n_lm, const float *w_emb_t, const float *w_lm_t, int32_t ns,
+                          float *out, void *stream);
+
 /* node_attr[n][:ns] = static_part[n][:] + u[graph_of[n]][:]  (AtomEncoder, models/score_model.py:74-82,
  * with the time-independent part of the Linear precomputed once per complex). */
 int ddp_node_init(const float *static_part, const float *u, const int32_t *graph_of, int32_t n, int32_t ns,

@@ -372,3 +372,63 @@ def test_sampler_schedules_agree():
             assert float((a['ligand'].pos - b['ligand'].pos).abs().max()) < 2e-3, opts
             assert float((a['atom'].pos - b['atom'].pos).abs().max()) < 2e-3, opts
         assert T.rel_err(conf, conf0) < 1e-3, opts
+
+
+def test_static_embed_kernel_matches_encoder_arithmetic():
+    """``ddp_node_static_embed`` (once-per-complex part of AtomEncoder.forward, models/score_model.py:74-82, and of
+    OldAtomEncoder :38-52 with its two Linears folded) against the same arithmetic in PyTorch fp32, for the three node types."""
+    from diffdock_pocket_b200.score_model import AtomEncoder, OldAtomEncoder, FEATURE_DIMS, static_embed
+    g = T.graph('3dpf_apo')
+    torch.manual_seed(0)
+    for cls in (AtomEncoder, OldAtomEncoder):
+        for kind, key, lm_type in (('lig', 'ligand', None), ('atom', 'atom', None), ('rec_residue', 'receptor', 'esm')):
+            enc = cls(60, FEATURE_DIMS[kind], 64, lm_embedding_type=lm_type).to(DEV)
+            x = g[key].x
+            cat, lm = (x[:, :1], x[:, 1:]) if lm_type else (x, None)
+            with torch.no_grad():
+                want = enc.static_part(cat.to(DEV), lm.to(DEV).float() if lm is not None else None)
+                got = static_embed(enc.static_pack(DEV), cat, lm, DEV)
+            assert got.shape == want.shape and T.rel_err(got, want) < 2e-6 and T.rel_err_cols(got, want) < 1e-4, (cls.__name__, kind)
+
+
+def test_pipelined_and_shared_copy_inference_equals_serial_deepcopy_path():
+    """The host mirror of inference.py: (a) samples that share their complex's static tensors (``sample_copies``) and the
+    per-complex static cache give the same poses as deep-copied graphs (the reference's inference.py:135) passed straight to
+    ``sampling()``; (b) the depth-2 software pipeline over complexes (``defer``) returns exactly what the serial loop returns,
+    also with several complexes per sampler call."""
+    from diffdock_pocket_b200 import inference
+    m, c, om, oc, sa, ca = T.models(DEV, small=True)
+    graphs = [inputs.synthetic_complex(50 + i, n_lig=10 + 3 * i, n_res=30 + 4 * i, flexible_residues=i % 3) for i in range(5)]
+    rows = [(i, dict(complex_name=g.name, complex_graph=g)) for i, g in enumerate(graphs)]
+    args = inference.default_args(samples_per_complex=4, batch_size=8, inference_steps=4, no_random=True)
+    sched = du.get_t_schedule('expbeta', 4)
+    m.conv_mode = 'fp32'
+    run = lambda **kw: inference.infer_multiple_complexes(rows, m, args, sa, filtering_model=c, filtering_model_args=ca, tr_schedule=sched,
+                                                          device=DEV, **kw)
+    outs = {}
+    for name, kw in (('serial', dict(pipeline=False)), ('pipe', dict(pipeline=True)), ('group_serial', dict(pipeline=False, batch_complexes=True)),
+                     ('group_pipe', dict(pipeline=True, batch_complexes=True))):
+        np.random.seed(3)
+        torch.manual_seed(3)
+        res, ok = run(**kw)
+        assert ok == len(rows), name
+        outs[name] = res
+    for a, b in zip(outs['serial'], outs['pipe']):                      # identical work, only the host schedule differs
+        assert a['name'] == b['name'] and np.abs(a['ligand_pos'] - b['ligand_pos']).max() < 2e-3 and np.abs(a['atom_pos'] - b['atom_pos']).max() < 2e-3
+        assert np.abs(a['confidence'] - b['confidence']).max() < 1e-4
+    for a, b in zip(outs['group_serial'], outs['group_pipe']):
+        assert np.abs(a['ligand_pos'] - b['ligand_pos']).max() < 2e-3 and np.abs(a['confidence'] - b['confidence']).max() < 1e-4
+    # (a): the reference-style call on deep copies of complex 1
+    np.random.seed(3)
+    torch.manual_seed(3)
+    for i, g in enumerate(graphs[:2]):                                  # consume the generators exactly like the loop above
+        dl = [copy.deepcopy(g) for _ in range(4)]
+        ps.randomize_position(dl, sa.no_torsion, True, sa.tr_sigma_max, flexible_sidechains='flexResidues' in g)
+        out, conf = ps.sampling(dl, m, 4, sched, sched, sched, sched, DEV, partial(du.t_to_sigma, args=sa), sa, confidence_model=c,
+                                filtering_model_args=ca, batch_size=8, no_random=True,
+                                temp_sampling=[args.temp_sampling_tr, args.temp_sampling_rot, args.temp_sampling_tor, args.temp_sampling_sc_tor],
+                                temp_psi=[args.temp_psi_tr, args.temp_psi_rot, args.temp_psi_tor, args.temp_psi_sc_tor])
+    want = outs['serial'][1]
+    order = np.argsort(conf.cpu().numpy())[::-1]
+    got = np.asarray([out[k]['ligand'].pos.cpu().numpy() + g.original_center.numpy() for k in order])
+    assert np.abs(got - want['ligand_pos']).max() < 2e-3
