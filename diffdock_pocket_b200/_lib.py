@@ -112,12 +112,20 @@ def launch_count():
     return sum(n * KERNELS_PER_CALL.get(k, 1) for k, n in COUNTS.items())
 
 
+# While a list is installed here every C call is also appended to it as (name, fn, args): the score model records the
+# launch sequence of a resident plan once and replays it on later steps without re-marshalling ~60 descriptors
+# (all_atom_score_model.launch_plan).
+RECORD = None
+
+
 class _Counted:
     def __init__(self, name, fn):
         self.name, self.fn = name, fn
 
     def __call__(self, *a):
         COUNTS[self.name] = COUNTS.get(self.name, 0) + 1
+        if RECORD is not None:
+            RECORD.append((self.name, self.fn, a))
         return self.fn(*a)
 
 

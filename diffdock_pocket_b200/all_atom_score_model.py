@@ -644,7 +644,46 @@ class TensorProductScoreModel(nn.Module):
         return self._br[key]
 
     def launch_plan(self, pl, return_layers=False):
-        """Kernel launches only (per-graph scalars already staged in ``pl.scal``): CUDA-graph capturable."""
+        """Kernel launches only (per-graph scalars already staged in ``pl.scal``): CUDA-graph capturable.
+
+        Nothing in the launch sequence of a resident plan changes from step to step (every pointer, count and descriptor is
+        fixed; the per-step scalars live in device buffers), so the first launch RECORDS it -- the C-ABI calls with their
+        marshalled arguments, the few torch fills in between, the stream forks / joins -- and later launches replay the
+        record: ~0.5 ms of host time per forward instead of ~2.8 ms of Python descriptor building."""
+        key = (self.conv_mode, torch.cuda.current_stream().cuda_stream, getattr(self, 'group_convs', True), id(self.packed()))
+        debug = return_layers or getattr(self, 'profile', None) is not None
+        prog = getattr(pl, 'program', None)
+        if prog is not None and prog[0] == key and not debug:
+            base = torch.cuda.current_stream()
+            for name, fn, args in prog[1]:
+                if name is None:                                   # torch op recorded with the stream it ran on
+                    if args is None or args == base:
+                        fn()
+                    else:
+                        with torch.cuda.stream(args):
+                            fn()
+                elif fn(*args) != 0:
+                    raise RuntimeError(f'{name} failed in a replayed launch')
+            return prog[2]
+        if debug:
+            return self._launch_plan_body(pl, return_layers)
+        assert _lib.RECORD is None, 'nested launch recording'
+        _lib.RECORD = rec = []
+        try:
+            out = self._launch_plan_body(pl, False)
+        finally:
+            _lib.RECORD = None
+        pl.program = (key, rec, out)
+        return out
+
+    @staticmethod
+    def _py(fn):
+        """Run a torch-side step of the launch sequence (fill, copy, fork / join) and record it with its stream."""
+        fn()
+        if _lib.RECORD is not None:
+            _lib.RECORD.append((None, fn, torch.cuda.current_stream()))
+
+    def _launch_plan_body(self, pl, return_layers=False):
         P = self.packed()
         L = _lib.lib()
         st = _lib.stream_ptr()
@@ -698,15 +737,16 @@ class TensorProductScoreModel(nn.Module):
             embed(nm, st_)
 
         br = self._branches(pl.device)
-        main = br.fork(3)
+        main = torch.cuda.current_stream()
+        self._py(lambda: br.fork(3))
         for side, nm in zip(br.side, ('aa', 'lr', 'la')):
             with torch.cuda.stream(side):
                 build(nm, _lib.stream_ptr())
         build('ll', st)
         embed('rr', st)
         embed('ar', st)
-        br.join(main, 3)
-        pl.deg_arena.copy_(pl.deg_base)                               # static edge sets + ligand bond edges
+        self._py(lambda: br.join(main, 3))
+        self._py(lambda: pl.deg_arena.copy_(pl.deg_base))            # static edge sets + ligand bond edges
         chk(L.ddp_degree_multi(pl.deg_jobs, len(pl.deg_jobs), st), 'ddp_degree_multi')   # dynamic ones, one launch
         # ---- interaction layers (all_atom_score_model.py:271-324) --------------------------------
         layers_out = []
@@ -715,7 +755,7 @@ class TensorProductScoreModel(nn.Module):
             last = l == self.num_conv_layers - 1
             f_old, f_new = seq_dims[min(l, 3)], seq_dims[min(l + 1, 3)]
             Cv, Pk = self.conv_layers, P['convs']
-            pl.sum_arena[:pl.sum_used[min(l + 1, 3)]].zero_()
+            self._py(lambda n_=pl.sum_used[min(l + 1, 3)]: pl.sum_arena[:n_].zero_())
             o = 0
 
             def take(n):
@@ -787,7 +827,7 @@ class TensorProductScoreModel(nn.Module):
                         chk(L.ddp_segment_mean(xa.data_ptr() + 4 * (f_last - ns), ptr(pl.flex_atoms), ptr(pl.flex_ptr), B, ns, F,
                                                pl.conf_in.data_ptr() + 4 * (w + ns), ld, st), 'segment_mean')
                 else:
-                    pl.conf_in[:, w:].zero_()
+                    self._py(lambda: pl.conf_in[:, w:].zero_())
             lay = P['conf_mlp']
             arr = (_lib.MlpLayer * 3)(*[_lib.MlpLayer(wt=ptr(wt), b=ptr(b), n_in=wt.shape[0], n_out=wt.shape[1], act=a)
                                        for (wt, b), a in zip(lay, (1, 1, 0))])
@@ -809,8 +849,7 @@ class TensorProductScoreModel(nn.Module):
                 chk(L.ddp_tor_edge_sh_generic(ptr(e.sh), self.sh_dim, ptr(h.y2), P['ftp_paths'], len(P['ftp_paths']), ptr(P['ftp_ctab']),
                                               ptr(e.edge), ptr(e.n_dev), e.cap, ptr(h.sh_tor), self._tor_ftp['dim'], st_), 'tor_edge_sh_generic')
             e.sh_conv = h.sh_tor
-            h.sum.zero_()
-            h.deg.zero_()
+            self._py(lambda: (h.sum.zero_(), h.deg.zero_()))
             chk(L.ddp_degree(e.row(0), ptr(e.n_dev), e.cap, ptr(h.deg), st_), 'ddp_degree')
             pk = P[key + '_conv']
             self._conv_group(L, st_, [(conv, pk, e, False, xn, xn, 1, h.attr, 0, h.sum)])
@@ -825,7 +864,7 @@ class TensorProductScoreModel(nn.Module):
 
         heads = (('tor', pl.T, pl.lig_pos, xl, pl.lig_ptr, getattr(self, 'tor_bond_conv', None), 'tor_mlp', 'tor', pl.tor_out, 4 * B),
                  ('sc', pl.S, pl.atom_pos, xa, pl.atom_ptr, getattr(self, 'sc_tor_bond_conv', None), 'sc_mlp', 'sc', pl.sc_out, 4 * B + pl.T))
-        main = br.fork(2)
+        self._py(lambda: br.fork(2))
         outs = []
         for side, hd in zip(br.side, heads):
             if hd[1] == 0:
@@ -838,7 +877,7 @@ class TensorProductScoreModel(nn.Module):
         chk(L.ddp_segment_mean(ptr(pl.lig_pos), None, ptr(pl.lig_ptr), B, 3, 3, ptr(pl.center), 3, st), 'segment_mean')
         chk(L.ddp_edge_embed(ptr(pl.center), ptr(pl.lig_pos), ptr(ec.edge), ec.cap, ptr(ec.n_dev), None, None, 0, ptr(U['center']),
                              C.byref(em['center']['desc']), ptr(ec.sh), ptr(ec.emb), st), 'ddp_edge_embed(center)')
-        pl.g_sum.zero_()
+        self._py(lambda: pl.g_sum.zero_())
         self._conv_group(L, st, [(self.final_conv, P['final_conv'], ec, False, xl, xl, 1 if self.fixed_center_conv else 0, None, 0, pl.g_sum)])
         fc = P['final_conv']
         up = _lib.Update(sum=ptr(pl.g_sum), deg=ptr(pl.center_deg), scale=ptr(fc.bn_scale), shift=ptr(fc.bn_shift), n_edges_dev=ptr(ec.n_dev))
@@ -850,7 +889,7 @@ class TensorProductScoreModel(nn.Module):
             trs = son = pl.ones_F[:B] if B <= pl.ones_F.numel() else torch.ones(B, device=pl.device)
         chk(L.ddp_tr_rot_head(ptr(pl.g), ptr(pl.sig), self.sigma_embed_dim, B, ptr(tw1), ptr(tb1), ptr(tw2), ptr(tb2), ptr(rw1),
                               ptr(rb1), ptr(rw2), ptr(rb2), ns, ptr(trs), ptr(son), ptr(pl.tr_out), ptr(pl.rot_out), st), 'tr_rot_head')
-        br.join(main, 2)
+        self._py(lambda: br.join(main, 2))
         return pl.tr_out, pl.rot_out, outs[0], outs[1]
 
     def forward(self, data):

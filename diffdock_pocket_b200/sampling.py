@@ -116,21 +116,31 @@ class StepRunner:
         self.n_extra = 8 + 6 * b + n_tor + n_sc
         self.pl = model.make_plan(Batch.from_data_list(data_sub, skip=STATIC_KEYS), extra_step_floats=self.n_extra, graphs=data_sub)
         pl = self.pl
-        self.ps = PoseState(data_sub, pl.device, lig_pos=pl.lig_pos, atom_pos=pl.atom_pos,
-                            flexible_sidechains=flexible_sidechains, no_torsion=no_torsion)
-        self.T, self.S = self.ps.T, self.ps.S
+        # the pose state (host loops over the samples' bond tables) is only needed by the pose update that FOLLOWS the first
+        # forward: it is built after that forward has been launched, i.e. while the GPU already works (see _launch)
+        self._ps_args = (data_sub, pl.device, flexible_sidechains, no_torsion)
+        self._ps = None
+        self.T, self.S = n_tor, n_sc
         o = pl.n_scal
         x = pl.step_in
         self.coef_dev = x[o:o + 8]
         o += 8
         self.z = (x[o:o + 3 * b], x[o + 3 * b:o + 6 * b], x[o + 6 * b:o + 6 * b + self.T],
                   x[o + 6 * b + self.T:o + 6 * b + self.T + self.S])
-        self.use_sc = flexible_sidechains and self.ps.has_sc
-        assert (self.T, self.S) == (n_tor, n_sc)
+        self.use_sc = flexible_sidechains and n_sc > 0
         self.graph = None
         self.use_graph = use_graph
         self.out = None
         self.calls = 0
+
+    @property
+    def ps(self):
+        if self._ps is None:
+            data_sub, dev, flex, no_tor = self._ps_args
+            self._ps = PoseState(data_sub, dev, lig_pos=self.pl.lig_pos, atom_pos=self.pl.atom_pos, flexible_sidechains=flex, no_torsion=no_tor)
+            assert (self._ps.T, self._ps.S) == (self.T, self.S)
+            self._ps_args = None
+        return self._ps
 
     def _launch(self):
         tr, rot, tor, sc = self.model.launch_plan(self.pl)

@@ -383,7 +383,7 @@ def test_static_embed_kernel_matches_encoder_arithmetic():
     g = T.graph('3dpf_apo')
     torch.manual_seed(0)
     for cls in (AtomEncoder, OldAtomEncoder):
-        for kind, key, lm_type in (('lig', 'ligand', None), ('atom', 'atom', None), ('rec_residue', 'receptor', 'esm')):
+        for kind, key, lm_type in (('lig', 'ligand', None), ('rec_atom', 'atom', None), ('rec_residue', 'receptor', 'esm')):
             enc = cls(60, FEATURE_DIMS[kind], 64, lm_embedding_type=lm_type).to(DEV)
             x = g[key].x
             cat, lm = (x[:, :1], x[:, 1:]) if lm_type else (x, None)
