@@ -124,7 +124,7 @@ class _Counted:
 
     def __call__(self, *a):
         COUNTS[self.name] = COUNTS.get(self.name, 0) + 1
-        if RECORD is not None:
+        if RECORD is not None and KERNELS_PER_CALL.get(self.name, 1) > 0:     # launches only (not ddp_tpconv_pack & co.)
             RECORD.append((self.name, self.fn, a))
         return self.fn(*a)
 

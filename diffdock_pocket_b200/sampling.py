@@ -51,6 +51,8 @@ def randomize_position(data_list, no_torsion, no_random, tr_sigma_max, pocket_kn
     if flexible_sidechains:
         from .torsion import modify_sidechains_host
         for g in data_list:
+            if 'flexResidues' not in g or 'edge_idx' not in g['flexResidues']:
+                continue                                  # complex without flexible residues in a mixed list (draws nothing)
             upd = np.random.uniform(low=-np.pi, high=np.pi, size=len(g['flexResidues'].edge_idx))
             modify_sidechains_host(g, upd)
     for g in data_list:
