@@ -612,6 +612,8 @@ class TensorProductScoreModel(nn.Module):
             ev0.record()
         tc = self.conv_mode != 'fp32' and all(tpmod.umma_supported(it[1].spec, self.ns) and it[5] is not None and it[7] is not None for it in items)
         eds = [self._edges_desc(*it[2:9], *it[10:12]) for it in items]
+        if _lib.RECORD is not None:
+            _lib.RECORD.append((None, None, eds))       # the grouped launch receives raw ADDRESSES of these: keep them alive with the record
         if tc:
             mode = 0 if self.conv_mode == 'bf16' else 1
             n = len(items)
@@ -657,6 +659,8 @@ class TensorProductScoreModel(nn.Module):
             base = torch.cuda.current_stream()
             for name, fn, args in prog[1]:
                 if name is None:                                   # torch op recorded with the stream it ran on
+                    if fn is None:
+                        continue                                   # keep-alive entry
                     if args is None or args == base:
                         fn()
                     else:
