@@ -651,7 +651,9 @@ class TensorProductScoreModel(nn.Module):
         Nothing in the launch sequence of a resident plan changes from step to step (every pointer, count and descriptor is
         fixed; the per-step scalars live in device buffers), so the first launch RECORDS it -- the C-ABI calls with their
         marshalled arguments, the few torch fills in between, the stream forks / joins -- and later launches replay the
-        record: ~0.5 ms of host time per forward instead of ~2.8 ms of Python descriptor building."""
+        record: ~0.5 ms of host time per forward instead of ~2.8 ms of Python descriptor building.  (The recorded closures
+        capture tensors, never the plan itself: a plan -> record -> plan cycle would keep freed plans away from the caching
+        allocator until the cyclic GC runs, and every new plan would pay cudaMalloc.)"""
         key = (self.conv_mode, torch.cuda.current_stream().cuda_stream, getattr(self, 'group_convs', True), id(self.packed()))
         debug = return_layers or getattr(self, 'profile', None) is not None
         prog = getattr(pl, 'program', None)
@@ -750,7 +752,7 @@ class TensorProductScoreModel(nn.Module):
         embed('rr', st)
         embed('ar', st)
         self._py(lambda: br.join(main, 3))
-        self._py(lambda: pl.deg_arena.copy_(pl.deg_base))            # static edge sets + ligand bond edges
+        self._py(lambda a=pl.deg_arena, b=pl.deg_base: a.copy_(b))   # static edge sets + ligand bond edges
         chk(L.ddp_degree_multi(pl.deg_jobs, len(pl.deg_jobs), st), 'ddp_degree_multi')   # dynamic ones, one launch
         # ---- interaction layers (all_atom_score_model.py:271-324) --------------------------------
         layers_out = []
@@ -759,7 +761,7 @@ class TensorProductScoreModel(nn.Module):
             last = l == self.num_conv_layers - 1
             f_old, f_new = seq_dims[min(l, 3)], seq_dims[min(l + 1, 3)]
             Cv, Pk = self.conv_layers, P['convs']
-            self._py(lambda n_=pl.sum_used[min(l + 1, 3)]: pl.sum_arena[:n_].zero_())
+            self._py(lambda a=pl.sum_arena[:pl.sum_used[min(l + 1, 3)]]: a.zero_())
             o = 0
 
             def take(n):
@@ -831,7 +833,7 @@ class TensorProductScoreModel(nn.Module):
                         chk(L.ddp_segment_mean(xa.data_ptr() + 4 * (f_last - ns), ptr(pl.flex_atoms), ptr(pl.flex_ptr), B, ns, F,
                                                pl.conf_in.data_ptr() + 4 * (w + ns), ld, st), 'segment_mean')
                 else:
-                    self._py(lambda: pl.conf_in[:, w:].zero_())
+                    self._py(lambda a=pl.conf_in[:, w:]: a.zero_())
             lay = P['conf_mlp']
             arr = (_lib.MlpLayer * 3)(*[_lib.MlpLayer(wt=ptr(wt), b=ptr(b), n_in=wt.shape[0], n_out=wt.shape[1], act=a)
                                        for (wt, b), a in zip(lay, (1, 1, 0))])
@@ -853,7 +855,7 @@ class TensorProductScoreModel(nn.Module):
                 chk(L.ddp_tor_edge_sh_generic(ptr(e.sh), self.sh_dim, ptr(h.y2), P['ftp_paths'], len(P['ftp_paths']), ptr(P['ftp_ctab']),
                                               ptr(e.edge), ptr(e.n_dev), e.cap, ptr(h.sh_tor), self._tor_ftp['dim'], st_), 'tor_edge_sh_generic')
             e.sh_conv = h.sh_tor
-            self._py(lambda: (h.sum.zero_(), h.deg.zero_()))
+            self._py(lambda a=h.sum, b=h.deg: (a.zero_(), b.zero_()))
             chk(L.ddp_degree(e.row(0), ptr(e.n_dev), e.cap, ptr(h.deg), st_), 'ddp_degree')
             pk = P[key + '_conv']
             self._conv_group(L, st_, [(conv, pk, e, False, xn, xn, 1, h.attr, 0, h.sum)])
@@ -881,7 +883,7 @@ class TensorProductScoreModel(nn.Module):
         chk(L.ddp_segment_mean(ptr(pl.lig_pos), None, ptr(pl.lig_ptr), B, 3, 3, ptr(pl.center), 3, st), 'segment_mean')
         chk(L.ddp_edge_embed(ptr(pl.center), ptr(pl.lig_pos), ptr(ec.edge), ec.cap, ptr(ec.n_dev), None, None, 0, ptr(U['center']),
                              C.byref(em['center']['desc']), ptr(ec.sh), ptr(ec.emb), st), 'ddp_edge_embed(center)')
-        self._py(lambda: pl.g_sum.zero_())
+        self._py(lambda a=pl.g_sum: a.zero_())
         self._conv_group(L, st, [(self.final_conv, P['final_conv'], ec, False, xl, xl, 1 if self.fixed_center_conv else 0, None, 0, pl.g_sum)])
         fc = P['final_conv']
         up = _lib.Update(sum=ptr(pl.g_sum), deg=ptr(pl.center_deg), scale=ptr(fc.bn_scale), shift=ptr(fc.bn_shift), n_edges_dev=ptr(ec.n_dev))

@@ -69,7 +69,7 @@ def randomized_list(g, n, sa, seed=0):
     np.random.seed(seed)
     torch.manual_seed(seed)
     dl = [copy.deepcopy(g) for _ in range(n)]
-    S.randomize_position(dl, False, False, sa.tr_sigma_max, flexible_sidechains='flexResidues' in g)
+    S.randomize_position(dl, False, False, sa.tr_sigma_max, flexible_sidechains='flexResidues' in g and 'edge_idx' in g['flexResidues'])
     return dl
 
 
