@@ -15,6 +15,7 @@ The per-graph diffusion time is read from ``data.complex_t['tr']`` (``set_time``
 value to every node of a graph, utils/diffusion_utils.py:124-149).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -645,6 +646,8 @@ class TensorProductScoreModel(nn.Module):
             self._br[key] = _Branches(device)
         return self._br[key]
 
+    replay_launches = os.environ.get('DDP_NO_REPLAY', '') == ''     # A/B switch of the recorded launch sequences
+
     def launch_plan(self, pl, return_layers=False):
         """Kernel launches only (per-graph scalars already staged in ``pl.scal``): CUDA-graph capturable.
 
@@ -655,7 +658,7 @@ class TensorProductScoreModel(nn.Module):
         capture tensors, never the plan itself: a plan -> record -> plan cycle would keep freed plans away from the caching
         allocator until the cyclic GC runs, and every new plan would pay cudaMalloc.)"""
         key = (self.conv_mode, torch.cuda.current_stream().cuda_stream, getattr(self, 'group_convs', True), id(self.packed()))
-        debug = return_layers or getattr(self, 'profile', None) is not None
+        debug = return_layers or getattr(self, 'profile', None) is not None or not self.replay_launches
         prog = getattr(pl, 'program', None)
         if prog is not None and prog[0] == key and not debug:
             base = torch.cuda.current_stream()
