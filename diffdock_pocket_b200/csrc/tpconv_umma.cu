@@ -38,11 +38,12 @@ constexpr uint32_t MAGIC = 0x44445055u;  // "DDPU"
 
 struct TileDesc {
     uint16_t n_cols;      // UMMA N of this weight tile (multiple of 16): n_rows * mul_out rounded up, rest zero padding
-    uint8_t kind;         // basis of every row of the tile: 0 x*s0, 1 dot(xv,s1), 2 x*s1, 3 xv*s0, 4 cross(xv,s1)
+    uint8_t kind;         // basis of every row of the tile: 0 x*s0, 1 dot(xv,s1), 2 x*s1, 3 xv*s0, 4 cross(xv,s1),
+                          // 5 (sh_lmax = 2 only) C(1,2,1)(xv, s2): the l = 2 harmonics as a 3 x 3 matrix applied to xv
     uint8_t n_rows;       // basis rows covered
     uint16_t out_off;     // first output feature of the block
     uint8_t flags;        // bit 0: first tile of its block; bit 1: swap the last input irrep into slot 0 first; bit 2: last tile
-    uint8_t pad0;
+    uint8_t ctab5;        // kind 5: which 45-float coupling table of the image (Header::ctab5_off)
     uint16_t x_off;       // slot of the first input feature of row 0 (row rr reads x_off + rr * (kind 0/2 ? 1 : 3))
     uint16_t pad1;
     uint32_t pad2;
@@ -55,6 +56,8 @@ struct Header {
     int32_t f_in, f_out, n_parts;
     int32_t slab_elems_max;   // elements (bf16) of the largest slab part (one of hi / lo)
     int64_t tiles_off, slabs_off, total_bytes;
+    int32_t sh_dim, n_ctab5;  // 4 (sh_lmax 1) or 9 (sh_lmax 2); coupling tables [i][j][k] (3 x 5 x 3 floats each) of the kind-5 groups
+    int64_t ctab5_off;
 };
 
 __host__ __device__ inline int slab_bytes(int n_cols, int stage_k, int mode) { return n_cols * stage_k * 2 * (mode ? 2 : 1); }
@@ -560,7 +563,9 @@ __device__ __forceinline__ void gather_rows(const ddp_tpconv_edges_t &ed, int n_
     fence_proxy_async();
 }
 
-template <int NS, int NV, int KS, bool SPLIT>
+// L2: the edge harmonics have 9 components (sh_lmax = 2, e3nn FullyConnectedTensorProduct trunk convs) and kind-5 tiles
+// exist; a separate instantiation so that the sh_lmax = 1 kernel keeps its register allocation.
+template <int NS, int NV, int KS, bool SPLIT, bool L2>
 __global__ void __launch_bounds__(N_THREADS, 1)
 tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
     using C = Cfg<NS, NV, KS, SPLIT>;
@@ -903,9 +908,14 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
             if (valid) {
                 agg = __ldg(ed.agg + e);
                 if (ed.agg_deg != nullptr) inv_deg = __frcp_rn((float)max(__ldg(ed.agg_deg + agg), 1));
-                const float4 sh4 = __ldg(reinterpret_cast<const float4 *>(ed.sh + (size_t)e * 4));
                 // every basis row is linear in the edge harmonics: scaling them applies the scatter-mean for free
-                s0 = sh4.x * inv_deg; s1x = sh4.y * inv_deg; s1y = sh4.z * inv_deg; s1z = sh4.w * inv_deg;
+                if (L2) {
+                    const float *shp = ed.sh + (size_t)e * 9;         // [s0 | s1 (3) | s2 (5)]: rows are not 16-byte aligned
+                    s0 = __ldg(shp) * inv_deg; s1x = __ldg(shp + 1) * inv_deg; s1y = __ldg(shp + 2) * inv_deg; s1z = __ldg(shp + 3) * inv_deg;
+                } else {
+                    const float4 sh4 = __ldg(reinterpret_cast<const float4 *>(ed.sh + (size_t)e * 4));
+                    s0 = sh4.x * inv_deg; s1x = sh4.y * inv_deg; s1y = sh4.z * inv_deg; s1z = sh4.w * inv_deg;
+                }
                 xg = ed.x + (size_t)__ldg(ed.gather + e) * ed.ldx;
             }
             // runs of equal aggregation nodes inside this warp's 32 edges: seg = off | steps << 8 | is_tail << 16
@@ -1022,6 +1032,30 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                                 const bool on = rr < n_rows;
                                 bx[rr] = on ? xn[3 * rr] * s0 : 0.f; by[rr] = on ? xn[3 * rr + 1] * s0 : 0.f; bz[rr] = on ? xn[3 * rr + 2] * s0 : 0.f;
                             }
+                        } else if (L2 && kind == 5) {
+                            // b_k = sum_{i,j} C[i][j][k] x_i s2_j: fold the five l = 2 harmonics of the edge into a 3 x 3 matrix
+                            // first (45 uniform table reads, 2 such tiles per edge tile), then apply it to every input vector
+                            const float *c5 = reinterpret_cast<const float *>(jobs.job[0].image + hdr->ctab5_off) + 45 * (int)((tdw.y >> 24) & 0xffu);
+                            float m[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+                            if (valid) {
+                                const float *s2p = ed.sh + (size_t)e * 9 + 4;
+#pragma unroll
+                                for (int j = 0; j < 5; ++j) {
+                                    const float sj = __ldg(s2p + j) * inv_deg;
+#pragma unroll
+                                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                                        for (int k = 0; k < 3; ++k) m[i][k] = fmaf(__ldg(c5 + (i * 5 + j) * 3 + k), sj, m[i][k]);
+                                }
+                            }
+#pragma unroll
+                            for (int rr = 0; rr < NV; ++rr) {
+                                const bool on = rr < n_rows;
+                                const float ax = on ? xn[3 * rr] : 0.f, ay = on ? xn[3 * rr + 1] : 0.f, az = on ? xn[3 * rr + 2] : 0.f;
+                                bx[rr] = ax * m[0][0] + ay * m[1][0] + az * m[2][0];
+                                by[rr] = ax * m[0][1] + ay * m[1][1] + az * m[2][1];
+                                bz[rr] = ax * m[0][2] + ay * m[1][2] + az * m[2][2];
+                            }
                         } else {
 #pragma unroll
                             for (int rr = 0; rr < NV; ++rr) {
@@ -1101,6 +1135,7 @@ struct HostPlan {
     Header h;
     std::vector<TileDesc> tiles;
     std::vector<std::vector<std::pair<int, float>>> tile_cols;  // per tile: (weight column or -1, scale) per UMMA column
+    std::vector<float> ctab5;                                   // 45 floats per kind-5 group
 };
 
 static bool pick_cfg(int ns, int nv, int &ks) {
@@ -1118,6 +1153,7 @@ static int group_kind(const ddp_tp_group_t &g, const float *ctab, float &scale) 
     if (g.d1 == 1 && g.d2 == 3 && g.d_out == 3) { scale = c[0]; return 2; }          // delta_jk * scale
     if (g.d1 == 3 && g.d2 == 1 && g.d_out == 3) { scale = c[0]; return 3; }          // delta_ik * scale
     if (g.d1 == 3 && g.d2 == 3 && g.d_out == 3) { scale = c[(0 * 3 + 1) * 3 + 2]; return 4; }  // eps_ijk * scale
+    if (g.d1 == 3 && g.d2 == 5 && g.d_out == 3) { scale = 1.f; return 5; }           // C(1,2,1): the table itself goes into the image
     return -1;
 }
 
@@ -1130,13 +1166,13 @@ static int build_plan(const ddp_tpconv_t &c, const ddp_tp_group_t *groups, const
         if (groups[g].d_out == 3) { nv = groups[g].mul_out; break; }
     if (nv == 0) nv = (ns == 60) ? 10 : (ns == 24 ? 6 : 4);
     if (!pick_cfg(ns, nv, ks)) return DDP_E_UNSUPPORTED;
-    if (c.k1 != 3 * ns || c.hid != 3 * ns || c.n_emb != ns || c.sh_dim != 4) return DDP_E_UNSUPPORTED;
+    if (c.k1 != 3 * ns || c.hid != 3 * ns || c.n_emb != ns || (c.sh_dim != 4 && c.sh_dim != 9)) return DDP_E_UNSUPPORTED;
     const bool ts = use_ts(mode != 0);
     const int rows_s = rows_scalar(ns, ts), rows_v = rows_vector(nv);
     Header &h = P.h;
     memset(&h, 0, sizeof(h));
     h.magic = MAGIC; h.mode = mode; h.ns = ns; h.nv = nv; h.ks = ks; h.kp = 3 * ks; h.n1 = 3 * ks;
-    h.stage_k = stage_k_of(ks, mode != 0); h.f_in = c.f_in; h.f_out = c.f_out;
+    h.stage_k = stage_k_of(ks, mode != 0); h.f_in = c.f_in; h.f_out = c.f_out; h.sh_dim = c.sh_dim;
     // groups sharing (out_off, d_out) form one weight block (one accumulation of the kernel); they are contiguous in
     // w_off order.  Every tile covers rows of ONE group, so its basis kind and x stride are uniform.
     int g = 0;
@@ -1151,7 +1187,14 @@ static int build_plan(const ddp_tpconv_t &c, const ddp_tp_group_t *groups, const
             float sc;
             const int kind = group_kind(groups[q], ctab_host, sc);
             if (kind < 0 || (vec != (kind >= 2))) return DDP_E_UNSUPPORTED;
-            if (groups[q].sh_off != ((kind == 0 || kind == 3) ? 0 : 1)) return DDP_E_UNSUPPORTED;
+            if (kind == 5 && c.sh_dim != 9) return DDP_E_UNSUPPORTED;
+            if (groups[q].sh_off != (kind == 5 ? 4 : ((kind == 0 || kind == 3) ? 0 : 1))) return DDP_E_UNSUPPORTED;
+            int table5 = 0;
+            if (kind == 5) {
+                table5 = (int)P.ctab5.size() / 45;
+                if (table5 > 255) return DDP_E_UNSUPPORTED;
+                P.ctab5.insert(P.ctab5.end(), ctab_host + groups[q].c_off, ctab_host + groups[q].c_off + 45);
+            }
             const int d1 = groups[q].d1;
             // rows per tile: scalar tiles ROWS_S; x (x) s1 tiles 2 NV (two epilogue passes); stride-3 vector kinds NV
             const int per = !vec ? rows_s : (kind == 2 ? rows_v : nv);
@@ -1161,6 +1204,7 @@ static int build_plan(const ddp_tpconv_t &c, const ddp_tp_group_t *groups, const
                 memset(&td, 0, sizeof(td));
                 td.n_cols = (uint16_t)(vec ? ncol_vector(nv, nr) : ncol_scalar(ns, ts));
                 td.kind = (uint8_t)kind;
+                td.ctab5 = (uint8_t)table5;
                 td.n_rows = (uint8_t)nr;
                 td.out_off = (uint16_t)groups[g].out_off;
                 const int xo = groups[q].x_off + r0 * d1;   // first gathered feature the tile reads
@@ -1182,6 +1226,9 @@ static int build_plan(const ddp_tpconv_t &c, const ddp_tp_group_t *groups, const
     int64_t off = (sizeof(Header) + 127) / 128 * 128;
     h.tiles_off = off;
     off += (int64_t)((h.n_tiles * sizeof(TileDesc) + 127) / 128 * 128);
+    h.n_ctab5 = (int)P.ctab5.size() / 45;
+    h.ctab5_off = off;
+    off += (int64_t)((P.ctab5.size() * sizeof(float) + 127) / 128 * 128);
     h.slabs_off = off;
     int64_t slab_total = (int64_t)slab_bytes(h.n1, h.stage_k, mode) * (h.kp / h.stage_k);
     for (auto &td : P.tiles) slab_total += (int64_t)slab_bytes(td.n_cols, h.stage_k, mode) * (h.kp / h.stage_k);
@@ -1243,6 +1290,7 @@ extern "C" int64_t ddp_tpconv_pack(const ddp_tpconv_t *conv, const ddp_tp_group_
     memset(base, 0, (size_t)h.total_bytes);
     memcpy(base, &h, sizeof(h));
     memcpy(base + h.tiles_off, P.tiles.data(), P.tiles.size() * sizeof(TileDesc));
+    if (!P.ctab5.empty()) memcpy(base + h.ctab5_off, P.ctab5.data(), P.ctab5.size() * sizeof(float));
     const int ns = h.ns, ks = h.ks, hid = conv->hid, k1 = conv->k1;
     uint8_t *dst = base + h.slabs_off;
     // GEMM1 operand: rows n = hidden unit, k' = source * ks + j; bias in (source 0, j = ns); row `hid` regenerates the one
@@ -1269,10 +1317,10 @@ extern "C" int64_t ddp_tpconv_pack(const ddp_tpconv_t *conv, const ddp_tp_group_
     return (dst - base) == h.total_bytes ? 0 : DDP_E_SHAPE;
 }
 
-template <int NS, int NV, int KS, bool SPLIT>
-static int launch_umma(const umma::Jobs &jobs, int tiles_cap, cudaStream_t st) {
+template <int NS, int NV, int KS, bool SPLIT, bool L2>
+static int launch_umma_l(const umma::Jobs &jobs, int tiles_cap, cudaStream_t st) {
     using C = umma::Cfg<NS, NV, KS, SPLIT>;
-    auto kern = umma::tpconv_umma_kernel<NS, NV, KS, SPLIT>;
+    auto kern = umma::tpconv_umma_kernel<NS, NV, KS, SPLIT, L2>;
     static bool configured[DDP_MAX_DEVICES] = {false};
     cudaError_t err = ddp_smem_opt_in(kern, C::SMEM, configured);
     if (err != cudaSuccess) return (int)err;
@@ -1280,6 +1328,11 @@ static int launch_umma(const umma::Jobs &jobs, int tiles_cap, cudaStream_t st) {
     kern<<<grid, umma::N_THREADS, C::SMEM, st>>>(jobs);
     DDP_LAUNCH_CHECK();
     return 0;
+}
+
+template <int NS, int NV, int KS, bool SPLIT>
+static int launch_umma(const umma::Jobs &jobs, int tiles_cap, cudaStream_t st, bool l2) {
+    return l2 ? launch_umma_l<NS, NV, KS, SPLIT, true>(jobs, tiles_cap, st) : launch_umma_l<NS, NV, KS, SPLIT, false>(jobs, tiles_cap, st);
 }
 
 static long long *g_umma_trace = nullptr;
@@ -1310,8 +1363,10 @@ extern "C" int ddp_tpconv_umma_group(const ddp_tpconv_t *const *convs, const voi
         const ddp_tpconv_t &c = *convs[j];
         const ddp_tpconv_edges_t &e = *edges[j];
         // one tile table for the whole launch: same irreps / weight layout in every job
-        if (c.ns != c0.ns || c.f_in != c0.f_in || c.f_out != c0.f_out || c.w_numel != c0.w_numel || c.n_groups != c0.n_groups)
+        if (c.ns != c0.ns || c.f_in != c0.f_in || c.f_out != c0.f_out || c.w_numel != c0.w_numel || c.n_groups != c0.n_groups ||
+            c.sh_dim != c0.sh_dim)
             return DDP_E_SHAPE;
+        if (c.sh_dim != 4 && c.sh_dim != 9) return DDP_E_UNSUPPORTED;
         if (!e.emb || !e.x || !e.gather || !e.sh || !e.agg || !e.n_edges_dev || !e.p1 || !e.p2 || !e.i1 || !e.i2) return DDP_E_ARG;
         if (e.ew != nullptr) return DDP_E_UNSUPPORTED;
         if ((e.ldx & 1) || (c.f_out & 1)) return DDP_E_UNSUPPORTED;      // 8-byte aligned rows (vector loads / reductions)
@@ -1324,9 +1379,10 @@ extern "C" int ddp_tpconv_umma_group(const ddp_tpconv_t *const *convs, const voi
     }
     if (jobs.n == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (c0.ns == 60) return mode ? launch_umma<60, 10, 64, true>(jobs, tiles_cap, st) : launch_umma<60, 10, 64, false>(jobs, tiles_cap, st);
-    if (c0.ns == 24) return mode ? launch_umma<24, 6, 32, true>(jobs, tiles_cap, st) : launch_umma<24, 6, 32, false>(jobs, tiles_cap, st);
-    if (c0.ns == 16) return mode ? launch_umma<16, 4, 32, true>(jobs, tiles_cap, st) : launch_umma<16, 4, 32, false>(jobs, tiles_cap, st);
+    const bool l2 = c0.sh_dim == 9;
+    if (c0.ns == 60) return mode ? launch_umma<60, 10, 64, true>(jobs, tiles_cap, st, l2) : launch_umma<60, 10, 64, false>(jobs, tiles_cap, st, l2);
+    if (c0.ns == 24) return mode ? launch_umma<24, 6, 32, true>(jobs, tiles_cap, st, l2) : launch_umma<24, 6, 32, false>(jobs, tiles_cap, st, l2);
+    if (c0.ns == 16) return mode ? launch_umma<16, 4, 32, true>(jobs, tiles_cap, st, l2) : launch_umma<16, 4, 32, false>(jobs, tiles_cap, st, l2);
     return DDP_E_UNSUPPORTED;
 }
 

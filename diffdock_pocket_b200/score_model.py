@@ -241,7 +241,12 @@ class PackedConv:
             w1, b1 = self.w1_host, self.b1_host
             w2, b2 = self.w2_host, self.b2_host
             ctab = torch.tensor(self.spec.ctab, dtype=torch.float32)
-            args = (C.byref(self.cdesc), self.groups_host, ptr(ctab), ptr(w1), ptr(b1), ptr(w2), ptr(b2), mode)
+            # the packer builds one accumulation block per run of groups with the same output irrep: hand it the groups
+            # sorted by output (e3nn orders FullyConnectedTensorProduct instructions by input irrep, which would split every
+            # output into several blocks, i.e. several flushes per edge tile); weight columns are addressed through w_off
+            order = sorted(range(len(self.spec.groups)), key=lambda i: self.spec.groups[i]['out_off'])
+            garr = (_lib.TpGroup * len(order))(*[_lib.TpGroup(**self.spec.groups[i]) for i in order])
+            args = (C.byref(self.cdesc), garr, ptr(ctab), ptr(w1), ptr(b1), ptr(w2), ptr(b2), mode)
             size = L.ddp_tpconv_pack(*args, None)
             if size <= 0:
                 raise RuntimeError(f'ddp_tpconv_pack failed ({size}): conv is not tensor-core eligible')

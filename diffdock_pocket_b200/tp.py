@@ -205,6 +205,11 @@ def fctp_spec(in_irreps, sh_irreps, out_irreps, sh_keep=None, sh_base=0):
         spec.add(wigner_3j(l1, l2, lo) * coeff, xo[i1], m1, sh_off[i2], w, oo[io], mo)
         w += m1 * mo
     spec.weight_numel = w
+    # tensor-core candidates: node irreps with l <= 1 and the plain spherical harmonics up to l = 1 or 2 as second operand --
+    # every instruction is then one of the six row kinds of csrc/tpconv_umma.cu (x s0, x1.s1, x (x) s1, x1 s0, x1 x s1, and,
+    # for sh_lmax = 2, C(1,2,1)(x1, s2))
+    plain_sh = [tuple(t) for t in sh_irreps] in ([(1, 0, 1), (1, 1, -1)], [(1, 0, 1), (1, 1, -1), (1, 2, 1)])
+    spec.tc_eligible = bool(sh_keep is None and plain_sh and all(l <= 1 for _, l, _ in in_irreps) and all(l <= 1 for _, l, _ in out_irreps))
     return spec
 
 

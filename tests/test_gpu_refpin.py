@@ -128,7 +128,7 @@ def test_big_confidence_and_forward_side_effects_vs_reference():
     assert np.array_equal(b['atom', 'atom'].edge_index.cpu().numpy().astype(np.int32), z['side_aa_edge_index'])
 
 
-@pytest.mark.parametrize('name,mode', [('small', 'fp32'), ('small', 'bf16x3'), ('small', 'bf16'), ('lmax2', 'fp32')])
+@pytest.mark.parametrize('name,mode', [('small', 'fp32'), ('small', 'bf16x3'), ('small', 'bf16'), ('lmax2', 'fp32'), ('lmax2', 'bf16x3'), ('lmax2', 'bf16')])
 def test_small_models_forward_vs_reference(name, mode):
     z = _z('ref_forward_small.npz')
     m, c, sa, ca = _small(**(dict(sh_lmax=2, num_conv_layers=3) if name == 'lmax2' else {}))
@@ -140,6 +140,30 @@ def test_small_models_forward_vs_reference(name, mode):
     with torch.no_grad():
         conf = c(T.batch_at(dl, 0.0))
     assert T.rel_err(conf, z[f'{name}_confidence']) < 1e-4
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16x3', 'bf16'])
+@pytest.mark.parametrize('case', list(refpin.CONV_CASES))
+def test_conv_operator_vs_reference_score_model_py(case, mode):
+    """models/score_model.py:84-125 (TensorProductConvLayer with FasterTensorProduct, and with the e3nn FullyConnectedTensorProduct
+    over lmax-2 harmonics) executed unmodified vs the operator-level drop-in in every conv mode.  The tensor-core kernel takes the
+    trunk shapes (sh_lmax 1 and 2); 'final' (2x1o + 2x1e outputs) is not a shape it is built for and must fall back to the fp32
+    kernel rather than fail."""
+    from diffdock_pocket_b200.score_model import TensorProductConvLayer
+    from diffdock_pocket_b200 import tp as tpmod
+    z = _z('ref_ops.npz')
+    in_ir, out_ir, nf, faster, sh_ir = refpin.CONV_CASES[case]
+    conv = TensorProductConvLayer(in_ir, sh_ir, out_ir, nf, residual=False, batch_norm=True, faster=faster)
+    refpin.np_fill(conv, 7)
+    conv = conv.to(DEV).eval()
+    assert tpmod.umma_supported(conv.tp.spec, nf // 3) == (case != 'final')
+    x, ei, ea, sh = refpin.conv_inputs(case)
+    conv.conv_mode = mode
+    with torch.no_grad():
+        got = conv(x.to(DEV), ei.to(DEV), ea.to(DEV), sh.to(DEV), out_nodes=x.shape[0] + 3)
+    want = z[f'conv_{case}_out']
+    tol = TOL[mode] if case != 'final' else 1e-4
+    assert T.rel_err(got, want) < tol and T.rel_err_cols(got, want) < 4 * tol, (case, mode, T.rel_err(got, want), T.rel_err_cols(got, want))
 
 
 def test_rigid_ligand_forward_vs_reference():
