@@ -450,6 +450,37 @@ def main():
         ms = float(t.item())
     value = total_samples / (ms / 1000.0)
 
+    # ---- roofline of the dominant kernel: instrumented forward (events around every fused conv launch) -----
+    roof = None
+    if rank == 0:
+        peak_tf, hbm, peak_src = peaks()
+        pl = plans[0]
+        ct = {k: torch.full((len(chunks[0]),), 0.5) for k in ('tr', 'rot', 'tor', 'sc_tor')}
+        model.profile = []
+        with torch.no_grad():
+            model.run_plan(pl, ct)
+        torch.cuda.synchronize()
+        tot_ms, tot_fl, tot_bytes, n_l, li = 0.0, 0.0, 0.0, 0, 0
+        from diffdock_pocket_b200 import tp as tpmod
+        dims = [tpmod.irreps_dim(tpmod.parse_irreps(q)) for q in model.irrep_seq]
+        for (e0, e1, convs) in model.profile:
+            tot_ms += e0.elapsed_time(e1)
+            tot_fl += sum(conv_flops(ns, w_numel) * int(es.n_dev.item()) for (w_numel, es, ns) in convs)
+            tot_bytes += sum(conv_bytes(ns, dims[min(li, 3)], int(es.n_dev.item())) for (w_numel, es, ns) in convs)
+            li += 1
+            n_l += 1
+        model.profile = None
+        ach = tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
+        # DRAM bytes of one conv launch (dram__bytes_read + write, ncu --set full of the grouped layer-3 launch of this
+        # same batch: profiles/r1_ncu_umma_v27_summary.txt); far below the algorithmic 1.2 kB/edge because gathered
+        # node rows and the weight image are served by L2
+        traffic, traffic_src = ncu_traffic(args)
+        roof = {'bound': 'tensor', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'traffic': traffic,
+                'kernel': 'tpconv_umma_kernel' if args.mode != 'fp32' else 'tpconv_fp32_kernel', 'launches_measured': n_l,
+                'peak_source': peak_src, 'conv_share_of_forward_ms': tot_ms, 'traffic_source': traffic_src,
+                # BASELINE.json's metric also names "TP-conv GB/s": the fused kernel's ALGORITHMIC bytes (SURVEY 8(d): edge
+                # embedding + two scalar blocks + gathered features + indices per edge, output rows once) over its time
+                'algorithmic_gbs': tot_bytes / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0, 'hbm_peak_gbs': hbm}
     # e2e: same metric through sampling() with host buffers
     n_e2e = max(3, min(args.steps, 5))
     e2e_inputs = [copy.deepcopy(dl0) for _ in range(n_e2e + 2)]      # host graphs (sampling() updates them in place)
@@ -507,37 +538,6 @@ def main():
         del R3
         model.conv_mode = conf.conv_mode = args.mode
 
-    # ---- roofline of the dominant kernel: instrumented forward (events around every fused conv launch) -----
-    roof = None
-    if rank == 0:
-        peak_tf, hbm, peak_src = peaks()
-        pl = plans[0]
-        ct = {k: torch.full((len(chunks[0]),), 0.5) for k in ('tr', 'rot', 'tor', 'sc_tor')}
-        model.profile = []
-        with torch.no_grad():
-            model.run_plan(pl, ct)
-        torch.cuda.synchronize()
-        tot_ms, tot_fl, tot_bytes, n_l, li = 0.0, 0.0, 0.0, 0, 0
-        from diffdock_pocket_b200 import tp as tpmod
-        dims = [tpmod.irreps_dim(tpmod.parse_irreps(q)) for q in model.irrep_seq]
-        for (e0, e1, convs) in model.profile:
-            tot_ms += e0.elapsed_time(e1)
-            tot_fl += sum(conv_flops(ns, w_numel) * int(es.n_dev.item()) for (w_numel, es, ns) in convs)
-            tot_bytes += sum(conv_bytes(ns, dims[min(li, 3)], int(es.n_dev.item())) for (w_numel, es, ns) in convs)
-            li += 1
-            n_l += 1
-        model.profile = None
-        ach = tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
-        # DRAM bytes of one conv launch (dram__bytes_read + write, ncu --set full of the grouped layer-3 launch of this
-        # same batch: profiles/r1_ncu_umma_v27_summary.txt); far below the algorithmic 1.2 kB/edge because gathered
-        # node rows and the weight image are served by L2
-        traffic, traffic_src = ncu_traffic(args)
-        roof = {'bound': 'tensor', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'traffic': traffic,
-                'kernel': 'tpconv_umma_kernel' if args.mode != 'fp32' else 'tpconv_fp32_kernel', 'launches_measured': n_l,
-                'peak_source': peak_src, 'conv_share_of_forward_ms': tot_ms, 'traffic_source': traffic_src,
-                # BASELINE.json's metric also names "TP-conv GB/s": the fused kernel's ALGORITHMIC bytes (SURVEY 8(d): edge
-                # embedding + two scalar blocks + gathered features + indices per edge, output rows once) over its time
-                'algorithmic_gbs': tot_bytes / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0, 'hbm_peak_gbs': hbm}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, dt = cpu_arm(args, args.cpu_samples, args.cpu_steps, os.cpu_count())

@@ -2,8 +2,9 @@
 
 ``infer_single_complex`` follows inference.py:106-291 up to the ranking step (:135 copy the complex graph
 ``samples_per_complex`` times, :140 ``randomize_position``, :177 ``sampling``, :198-219 gather poses in the original
-frame and sort by confidence, descending); writing SDF / PDB files (:221-280) stays with the reference's own code,
-which consumes exactly the arrays returned here.  ``infer_multiple_complexes`` is the per-device loop (:294-304) with
+frame and sort by confidence, descending); the ranked SDF / PDB files (:221-240) are written by ``writer.AsyncWriter``
+(text-level, on worker threads) when the rows carry the template files' lines; relaxation (:242-262) stays with the
+reference's OpenMM code.  ``infer_multiple_complexes`` is the per-device loop (:294-304) with
 the reference's per-complex failure isolation (:282-287: a failing complex is reported and skipped).
 
 Multi-GPU: the reference splits the complex table with ``np.array_split`` over a spawn pool (inference.py:466-488).
@@ -12,6 +13,7 @@ collective: an all-gather of every complex's best confidence so that all ranks h
 (virtual-screening use, BASELINE.json configs[4]).
 """
 import copy
+import os
 import traceback
 from argparse import Namespace
 from functools import partial
@@ -41,7 +43,7 @@ def default_args(**over):
 
 def infer_single_complex(idx, protein_ligand_info_row, model, args, score_model_args, filtering_args=None,
                          filtering_model=None, filtering_model_args=None, filtering_complex_dict=None, t_schedule=None,
-                         tr_schedule=None, device=None, defer=False):
+                         tr_schedule=None, device=None, defer=False, writer=None, out_dir=None):
     """-> dict(name, ligand_pos [spc, N_l, 3], atom_pos [spc, N_a, 3], confidence [spc] or None), poses in the original
     frame and sorted by confidence (descending); ``None`` if the complex failed (the reference returns 0 and goes on).
     ``defer=True`` returns a zero-argument callable producing that result instead: all GPU work is enqueued, nothing has
@@ -84,10 +86,23 @@ def infer_single_complex(idx, protein_ligand_info_row, model, args, score_model_
     def finish():
         try:
             graphs, confidence = pending()
-            return _rank(orig, idx, graphs, confidence)             # inference.py:198-219
+            res = _rank(orig, idx, graphs, confidence)              # inference.py:198-219
+            _submit_write(writer, out_dir, protein_ligand_info_row, res, flex)
+            return res
         except Exception as e:
             return failed(e)
     return finish if defer else finish()
+
+
+def _submit_write(writer, out_dir, row, res, flex):
+    """inference.py:221-240 handed to ``writer.AsyncWriter`` (rows carry the template files' lines: 'ligand_sdf_lines' and,
+    for flexible side chains, 'protein_pdb_lines'); the files are written while the next complex is docked."""
+    if writer is None or res is None or 'ligand_sdf_lines' not in row:
+        return
+    g = row['complex_graph']
+    fr = g['flexResidues'] if flex and 'flexResidues' in g and 'edge_idx' in g['flexResidues'] else None
+    writer.submit(os.path.join(out_dir or '.', str(res['name'])), res, row['ligand_sdf_lines'],
+                  row.get('protein_pdb_lines') if fr is not None else None, fr)
 
 
 def _rank(orig, idx, graphs, confidence):
@@ -104,7 +119,7 @@ def _rank(orig, idx, graphs, confidence):
 
 
 def infer_complex_group(group, model, args, score_model_args, filtering_model=None, filtering_model_args=None,
-                        tr_schedule=None, t_schedule=None, device=None, defer=False):
+                        tr_schedule=None, t_schedule=None, device=None, defer=False, writer=None, out_dir=None):
     """Cross-complex batching (the reference's sampler assumes one complex per call, F9): the samples
     of several complexes share one ``sampling()`` call, so that small ``samples_per_complex`` still fill the mini-batch
     (virtual screening).  ``group``: [(idx, row), ...].  Falls back to one call per complex if the joint call fails.
@@ -116,7 +131,7 @@ def infer_complex_group(group, model, args, score_model_args, filtering_model=No
         print('Joint call failed for', [row['complex_graph'].name for _, row in group], e, '- retrying one complex at a time')
         return [infer_single_complex(idx, row, model, args, score_model_args, filtering_model=filtering_model,
                                      filtering_model_args=filtering_model_args, tr_schedule=tr_schedule, t_schedule=t_schedule,
-                                     device=device) for idx, row in group]
+                                     device=device, writer=writer, out_dir=out_dir) for idx, row in group]
     try:
         data_list = []
         for _, row in group:
@@ -140,8 +155,11 @@ def infer_complex_group(group, model, args, score_model_args, filtering_model=No
     def finish():
         try:
             graphs, confidence = pending()
-            return [_rank(row['complex_graph'], idx, graphs[k * spc:(k + 1) * spc],
-                          confidence[k * spc:(k + 1) * spc] if confidence is not None else None) for k, (idx, row) in enumerate(group)]
+            out = [_rank(row['complex_graph'], idx, graphs[k * spc:(k + 1) * spc],
+                         confidence[k * spc:(k + 1) * spc] if confidence is not None else None) for k, (idx, row) in enumerate(group)]
+            for (idx, row), res in zip(group, out):
+                _submit_write(writer, out_dir, row, res, flex)
+            return out
         except Exception as e:
             return one_by_one(e)
     return finish if defer else finish()
@@ -160,7 +178,7 @@ def infer_multiple_complexes(rows, *a, batch_complexes=False, pipeline=True, **k
         items, wrap = list(rows), (lambda r: [r])
     else:
         model, score_model_args = (a[0] if a else kw['model']), (a[2] if len(a) > 2 else kw['score_model_args'])
-        passthrough = {k: kw[k] for k in ('filtering_model', 'filtering_model_args', 'tr_schedule', 't_schedule', 'device') if k in kw}
+        passthrough = {k: kw[k] for k in ('filtering_model', 'filtering_model_args', 'tr_schedule', 't_schedule', 'device', 'writer', 'out_dir') if k in kw}
         launch = lambda grp: infer_complex_group(grp, model, args, score_model_args, defer=True, **passthrough)
         items, wrap = [rows[j:j + per_call] for j in range(0, len(rows), per_call)], (lambda r: r)
     results, pending = [], None
