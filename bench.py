@@ -54,6 +54,7 @@ def parse():
     p.add_argument('--complexes', type=int, default=None, help='pdbbind_synth: complexes (default 48; 363 = the whole test-set law); '
                                                                'screen: ligands (default 192; configs[4] names 10000)')
     p.add_argument('--no-pipeline', action='store_true', help='pdbbind_synth / screen: serial loop over the complexes (A/B of the software pipeline)')
+    p.add_argument('--profile-range', action='store_true', help='cudaProfilerStart/Stop around the timed resident steps (for ncu --profile-from-start off)')
     p.add_argument('--no-fp32-grade', action='store_true', help='skip the additional bf16x3 (fp32-grade) resident measurement')
     p.add_argument('--cpu-samples', type=int, default=4)
     p.add_argument('--cpu-steps', type=int, default=3)
@@ -435,12 +436,16 @@ def main():
     _lib.COUNTS.clear()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.profile_range:
+        torch.cuda.profiler.start()
     ev0.record()
     for _ in range(args.steps):
         resident_step()
         flush.fill_(0)                           # L2 flush between timed iterations (256 MiB > 126 MB L2)
     ev1.record()
     barrier()
+    if args.profile_range:
+        torch.cuda.profiler.stop()
     ms = ev0.elapsed_time(ev1) / args.steps
     launches = launches_per_step
     sampler.stop_flag = True
@@ -460,6 +465,23 @@ def main():
         with torch.no_grad():
             model.run_plan(pl, ct)
         torch.cuda.synchronize()
+        # the HBM-type kernels of the forward (BASELINE.json's metric names GB/s): events around each launch of a second
+        # instrumented forward on ONE stream (the edge-set chains normally run on side streams), algorithmic bytes / time
+        prof_conv, model.profile = model.profile, None
+        model.profile_small = []
+        with torch.no_grad():
+            model.run_plan(pl, ct)
+        torch.cuda.synchronize()
+        small = {}
+        for name, a, b, nbytes in model.profile_small:
+            d = small.setdefault(name, [0, 0.0, 0.0])
+            d[0] += 1
+            d[1] += a.elapsed_time(b)
+            d[2] += nbytes()
+        model.profile_small = None
+        model.profile = prof_conv
+        hbm_kernels = {k: {'launches': n, 'avg_us': 1e3 * ms_ / n, 'algorithmic_gbs': by / (ms_ * 1e-3) / 1e9, 'frac_of_hbm_peak': by / (ms_ * 1e-3) / 1e9 / hbm}
+                       for k, (n, ms_, by) in small.items() if ms_ > 0}
         tot_ms, tot_fl, tot_bytes, n_l, li = 0.0, 0.0, 0.0, 0, 0
         from diffdock_pocket_b200 import tp as tpmod
         dims = [tpmod.irreps_dim(tpmod.parse_irreps(q)) for q in model.irrep_seq]
@@ -480,7 +502,8 @@ def main():
                 'peak_source': peak_src, 'conv_share_of_forward_ms': tot_ms, 'traffic_source': traffic_src,
                 # BASELINE.json's metric also names "TP-conv GB/s": the fused kernel's ALGORITHMIC bytes (edge
                 # embedding + two scalar blocks + gathered features + indices per edge, output rows once) over its time
-                'algorithmic_gbs': tot_bytes / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0, 'hbm_peak_gbs': hbm}
+                'algorithmic_gbs': tot_bytes / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0, 'hbm_peak_gbs': hbm,
+                'hbm_kernels': hbm_kernels}
     # e2e: same metric through sampling() with host buffers
     n_e2e = max(3, min(args.steps, 5))
     e2e_inputs = [copy.deepcopy(dl0) for _ in range(n_e2e + 2)]      # host graphs (sampling() updates them in place)

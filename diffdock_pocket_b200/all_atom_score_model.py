@@ -658,7 +658,7 @@ class TensorProductScoreModel(nn.Module):
         capture tensors, never the plan itself: a plan -> record -> plan cycle would keep freed plans away from the caching
         allocator until the cyclic GC runs, and every new plan would pay cudaMalloc.)"""
         key = (self.conv_mode, torch.cuda.current_stream().cuda_stream, getattr(self, 'group_convs', True), id(self.packed()))
-        debug = return_layers or getattr(self, 'profile', None) is not None or not self.replay_launches
+        debug = return_layers or getattr(self, 'profile', None) is not None or getattr(self, 'profile_small', None) is not None or not self.replay_launches
         prog = getattr(pl, 'program', None)
         if prog is not None and prog[0] == key and not debug:
             base = torch.cuda.current_stream()
@@ -684,6 +684,20 @@ class TensorProductScoreModel(nn.Module):
             _lib.RECORD = None
         pl.program = (key, rec, out)
         return out
+
+    def _small_begin(self):
+        """Instrumented forwards only (``model.profile_small = []``): CUDA events around the HBM-type kernels."""
+        if getattr(self, 'profile_small', None) is None:
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return ev
+
+    def _small_end(self, ev0, name, nbytes):
+        if ev0 is not None:
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record()
+            self.profile_small.append((name, ev0, ev1, nbytes))
 
     @staticmethod
     def _py(fn):
@@ -720,8 +734,11 @@ class TensorProductScoreModel(nn.Module):
             pa, pb, ga = geo[nm]
             e_ = es[nm]
             pre, npre = (pl.bond_attr, pl.Eb) if nm == 'll' else (None, 0)
+            t0 = self._small_begin()
             chk(L.ddp_edge_embed(ptr(pa), ptr(pb), ptr(e_.edge), e_.cap, ptr(e_.n_dev), ptr(ga), ptr(pre), npre, ptr(U[nm]),
                                  C.byref(em[nm]['desc']), ptr(e_.sh), ptr(e_.emb), st_), f'ddp_edge_embed({nm})')
+            # algorithmic bytes per edge: two positions + two indices in, harmonics + hidden activations out
+            self._small_end(t0, 'edge_embed_fold', lambda: int(e_.n_dev.item()) * (24 + 8 + 4 * (self.sh_dim + ns)))
 
         def build(nm, st_):
             e = es[nm]
@@ -815,7 +832,10 @@ class TensorProductScoreModel(nn.Module):
                     xr, Jr = update('r', xr, pl.NR, s_r, [('rr', 9 * l + 6), ('ar', 9 * l + 8), ('lr', 9 * l + 7)])
                     node_jobs.append(Jr)
                 xa = xa_new
+            t0 = self._small_begin()
             chk(L.ddp_node_update_multi((_lib.NodeUpdateJob * len(node_jobs))(*node_jobs), len(node_jobs), st), 'ddp_node_update_multi')
+            # algorithmic bytes per node: old features + the accumulated update in, new features out
+            self._small_end(t0, 'node_update_multi', lambda jobs_=tuple((J.n, J.f_old, J.f_new) for J in node_jobs): sum(4 * n * (fo + 2 * fn) for n, fo, fn in jobs_))
             xl = xl_new
             if return_layers:
                 layers_out.append((xl[:, :f_new].clone(), xa[:, :f_new if do_atom else f_old].clone(), xr.clone()))
