@@ -5,13 +5,20 @@
 //
 // One CTA (persistent, one per SM) walks 128-edge tiles (TMEM lane = edge) of up to 9 convolutions that share
 // irreps (the convs of one interaction layer): tile g of the launch belongs to job j with pref[j] <= g < pref[j+1].
-// Warp roles:
-//   warps 0-3  epilogue: after GEMM1 apply ReLU and write the hidden activations back as the A operand of GEMM2;
-//              then, per weight tile, tcgen05.ld the [128 x N] accumulator, multiply with the tensor-product basis
-//              (node features fetched from global memory into registers one tile ahead) and accumulate the edge's
-//              output in registers; at the end of each output block a warp-level segmented pre-reduction over runs of
-//              equal aggregation nodes, then vector red.global.add.  At an edge-tile boundary the next tile's hidden
-//              activations are written before the last flush and the next tile's per-edge set-up.
+// Warp roles (384 threads = three warpgroups; setmaxnreg moves registers from the middle one to the two epilogue ones):
+//   warps 0-3 and 8-11  epilogue, one warpgroup per TMEM accumulator (TMEM lane = edge in both): warpgroup g handles the
+//              weight tiles that land in accumulator g, i.e. every other tile of the image's tile order, with its own
+//              per-edge output registers.  Per weight tile: tcgen05.ld the [128 x N] accumulator, multiply with the
+//              tensor-product basis (node features fetched from global memory into registers one own tile ahead) and
+//              accumulate the edge's output in registers; when the warpgroup's next tile belongs to another output
+//              block, a warp-level segmented pre-reduction over runs of equal aggregation nodes, then vector
+//              red.global.add.  The packer interleaves the tiles of the first and the second half of the output blocks
+//              so that each warpgroup normally owns whole blocks (no duplicated atomics).  Warpgroup 0 also turns the
+//              GEMM1 result into the A operand of GEMM2 (ReLU, bf16, core-matrix order); at an edge-tile boundary it
+//              does so before its last flush and the next tile's per-edge set-up.
+//              Why two: the epilogue is a chain of dependent instructions (tile decode, basis, TMEM round trips) on ONE
+//              warp per scheduler, ~1350 cycles per scalar tile and ~2500 per vector tile against 1440 / 1250 cycles of
+//              MMAs (profiles/r2_umma_timeline_*.txt): a single warpgroup was busy 93 % of the time and set the pace.
 //   warp 4     TMA producer: streams the pre-packed weight image (already in UMMA core-matrix order and in
 //              consumption order) slab by slab.
 //   warps 5, 7 MMA issuers (one elected lane each), one per TMEM accumulator, so that one of them is always parked on
@@ -119,7 +126,7 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, lon
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
         if (!done && ++polls == (1ull << 18) && trace != nullptr && (threadIdx.x & 31) == 0) {
-            long long *rec = trace + ((size_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 4;
+            long long *rec = trace + ((size_t)blockIdx.x * 12 + (threadIdx.x >> 5)) * 4;   // 12 warps per CTA
             rec[0] = code; rec[1] = a; rec[2] = b; rec[3] = parity;
             __threadfence_system();
         }
@@ -267,6 +274,12 @@ __device__ __forceinline__ void tmem_ld4_async(uint32_t taddr, uint32_t (&r)[16]
                  : "r"(taddr)
                  : "memory");
 }
+__device__ __forceinline__ void tmem_ld8_async(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void red_add_v2(float *p, float a, float b) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
@@ -357,7 +370,11 @@ __host__ __device__ constexpr int rows_vector(int nv) { return 2 * nv; }
 __host__ __device__ constexpr int ncol_vector(int nv, int n_rows) { return (n_rows * nv + 15) / 16 * 16; }
 
 constexpr int MAX_JOBS = 9;
-constexpr int N_EPI = 128, N_GATHER = 64, N_THREADS = 256;   // N_GATHER: arrivals that complete an a_ready phase
+constexpr int N_EPI = 128, N_GATHER = 64, N_THREADS = 384;   // N_EPI: threads of ONE epilogue warpgroup; N_GATHER: arrivals that complete an a_ready phase
+// Registers per thread after the setmaxnreg hand-over: 384 threads start with 168 (64512 in total); the producer / issuer /
+// gather warpgroup keeps REGS_AUX, each epilogue warpgroup grows to REGS_EPI (128 * 104 + 256 * 200 = 64512).
+constexpr int REGS_AUX = 104, REGS_EPI = 200;
+static_assert(128 * REGS_AUX + 2 * N_EPI * REGS_EPI <= N_THREADS * 168, "register hand-over exceeds the CTA's allocation");
 
 // One fused convolution of a grouped launch.  All jobs of a launch share irreps (tile table, f_in, f_out).
 struct Job {
@@ -652,6 +669,10 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
     const Work &wk = *work;
     const int n_items = wk.n_items;
 
+    // register hand-over (warpgroup-wide; each setmaxnreg sits at the head of the code it governs so that ptxas allocates
+    // the two sides separately)
+    if (warp >= 4 && warp < 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX));
     if (C::DUAL && warp == 7 && (int)blockIdx.x < n_items) {
         // rows 64..127 of the CTA's first edge tile (then this warp turns MMA issuer)
         int g, t0, t1, job, et;
@@ -799,8 +820,8 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
             }
             hr_phase ^= 1u;
         }
-    } else if (warp == 6 || (warp == 7 && !C::DUAL)) {
-        // =============================== gather: A operand of the NEXT edge tile ===================
+    } else {
+        // =============================== gather: A operand of the NEXT edge tile (warp 6; warp 7 too without DUAL) ===
         // Two-issuer configurations: warp 6 stages all 128 rows of every edge tile (four per lane) except the CTA's
         // first one, where warp 7 -- idle as an issuer until the first hidden activations exist -- has taken rows
         // 64..127 (see above) so that the launch does not start with a single warp's gather latency.  Single-issuer
@@ -824,25 +845,29 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
             }
             mbar_arrive(&a_ready[ab]);
         }
+    }
     } else {
-        // =============================== epilogue warps ============================================
-        const int r = threadIdx.x;                       // edge row = TMEM lane
-        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-        uint32_t tf_phase = 0;                           // bit b: parity to wait on tmem_full[b]
+        // =============================== epilogue warps: one warpgroup per accumulator ==============
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
+        const uint32_t wg = (uint32_t)warp >> 3;         // accumulator this warpgroup reads (warps 0-3: 0, warps 8-11: 1)
+        const int r = threadIdx.x & 127;                 // edge row = TMEM lane
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const bool tracer = r == 0;                      // trace role 1 + wg
+        uint32_t tf_phase = 0;                           // parity to wait on tmem_full[wg] (warpgroup 0: GEMM1 results and tiles alike)
         const uint32_t a_row_off = (uint32_t)((r >> 3) * 128 + (r & 7) * 16);
+        const uint32_t taddr = tmem_base + lane_base + wg * (uint32_t)C::ACC_STRIDE;
         int it = 0;
-        int titer = 0;
-        // GEMM1 result -> ReLU -> hidden activations become the A operand of GEMM2 (TS: packed bf16 pairs into tensor memory,
-        // column c of the lane = k 2c, 2c + 1; SS: hi (/ lo) images back into the shared-memory A buffer in core-matrix
-        // order).  Needs nothing per edge, so at an item boundary it runs BEFORE the previous item's last flush and the
-        // next item's per-edge set-up (dependent global loads): tiles 0 and 1 of the next item are already on the tensor
-        // pipe while the epilogue does those.
+        // Warpgroup 0 only.  GEMM1 result -> ReLU -> hidden activations become the A operand of GEMM2 (TS: packed bf16 pairs
+        // into tensor memory, column c of the lane = k 2c, 2c + 1; SS: hi (/ lo) images back into the shared-memory A buffer
+        // in core-matrix order).  Needs nothing per edge, so at an item boundary it runs BEFORE the warpgroup's last flush
+        // and the next item's per-edge set-up (dependent global loads): tiles 0 and 1 of the next item are already on the
+        // tensor pipe while the epilogue does those.
         auto convert_hidden = [&](uint8_t *a_hi_, uint8_t *a_lo_, int it_) {
-            if (r == 0) trace_ev(jobs.trace, 1, titer, 0);
-            DDP_WAIT(&tmem_full[0], tf_phase & 1u, 8, it_, -1);
+            if (tracer) trace_ev(jobs.trace, 1, it_ * (n_tiles + 1), 0);
+            DDP_WAIT(&tmem_full[0], tf_phase, 8, it_, -1);
             tf_phase ^= 1u;
             tc_fence_after();
-            if (r == 0) trace_ev(jobs.trace, 1, titer, 1);
+            if (tracer) trace_ev(jobs.trace, 1, it_ * (n_tiles + 1), 1);
             {
                 uint32_t w[2][16];
                 tmem_ld16_async(tmem_base + lane_base, w[0]);
@@ -884,8 +909,7 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
             if (!C::TS) fence_proxy_async();
             mbar_arrive(h_ready);
             mbar_arrive(&tmem_empty[0]);
-            if (r == 0) trace_ev(jobs.trace, 1, titer, 2);
-
+            if (tracer) trace_ev(jobs.trace, 1, it_ * (n_tiles + 1), 2);
         };
         bool h_done = false;                             // the current item's hidden activations were written at the previous boundary
         for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
@@ -931,32 +955,42 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                 if (DDP_UMMA_SEGSCAN && __popc(heads) <= 16)
                     seg = off | ((32 - __clz(maxoff)) << 8) | ((lane_ == 31 || ((heads >> (lane_ + 1)) & 1u)) ? 1 << 16 : 0);
             }
-            // node features of weight tile 0 (registers; every tile prefetches the next one's)
+            // this warpgroup's tiles of the item: those in its accumulator (acc_of), i.e. every other one from tt_first
+            const int tt_first = (int)((wg ^ (uint32_t)nt) & 1u);
+            // node features of the first own weight tile (registers; every tile prefetches the next own one's)
             float xn[C::XN];
-            uint4 tdw = *reinterpret_cast<const uint4 *>(&tiles[t0]);
-            x_prefetch_tile<NS, NV, C::ROWS_S, C::XN>(xg, tdw, f_in, xn);
+            uint4 tdw = *reinterpret_cast<const uint4 *>(&tiles[min(t0 + tt_first, n_tiles - 1)]);
+            if (tt_first < nt) x_prefetch_tile<NS, NV, C::ROWS_S, C::XN>(xg, tdw, f_in, xn);
 
-            if (!h_done) convert_hidden(a_hi, a_lo, it);
+            if (wg == 0 && !h_done) convert_hidden(a_hi, a_lo, it);
             h_done = false;
-            ++titer;
             const bool has_next = w + (int)gridDim.x < n_items;
             uint8_t *a_hi_next = a_base + (size_t)((it + 1) % C::NBUF) * C::A_BYTES * (SPLIT ? 2 : 1);
 
             // ---- weight tiles: TMEM accumulator x tensor-product basis -> per-edge output registers ----
-            // Every tile has one basis kind; its node features arrive in registers (prefetched during the previous
+            // Every tile has one basis kind; its node features arrive in registers (prefetched during the previous own
             // tile); the accumulator is read 16 columns at a time with the next tcgen05.ld in flight under the FMAs.
             // Scalar tiles: ROWS_S rows in one pass; vector tiles: up to 2 NV rows in two passes of NV rows.
+            // The partial sums of an output block are zeroed at the warpgroup's first tile of the block (or of a split
+            // item) and flushed at its last one: when the two interleaved tile sequences are of unequal length both
+            // warpgroups hold partial sums of the same block and both add them.
             float acc[NS];
+            float u[NV];                                 // x (x) s1 tiles: scalar sums of the current run (see kind 2)
+            bool u_live = false;
+            int prev_off = -1;
 #pragma unroll 1
-            for (int tt = 0; tt < nt; ++tt, ++titer) {
+            for (int tt = tt_first; tt < nt; tt += 2) {
+                [[maybe_unused]] const int titer = it * (n_tiles + 1) + 1 + tt;    // trace row (full items)
                 const int t = t0 + tt;
                 const int kind = (int)((tdw.x >> 16) & 0xffu), n_rows = (int)(tdw.x >> 24);
                 const int out_off = (int)(tdw.y & 0xffffu);
-                // a split item starts / ends inside a block: its partial sums are zeroed / flushed at the item bounds
-                const int flags = (int)((tdw.y >> 16) & 0xffu) | (tt == 0 ? 1 : 0) | (tt == nt - 1 ? 4 : 0);
-                const uint32_t buf = acc_of(tt, nt);
-                const uint32_t taddr = tmem_base + lane_base + buf * (uint32_t)C::ACC_STRIDE;
-                if (flags & 1) {
+                const bool own_next = tt + 2 < nt;
+                uint4 tdn = tdw;
+                if (own_next) tdn = *reinterpret_cast<const uint4 *>(&tiles[t + 2]);
+                const bool blk_first = out_off != prev_off;
+                const bool blk_last = !own_next || (int)(tdn.y & 0xffffu) != out_off;
+                prev_off = out_off;
+                if (blk_first) {
 #pragma unroll
                     for (int o = 0; o < NS; ++o) acc[o] = 0.f;
                 }
@@ -971,15 +1005,12 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                         for (int rr = 0; rr < C::ROWS_S; ++rr)
                             b[rr] = rr < n_rows ? xn[3 * rr] * s1x + xn[3 * rr + 1] * s1y + xn[3 * rr + 2] * s1z : 0.f;
                     }
-                    if (tt + 1 < nt) {
-                        tdw = *reinterpret_cast<const uint4 *>(&tiles[t + 1]);
-                        x_prefetch_tile<NS, NV, C::ROWS_S, C::XN>(xg, tdw, f_in, xn);
-                    }
-                    if (r == 0) trace_ev(jobs.trace, 1, titer, 0);
-                    DDP_WAIT(&tmem_full[buf], (tf_phase >> buf) & 1u, 9, it, tt);
-                    tf_phase ^= 1u << buf;
+                    if (own_next) x_prefetch_tile<NS, NV, C::ROWS_S, C::XN>(xg, tdn, f_in, xn);
+                    if (tracer) trace_ev(jobs.trace, 1 + wg, titer, 0);
+                    DDP_WAIT(&tmem_full[wg], tf_phase, 9, it, tt);
+                    tf_phase ^= 1u;
                     tc_fence_after();
-                    if (r == 0) trace_ev(jobs.trace, 1, titer, 1);
+                    if (tracer) trace_ev(jobs.trace, 1 + wg, titer, 1);
                     tmem_ld16_async(taddr, w[0]);
                     constexpr int NCH = (C::NVAL_S + 15) / 16;
 #pragma unroll
@@ -993,10 +1024,10 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                         }
                     }
                     tc_fence_before();
-                    mbar_arrive(&tmem_empty[buf]);
-                    if (r == 0) trace_ev(jobs.trace, 1, titer, 2);
-                    if (tt == nt - 1 && has_next) { convert_hidden(a_hi_next, a_hi_next + C::A_BYTES, it + 1); h_done = true; }
-                    if (flags & 4) {
+                    mbar_arrive(&tmem_empty[wg]);
+                    if (tracer) trace_ev(jobs.trace, 1 + wg, titer, 2);
+                    if (wg == 0 && !own_next && has_next) { convert_hidden(a_hi_next, a_hi_next + C::A_BYTES, it + 1); h_done = true; }
+                    if (blk_last) {
                         if (valid && ed.out_scale != nullptr) {              // block offsets and widths are even: 8-byte loads
                             const float2 *sc2 = reinterpret_cast<const float2 *>(ed.out_scale + out_off);
 #pragma unroll
@@ -1010,102 +1041,128 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                         if (steps) seg_scan<NS>(acc, seg & 0xff, steps);
                         if (valid && (steps == 0 || (seg >> 16))) red_row<NS>(sum + (size_t)agg * f_out + out_off, acc);
                     }
-                    if (r == 0) trace_ev(jobs.trace, 1, titer, 3);
-                } else {
-                    // pass p covers basis rows [p NV, (p + 1) NV) = weight columns [p NV^2, (p + 1) NV^2)
-                    float bx[NV], by[NV], bz[NV];
-                    const int stride = kind == 2 ? 1 : 3;
-#pragma unroll 1
-                    for (int pass = 0; pass < 2; ++pass) {
-                        const int r0 = pass * NV;
-                        if (pass == 1 && n_rows <= NV) break;
-                        if (kind == 2) {
+                    if (tracer) trace_ev(jobs.trace, 1 + wg, titer, 3);
+                } else if (kind == 2) {
+                    // x (x) s1 tile (up to 2 NV scalar inputs): out[o][k] += s1[k] * sum_rr w[rr][o] x[rr].  The scalar sums
+                    // u[o] are accumulated over the run of such tiles -- one FMA per weight, the basis is the node feature
+                    // itself -- and expanded with the edge harmonics when the run ends (next own tile of another kind / block).
+                    if (!u_live) {
 #pragma unroll
-                            for (int rr = 0; rr < NV; ++rr) {
-                                // x (x) s1 tiles hold 2 NV scalars: pass 1 reads the upper half
-                                const float x0 = r0 + rr < n_rows ? (pass == 0 ? xn[rr] : xn[(NV + rr) % C::XN]) : 0.f;
-                                bx[rr] = x0 * s1x; by[rr] = x0 * s1y; bz[rr] = x0 * s1z;
-                            }
-                        } else if (kind == 3) {
+                        for (int o = 0; o < NV; ++o) u[o] = 0.f;
+                        u_live = true;
+                    }
 #pragma unroll
-                            for (int rr = 0; rr < NV; ++rr) {
-                                const bool on = rr < n_rows;
-                                bx[rr] = on ? xn[3 * rr] * s0 : 0.f; by[rr] = on ? xn[3 * rr + 1] * s0 : 0.f; bz[rr] = on ? xn[3 * rr + 2] * s0 : 0.f;
-                            }
-                        } else if (L2 && kind == 5) {
-                            // b_k = sum_{i,j} C[i][j][k] x_i s2_j: fold the five l = 2 harmonics of the edge into a 3 x 3 matrix
-                            // first (45 uniform table reads, 2 such tiles per edge tile), then apply it to every input vector
-                            const float *c5 = reinterpret_cast<const float *>(jobs.job[0].image + hdr->ctab5_off) + 45 * (int)((tdw.y >> 24) & 0xffu);
-                            float m[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-                            if (valid) {
-                                const float *s2p = ed.sh + (size_t)e * 9 + 4;
+                    for (int rr = 0; rr < C::ROWS_V; ++rr) xn[rr] = rr < n_rows ? xn[rr] : 0.f;     // padding columns are zero, their x is not
+                    if (tracer) trace_ev(jobs.trace, 1 + wg, titer, 0);
+                    DDP_WAIT(&tmem_full[wg], tf_phase, 10, it, tt);
+                    tf_phase ^= 1u;
+                    tc_fence_after();
+                    if (tracer) trace_ev(jobs.trace, 1 + wg, titer, 1);
+                    constexpr int NCOLS = C::ROWS_V * NV, NCH = NCOLS / 16, REM = NCOLS % 16;
+                    static_assert(REM == 0 || REM == 8, "x (x) s1 tile remainder is read with one x8 load");
+                    tmem_ld16_async(taddr, w[0]);
 #pragma unroll
-                                for (int j = 0; j < 5; ++j) {
-                                    const float sj = __ldg(s2p + j) * inv_deg;
-#pragma unroll
-                                    for (int i = 0; i < 3; ++i)
-#pragma unroll
-                                        for (int k = 0; k < 3; ++k) m[i][k] = fmaf(__ldg(c5 + (i * 5 + j) * 3 + k), sj, m[i][k]);
-                                }
-                            }
-#pragma unroll
-                            for (int rr = 0; rr < NV; ++rr) {
-                                const bool on = rr < n_rows;
-                                const float ax = on ? xn[3 * rr] : 0.f, ay = on ? xn[3 * rr + 1] : 0.f, az = on ? xn[3 * rr + 2] : 0.f;
-                                bx[rr] = ax * m[0][0] + ay * m[1][0] + az * m[2][0];
-                                by[rr] = ax * m[0][1] + ay * m[1][1] + az * m[2][1];
-                                bz[rr] = ax * m[0][2] + ay * m[1][2] + az * m[2][2];
-                            }
-                        } else {
-#pragma unroll
-                            for (int rr = 0; rr < NV; ++rr) {
-                                const bool on = rr < n_rows;
-                                const float ax = on ? xn[3 * rr] : 0.f, ay = on ? xn[3 * rr + 1] : 0.f, az = on ? xn[3 * rr + 2] : 0.f;
-                                bx[rr] = ay * s1z - az * s1y; by[rr] = az * s1x - ax * s1z; bz[rr] = ax * s1y - ay * s1x;
-                            }
-                        }
-                        (void)stride;
-                        if (pass == 0) {
-                            if (r == 0) trace_ev(jobs.trace, 1, titer, 0);
-                            DDP_WAIT(&tmem_full[buf], (tf_phase >> buf) & 1u, 10, it, tt);
-                            tf_phase ^= 1u << buf;
-                            tc_fence_after();
-                            if (r == 0) trace_ev(jobs.trace, 1, titer, 1);
-                        }
-                        if (pass == 1 || n_rows <= NV) {
-                            // the last basis rows are in registers: fetch the next tile's node features
-                            if (tt + 1 < nt) {
-                                tdw = *reinterpret_cast<const uint4 *>(&tiles[t + 1]);
-                                x_prefetch_tile<NS, NV, C::ROWS_S, C::XN>(xg, tdw, f_in, xn);
-                            }
-                        }
-                        const uint32_t tp = taddr + (uint32_t)(pass * C::PASS_COLS);
-                        constexpr int NCH = C::PASS_COLS / 16, REM = C::PASS_COLS % 16;
-                        static_assert(REM == 0 || REM == 4, "pass remainder is read with one x4 load");
-                        if (NCH > 0) tmem_ld16_async(tp, w[0]); else tmem_ld4_async(tp, w[0]);
-#pragma unroll
-                        for (int c16 = 0; c16 < NCH + (REM ? 1 : 0); ++c16) {
-                            tmem_wait16(w[c16 & 1]);
-                            if (c16 + 1 < NCH) tmem_ld16_async(tp + (uint32_t)((c16 + 1) * 16), w[(c16 + 1) & 1]);
-                            else if (c16 + 1 == NCH && REM) tmem_ld4_async(tp + (uint32_t)((c16 + 1) * 16), w[(c16 + 1) & 1]);
+                    for (int c16 = 0; c16 < NCH + (REM ? 1 : 0); ++c16) {
+                        tmem_wait16(w[c16 & 1]);
+                        if (c16 + 1 < NCH) tmem_ld16_async(taddr + (uint32_t)((c16 + 1) * 16), w[(c16 + 1) & 1]);
+                        else if (c16 + 1 == NCH && REM) tmem_ld8_async(taddr + (uint32_t)((c16 + 1) * 16), w[(c16 + 1) & 1]);
+                        if (c16 * 16 < n_rows * NV) {            // a short tile's accumulator is stale beyond its own (padded) columns
 #pragma unroll
                             for (int q = 0; q < 16; ++q) {
                                 const int c = c16 * 16 + q;
-                                if (c < C::PASS_COLS) {
-                                    const int rr = c / NV, o = c % NV;
-                                    const float wv = __uint_as_float(w[c16 & 1][q]);
-                                    acc[3 * o] = fmaf(wv, bx[rr], acc[3 * o]);
-                                    acc[3 * o + 1] = fmaf(wv, by[rr], acc[3 * o + 1]);
-                                    acc[3 * o + 2] = fmaf(wv, bz[rr], acc[3 * o + 2]);
-                                }
+                                if (c < NCOLS) u[c % NV] = fmaf(__uint_as_float(w[c16 & 1][q]), xn[c / NV], u[c % NV]);
                             }
                         }
                     }
                     tc_fence_before();
-                    mbar_arrive(&tmem_empty[buf]);
-                    if (r == 0) trace_ev(jobs.trace, 1, titer, 2);
-                    if (tt == nt - 1 && has_next) { convert_hidden(a_hi_next, a_hi_next + C::A_BYTES, it + 1); h_done = true; }
-                    if (flags & 4) {
+                    mbar_arrive(&tmem_empty[wg]);
+                    if (tracer) trace_ev(jobs.trace, 1 + wg, titer, 2);
+                    // (the accumulator is free again: everything below overlaps the next MMAs into it)
+                    if (own_next) x_prefetch_tile<NS, NV, C::ROWS_S, C::XN>(xg, tdn, f_in, xn);
+                    if (blk_last || (int)((tdn.x >> 16) & 0xffu) != 2) {
+#pragma unroll
+                        for (int o = 0; o < NV; ++o) {
+                            acc[3 * o] = fmaf(u[o], s1x, acc[3 * o]);
+                            acc[3 * o + 1] = fmaf(u[o], s1y, acc[3 * o + 1]);
+                            acc[3 * o + 2] = fmaf(u[o], s1z, acc[3 * o + 2]);
+                        }
+                        u_live = false;
+                    }
+                } else {
+                    // vector inputs (kinds 3, 4, 5): NV basis rows x NV outputs, three FMAs per weight
+                    float bx[NV], by[NV], bz[NV];
+                    if (kind == 3) {
+#pragma unroll
+                        for (int rr = 0; rr < NV; ++rr) {
+                            const bool on = rr < n_rows;
+                            bx[rr] = on ? xn[3 * rr] * s0 : 0.f; by[rr] = on ? xn[3 * rr + 1] * s0 : 0.f; bz[rr] = on ? xn[3 * rr + 2] * s0 : 0.f;
+                        }
+                    } else if (L2 && kind == 5) {
+                        // b_k = sum_{i,j} C[i][j][k] x_i s2_j: fold the five l = 2 harmonics of the edge into a 3 x 3 matrix
+                        // first (45 uniform table reads, 2 such tiles per edge tile), then apply it to every input vector
+                        const float *c5 = reinterpret_cast<const float *>(jobs.job[0].image + hdr->ctab5_off) + 45 * (int)((tdw.y >> 24) & 0xffu);
+                        float m[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+                        if (valid) {
+                            const float *s2p = ed.sh + (size_t)e * 9 + 4;
+#pragma unroll
+                            for (int j = 0; j < 5; ++j) {
+                                const float sj = __ldg(s2p + j) * inv_deg;
+#pragma unroll
+                                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                                    for (int k = 0; k < 3; ++k) m[i][k] = fmaf(__ldg(c5 + (i * 5 + j) * 3 + k), sj, m[i][k]);
+                            }
+                        }
+#pragma unroll
+                        for (int rr = 0; rr < NV; ++rr) {
+                            const bool on = rr < n_rows;
+                            const float ax = on ? xn[3 * rr] : 0.f, ay = on ? xn[3 * rr + 1] : 0.f, az = on ? xn[3 * rr + 2] : 0.f;
+                            bx[rr] = ax * m[0][0] + ay * m[1][0] + az * m[2][0];
+                            by[rr] = ax * m[0][1] + ay * m[1][1] + az * m[2][1];
+                            bz[rr] = ax * m[0][2] + ay * m[1][2] + az * m[2][2];
+                        }
+                    } else {
+#pragma unroll
+                        for (int rr = 0; rr < NV; ++rr) {
+                            const bool on = rr < n_rows;
+                            const float ax = on ? xn[3 * rr] : 0.f, ay = on ? xn[3 * rr + 1] : 0.f, az = on ? xn[3 * rr + 2] : 0.f;
+                            bx[rr] = ay * s1z - az * s1y; by[rr] = az * s1x - ax * s1z; bz[rr] = ax * s1y - ay * s1x;
+                        }
+                    }
+                    // the basis rows are in registers: fetch the next own tile's node features
+                    if (own_next) x_prefetch_tile<NS, NV, C::ROWS_S, C::XN>(xg, tdn, f_in, xn);
+                    if (tracer) trace_ev(jobs.trace, 1 + wg, titer, 0);
+                    DDP_WAIT(&tmem_full[wg], tf_phase, 10, it, tt);
+                    tf_phase ^= 1u;
+                    tc_fence_after();
+                    if (tracer) trace_ev(jobs.trace, 1 + wg, titer, 1);
+                    constexpr int NCH = C::PASS_COLS / 16, REM = C::PASS_COLS % 16;
+                    static_assert(REM == 0 || REM == 4, "vector tile remainder is read with one x4 load");
+                    if (NCH > 0) tmem_ld16_async(taddr, w[0]); else tmem_ld4_async(taddr, w[0]);
+#pragma unroll
+                    for (int c16 = 0; c16 < NCH + (REM ? 1 : 0); ++c16) {
+                        tmem_wait16(w[c16 & 1]);
+                        if (c16 + 1 < NCH) tmem_ld16_async(taddr + (uint32_t)((c16 + 1) * 16), w[(c16 + 1) & 1]);
+                        else if (c16 + 1 == NCH && REM) tmem_ld4_async(taddr + (uint32_t)((c16 + 1) * 16), w[(c16 + 1) & 1]);
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            const int c = c16 * 16 + q;
+                            if (c < C::PASS_COLS) {
+                                const int rr = c / NV, o = c % NV;
+                                const float wv = __uint_as_float(w[c16 & 1][q]);
+                                acc[3 * o] = fmaf(wv, bx[rr], acc[3 * o]);
+                                acc[3 * o + 1] = fmaf(wv, by[rr], acc[3 * o + 1]);
+                                acc[3 * o + 2] = fmaf(wv, bz[rr], acc[3 * o + 2]);
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&tmem_empty[wg]);
+                    if (tracer) trace_ev(jobs.trace, 1 + wg, titer, 2);
+                }
+                if (kind >= 2) {
+                    if (wg == 0 && !own_next && has_next) { convert_hidden(a_hi_next, a_hi_next + C::A_BYTES, it + 1); h_done = true; }
+                    if (blk_last) {
                         if (valid && ed.out_scale != nullptr) {
                             const float2 *sc2 = reinterpret_cast<const float2 *>(ed.out_scale + out_off);
 #pragma unroll
@@ -1119,9 +1176,12 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                         if (steps) seg_scan<3 * NV>(acc, seg & 0xff, steps);
                         if (valid && (steps == 0 || (seg >> 16))) red_row<3 * NV>(sum + (size_t)agg * f_out + out_off, acc);
                     }
-                    if (r == 0) trace_ev(jobs.trace, 1, titer, 3);
+                    if (tracer) trace_ev(jobs.trace, 1 + wg, titer, 3);
                 }
+                tdw = tdn;
             }
+            // warpgroup 0 without a tile of its own in this (split) item still owes the next item's hidden activations
+            if (wg == 0 && has_next && !h_done) { convert_hidden(a_hi_next, a_hi_next + C::A_BYTES, it + 1); h_done = true; }
         }
     }
     // ------------------------------------------------------------------------------------------ teardown
@@ -1220,6 +1280,39 @@ static int build_plan(const ddp_tpconv_t &c, const ddp_tp_group_t *groups, const
         P.tiles[first_tile].flags |= 1;
         P.tiles.back().flags |= 4;
         g = g_end;
+    }
+    // Tile order = consumption order.  The two epilogue warpgroups take alternate tiles (one per TMEM accumulator), so the
+    // tiles of the leading blocks (sequence A, about half of the MMA cost) are interleaved with those of the remaining blocks
+    // (sequence B): each warpgroup then owns whole output blocks -- one flush per block, as with a single warpgroup -- and
+    // the vector tiles of one sequence (slow epilogue) pair with scalar tiles of the other where the layer is symmetric.
+    // Left-over tiles of the longer sequence alternate between the warpgroups, which then both flush partial sums.
+    {
+        const int n = (int)P.tiles.size();
+        long total = 0, cum = 0, best_d = 0;
+        for (const TileDesc &td : P.tiles) total += td.n_cols;
+        int cut = n;
+        for (int t = 0; t < n; ++t) {
+            const long d = labs(2 * cum - total);
+            if (t > 0 && (P.tiles[t].flags & 1) && (cut == n || d < best_d)) { cut = t; best_d = d; }
+            cum += P.tiles[t].n_cols;
+        }
+        if (cut < n) {
+            std::vector<TileDesc> tiles;
+            std::vector<std::vector<std::pair<int, float>>> cols;
+            for (int i = 0, j = cut; i < cut || j < n;) {
+                if (i < cut) { tiles.push_back(P.tiles[i]); cols.push_back(std::move(P.tile_cols[i])); ++i; }
+                if (j < n) { tiles.push_back(P.tiles[j]); cols.push_back(std::move(P.tile_cols[j])); ++j; }
+            }
+            P.tiles.swap(tiles);
+            P.tile_cols.swap(cols);
+            // flags 1 / 4: first / last tile of its block in the new order (informative: the kernel compares block offsets)
+            for (int t = 0; t < n; ++t) {
+                bool first = true, last = true;
+                for (int u = 0; u < t; ++u) first = first && P.tiles[u].out_off != P.tiles[t].out_off;
+                for (int u = t + 1; u < n; ++u) last = last && P.tiles[u].out_off != P.tiles[t].out_off;
+                P.tiles[t].flags = (uint8_t)((P.tiles[t].flags & ~5) | (first ? 1 : 0) | (last ? 4 : 0));
+            }
+        }
     }
     h.n_tiles = (int)P.tiles.size();
     if (h.n_tiles > 64) return DDP_E_UNSUPPORTED;

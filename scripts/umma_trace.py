@@ -25,6 +25,7 @@ torch.manual_seed(0)
 dl = [copy.deepcopy(g) for _ in range(n)]
 S.randomize_position(dl, False, False, sa.tr_sigma_max, flexible_sidechains=True)
 L = _lib.lib()
+model.replay_launches = False          # the hook below needs every launch to go through the library wrapper
 with torch.no_grad():
     pl = model.make_plan(Batch.from_data_list(dl))
     ct = {k: torch.full((n,), 0.5) for k in ('tr', 'rot', 'tor', 'sc_tor')}
@@ -45,13 +46,14 @@ with torch.no_grad():
     model.run_plan(pl, ct)
     torch.cuda.synchronize()
     L.ddp_tpconv_umma_set_trace(None)
-t = buf.cpu().numpy().reshape(2, -1, 8)
+t = buf.cpu().numpy().reshape(3, -1, 8)
 t0 = t[0, 0, 0]
-print('iter | MMA: wait_empty_start empty_ok first_full issued | EPI: ready_to_wait full_ok released red_done   (cycles rel. to start)')
+print('iter | MMA: wait_empty_start empty_ok first_full issued | EPI warpgroup 0: ready_to_wait full_ok released red_done | EPI warpgroup 1: same   (cycles rel. to start)')
 n_it = int((t[0, :, 0] != 0).sum())
 print(f'{n_it} tile iterations traced (two MMA issuers: even iterations warp 5, odd iterations warp 7)')
 for i in range(160):
-    m, e = t[0, i], t[1, i]
+    m, e, e2 = t[0, i], t[1, i], t[2, i]
     if m[0] == 0:
         break
-    print(f'{i:4d} | ' + ' '.join(f'{int(v - t0):8d}' for v in m[:4]) + ' | ' + ' '.join(f'{int(v - t0):8d}' for v in e[:4]))
+    print(f'{i:4d} | ' + ' '.join(f'{int(v - t0):8d}' for v in m[:4]) + ' | ' + ' '.join(f'{int(v - t0):8d}' for v in e[:4])
+          + ' | ' + ' '.join(f'{int(v - t0):8d}' for v in e2[:4]))
