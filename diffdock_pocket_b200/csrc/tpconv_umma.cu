@@ -14,8 +14,8 @@
 //              block, a warp-level segmented pre-reduction over runs of equal aggregation nodes, then vector
 //              red.global.add.  The packer interleaves the tiles of the first and the second half of the output blocks
 //              so that each warpgroup normally owns whole blocks (no duplicated atomics).  Warpgroup 0 also turns the
-//              GEMM1 result into the A operand of GEMM2 (ReLU, bf16, core-matrix order); at an edge-tile boundary it
-//              does so before its last flush and the next tile's per-edge set-up.
+//              GEMM1 result into the A operand of GEMM2 (ReLU, bf16, core-matrix order), after its last flush and the
+//              next edge tile's per-edge set-up, which fit into the wait for that GEMM1.
 //              Why two: the epilogue is a chain of dependent instructions (tile decode, basis, TMEM round trips) on ONE
 //              warp per scheduler, ~1350 cycles per scalar tile and ~2500 per vector tile against 1440 / 1250 cycles of
 //              MMAs (profiles/r2_umma_timeline_*.txt): a single warpgroup was busy 93 % of the time and set the pace.
@@ -859,9 +859,10 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
         int it = 0;
         // Warpgroup 0 only.  GEMM1 result -> ReLU -> hidden activations become the A operand of GEMM2 (TS: packed bf16 pairs
         // into tensor memory, column c of the lane = k 2c, 2c + 1; SS: hi (/ lo) images back into the shared-memory A buffer
-        // in core-matrix order).  Needs nothing per edge, so at an item boundary it runs BEFORE the warpgroup's last flush
-        // and the next item's per-edge set-up (dependent global loads): tiles 0 and 1 of the next item are already on the
-        // tensor pipe while the epilogue does those.
+        // in core-matrix order).  At an item boundary warpgroup 0's last own tile is the last but one of the item, and the next
+        // item's GEMM1 is issued behind the last tile: the ~2400 cycles until its result exists take the warpgroup's last flush
+        // and the next item's per-edge set-up (dependent global loads), so that after the conversion tile 0's epilogue is
+        // ready when its MMAs are (profiles/r2_umma_timeline_*.txt).
         auto convert_hidden = [&](uint8_t *a_hi_, uint8_t *a_lo_, int it_) {
             if (tracer) trace_ev(jobs.trace, 1, it_ * (n_tiles + 1), 0);
             DDP_WAIT(&tmem_full[0], tf_phase, 8, it_, -1);
@@ -904,6 +905,7 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                     }
                 }
             }
+            if (tracer) trace_ev(jobs.trace, 1, it_ * (n_tiles + 1), 3);
             if (C::TS) tmem_wait_st();
             tc_fence_before();
             if (!C::TS) fence_proxy_async();
@@ -911,37 +913,55 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
             mbar_arrive(&tmem_empty[0]);
             if (tracer) trace_ev(jobs.trace, 1, it_ * (n_tiles + 1), 2);
         };
-        bool h_done = false;                             // the current item's hidden activations were written at the previous boundary
+        // First-level per-edge loads of an item (live edge count, aggregation node, gathered node, edge harmonics): issued one
+        // item ahead -- for the CTA's first item here, for item i + 1 at the top of item i -- so that at an item boundary only
+        // the loads that depend on them (in-degree, node features) remain, and those run under the hidden conversion.  The
+        // chain count -> agg -> degree / gather -> features was ~6000 cycles of exposed L2 latency per boundary
+        // (profiles/r2_umma_timeline_*.txt).  Rows past the live count read allocated but meaningless entries (e < edge_cap).
+        int nx_ne = 0, nx_agg = 0, nx_gather = 0;
+        float nx_s0 = 0.f, nx_s1x = 0.f, nx_s1y = 0.f, nx_s1z = 0.f;
+        auto stage1 = [&](int w_) {
+            int g_, t0_, t1_, job_, et_;
+            work_item(wk, w_, n_tiles, g_, t0_, t1_);
+            locate(pref, n_jobs, g_, job_, et_);
+            const ddp_tpconv_edges_t &ed_ = jobs.job[job_].ed;
+            nx_ne = min(__ldg(ed_.n_edges_dev), ed_.edge_cap);
+            const int e_ = et_ * TILE_M + r;
+            if (e_ < ed_.edge_cap) {
+                nx_agg = __ldg(ed_.agg + e_);
+                nx_gather = __ldg(ed_.gather + e_);
+                if (L2) {
+                    const float *shp = ed_.sh + (size_t)e_ * 9;       // [s0 | s1 (3) | s2 (5)]: rows are not 16-byte aligned
+                    nx_s0 = __ldg(shp); nx_s1x = __ldg(shp + 1); nx_s1y = __ldg(shp + 2); nx_s1z = __ldg(shp + 3);
+                } else {
+                    const float4 sh4 = __ldg(reinterpret_cast<const float4 *>(ed_.sh + (size_t)e_ * 4));
+                    nx_s0 = sh4.x; nx_s1x = sh4.y; nx_s1y = sh4.z; nx_s1z = sh4.w;
+                }
+            }
+        };
+        if ((int)blockIdx.x < n_items) stage1(blockIdx.x);
         for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+            if (tracer && wg == 0) trace_ev(jobs.trace, 2, it * (n_tiles + 1), 0);     // item set-up (free row of the warpgroup-1 trace)
             int g, t0, t1, job, et;
             work_item(wk, w, n_tiles, g, t0, t1);
             const int nt = t1 - t0;
             locate(pref, n_jobs, g, job, et);
             const ddp_tpconv_edges_t &ed = jobs.job[job].ed;
             float *__restrict__ sum = jobs.job[job].sum;
-            const int n_edges = min(*ed.n_edges_dev, ed.edge_cap);
             const int e = et * TILE_M + r;
-            const bool valid = e < n_edges;
+            const bool valid = e < nx_ne;
             const int ab = it % C::NBUF;
             uint8_t *a_hi = a_base + (size_t)ab * C::A_BYTES * (SPLIT ? 2 : 1);
             uint8_t *a_lo = a_hi + C::A_BYTES;
-            int agg = 0;
-            float s0 = 0.f, s1x = 0.f, s1y = 0.f, s1z = 0.f;
+            if (tracer && wg == 0) trace_ev(jobs.trace, 2, it * (n_tiles + 1), 1);
+            const int agg = valid ? nx_agg : 0;
             float inv_deg = 1.f;                         // pre-normalised accumulation: 1 / max(in-degree of agg, 1)
-            const float *xg = ed.x;                      // invalid rows read node 0 and are never written back
-            if (valid) {
-                agg = __ldg(ed.agg + e);
-                if (ed.agg_deg != nullptr) inv_deg = __frcp_rn((float)max(__ldg(ed.agg_deg + agg), 1));
-                // every basis row is linear in the edge harmonics: scaling them applies the scatter-mean for free
-                if (L2) {
-                    const float *shp = ed.sh + (size_t)e * 9;         // [s0 | s1 (3) | s2 (5)]: rows are not 16-byte aligned
-                    s0 = __ldg(shp) * inv_deg; s1x = __ldg(shp + 1) * inv_deg; s1y = __ldg(shp + 2) * inv_deg; s1z = __ldg(shp + 3) * inv_deg;
-                } else {
-                    const float4 sh4 = __ldg(reinterpret_cast<const float4 *>(ed.sh + (size_t)e * 4));
-                    s0 = sh4.x * inv_deg; s1x = sh4.y * inv_deg; s1y = sh4.z * inv_deg; s1z = sh4.w * inv_deg;
-                }
-                xg = ed.x + (size_t)__ldg(ed.gather + e) * ed.ldx;
-            }
+            if (valid && ed.agg_deg != nullptr) inv_deg = __frcp_rn((float)max(__ldg(ed.agg_deg + agg), 1));
+            // invalid rows read node 0 and are never written back
+            const float *xg = ed.x + (valid ? (size_t)nx_gather * ed.ldx : (size_t)0);
+            // every basis row is linear in the edge harmonics: scaling them applies the scatter-mean for free
+            const float s0 = valid ? nx_s0 * inv_deg : 0.f, s1x = valid ? nx_s1x * inv_deg : 0.f;
+            const float s1y = valid ? nx_s1y * inv_deg : 0.f, s1z = valid ? nx_s1z * inv_deg : 0.f;
             // runs of equal aggregation nodes inside this warp's 32 edges: seg = off | steps << 8 | is_tail << 16
             // (steps = 0: no pre-reduction, e.g. fewer than half of the lanes would merge)
             int seg = 0;
@@ -955,17 +975,18 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                 if (DDP_UMMA_SEGSCAN && __popc(heads) <= 16)
                     seg = off | ((32 - __clz(maxoff)) << 8) | ((lane_ == 31 || ((heads >> (lane_ + 1)) & 1u)) ? 1 << 16 : 0);
             }
+            if (tracer && wg == 0) trace_ev(jobs.trace, 2, it * (n_tiles + 1), 2);
             // this warpgroup's tiles of the item: those in its accumulator (acc_of), i.e. every other one from tt_first
             const int tt_first = (int)((wg ^ (uint32_t)nt) & 1u);
             // node features of the first own weight tile (registers; every tile prefetches the next own one's)
             float xn[C::XN];
             uint4 tdw = *reinterpret_cast<const uint4 *>(&tiles[min(t0 + tt_first, n_tiles - 1)]);
             if (tt_first < nt) x_prefetch_tile<NS, NV, C::ROWS_S, C::XN>(xg, tdw, f_in, xn);
+            if (tracer && wg == 0) trace_ev(jobs.trace, 2, it * (n_tiles + 1), 3);
 
-            if (wg == 0 && !h_done) convert_hidden(a_hi, a_lo, it);
-            h_done = false;
-            const bool has_next = w + (int)gridDim.x < n_items;
-            uint8_t *a_hi_next = a_base + (size_t)((it + 1) % C::NBUF) * C::A_BYTES * (SPLIT ? 2 : 1);
+            // (the in-degree load and the prefetch are in flight under the conversion)
+            if (wg == 0) convert_hidden(a_hi, a_lo, it);
+            if (w + (int)gridDim.x < n_items) stage1(w + (int)gridDim.x);
 
             // ---- weight tiles: TMEM accumulator x tensor-product basis -> per-edge output registers ----
             // Every tile has one basis kind; its node features arrive in registers (prefetched during the previous own
@@ -1026,7 +1047,6 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                     tc_fence_before();
                     mbar_arrive(&tmem_empty[wg]);
                     if (tracer) trace_ev(jobs.trace, 1 + wg, titer, 2);
-                    if (wg == 0 && !own_next && has_next) { convert_hidden(a_hi_next, a_hi_next + C::A_BYTES, it + 1); h_done = true; }
                     if (blk_last) {
                         if (valid && ed.out_scale != nullptr) {              // block offsets and widths are even: 8-byte loads
                             const float2 *sc2 = reinterpret_cast<const float2 *>(ed.out_scale + out_off);
@@ -1161,7 +1181,6 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                     if (tracer) trace_ev(jobs.trace, 1 + wg, titer, 2);
                 }
                 if (kind >= 2) {
-                    if (wg == 0 && !own_next && has_next) { convert_hidden(a_hi_next, a_hi_next + C::A_BYTES, it + 1); h_done = true; }
                     if (blk_last) {
                         if (valid && ed.out_scale != nullptr) {
                             const float2 *sc2 = reinterpret_cast<const float2 *>(ed.out_scale + out_off);
@@ -1180,8 +1199,6 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
                 }
                 tdw = tdn;
             }
-            // warpgroup 0 without a tile of its own in this (split) item still owes the next item's hidden activations
-            if (wg == 0 && has_next && !h_done) { convert_hidden(a_hi_next, a_hi_next + C::A_BYTES, it + 1); h_done = true; }
         }
     }
     // ------------------------------------------------------------------------------------------ teardown

@@ -51,7 +51,7 @@ t0 = t[0, 0, 0]
 print('iter | MMA: wait_empty_start empty_ok first_full issued | EPI warpgroup 0: ready_to_wait full_ok released red_done | EPI warpgroup 1: same   (cycles rel. to start)')
 n_it = int((t[0, :, 0] != 0).sum())
 print(f'{n_it} tile iterations traced (two MMA issuers: even iterations warp 5, odd iterations warp 7)')
-for i in range(160):
+for i in range(int(os.environ.get('TRACE_ROWS', '160'))):
     m, e, e2 = t[0, i], t[1, i], t[2, i]
     if m[0] == 0:
         break
