@@ -16,8 +16,16 @@ tr_z, rot_z, tor_z, sidechain_tor_z per step), but the loop body is restructured
 plans outlive many calls or the batch is so small that launches dominate: capture + instantiation cost ~40 ms per
 mini-batch, while at batch 20 the eager launch stream already runs ~4x ahead of the GPU).
 
+Resident state outlives the call: the runners (plans, workspaces, pose tables, recorded launch programs) and the
+confidence plans of the last ``PLAN_CACHE_SIZE`` distinct inputs are kept, keyed by the CONTENT of everything the plans
+were built from (topology, static features, receptor coordinates -- everything but the moving ligand / atom
+coordinates).  A later call on the same complex(es) -- re-docking, more samples, a screening loop over one pocket with a
+recurring ligand -- only uploads the new start poses: the ~50 ms of host-side collation and plan building of the first
+call, during which the GPU starves inside step 0, are gone (``DDP_PLAN_CACHE=0`` disables the cache).
+
 SVGD (svgd_weight > 0) and ``pivot`` are outside the accelerated path and raise NotImplementedError.
 """
+import collections
 import contextlib
 import copy
 import gc
@@ -63,6 +71,77 @@ def randomize_position(data_list, no_torsion, no_random, tr_sigma_max, pocket_kn
         g['ligand'].pos = (g['ligand'].pos - center) @ rot.T + center_pocket
         if not no_random:
             g['ligand'].pos += torch.normal(mean=0, std=tr_sigma_max, size=(1, 3))
+
+
+# ------------------------------------------------------------------------------------------ resident-state cache
+PLAN_CACHE_SIZE = int(os.environ.get('DDP_PLAN_CACHE', 2))      # inputs (lists of complexes) whose resident state is kept; 0: off
+_PLAN_CACHE = collections.OrderedDict()                         # key -> {'runners', 'conf_plans', 'busy'}
+LAST_CALL = {'plan_reused': False}                              # bench.py's H2D accounting reads this
+
+
+def _bytes_key(t):
+    if t is None:
+        return None
+    if torch.is_tensor(t):
+        t = t.detach().cpu().contiguous()
+        return (tuple(t.shape), str(t.dtype), hash(t.numpy().tobytes()))
+    a = np.ascontiguousarray(np.asarray(t))
+    return (a.shape, str(a.dtype), hash(a.tobytes()))
+
+
+def _graph_key(g, flexible_sidechains):
+    """Content key of everything a plan / pose state is built from in one complex graph, except the ligand and atom
+    coordinates (the only per-call inputs).  Exact (hash of the bytes) for the index / feature tables; the receptor's
+    wide language-model features are keyed by a strided sample next to the exact receptor coordinates."""
+    lig, rec, atom = g['ligand'], g['receptor'], g['atom']
+    mr = lig.mask_rotate if 'mask_rotate' in lig else None
+    if mr is not None and not isinstance(mr, np.ndarray):
+        mr = mr[0]
+    rx = rec.x.reshape(-1)
+    key = [tuple(lig.pos.shape), tuple(atom.pos.shape), _bytes_key(lig.x), _bytes_key(lig.edge_mask if 'edge_mask' in lig else None),
+           _bytes_key(mr), _bytes_key(g['ligand', 'ligand'].edge_index), _bytes_key(g['ligand', 'ligand'].edge_attr),
+           _bytes_key(rec.pos), tuple(rec.x.shape), tuple(rx[::max(1, rx.numel() // 251)][:256].tolist()),
+           _bytes_key(g['receptor', 'receptor'].edge_index), _bytes_key(atom.x), _bytes_key(g['atom', 'receptor'].edge_index)]
+    if flexible_sidechains and 'flexResidues' in g and 'edge_idx' in g['flexResidues']:
+        fr = g['flexResidues']
+        key += [_bytes_key(fr.edge_idx), _bytes_key(fr.subcomponents), _bytes_key(fr.subcomponentsMapping)]
+    else:
+        key.append(None)
+    return tuple(key)
+
+
+def _graph_tables(g, flexible_sidechains):
+    lig, rec, atom = g['ligand'], g['receptor'], g['atom']
+    mr = lig.mask_rotate if 'mask_rotate' in lig else None
+    if mr is not None and not isinstance(mr, np.ndarray):
+        mr = mr[0]
+    rx = rec.x.reshape(-1)                                         # wide language-model features: strided sample, as in _graph_key
+    t = [lig.x, lig.edge_mask if 'edge_mask' in lig else None, mr, g['ligand', 'ligand'].edge_index, g['ligand', 'ligand'].edge_attr,
+         rec.pos, rx[::max(1, rx.numel() // 251)][:256], g['receptor', 'receptor'].edge_index, atom.x, g['atom', 'receptor'].edge_index]
+    if flexible_sidechains and 'flexResidues' in g and 'edge_idx' in g['flexResidues']:
+        fr = g['flexResidues']
+        t += [fr.edge_idx, fr.subcomponents, fr.subcomponentsMapping]
+    return t
+
+
+def _same_tables(a, b):
+    if len(a) != len(b):
+        return False
+    for x, y in zip(a, b):
+        if x is y:
+            continue
+        if x is None or y is None:
+            return False
+        if torch.is_tensor(x) and torch.is_tensor(y):
+            if x.shape != y.shape or x.dtype != y.dtype or not torch.equal(x, y):
+                return False
+        elif not np.array_equal(np.asarray(x), np.asarray(y)):
+            return False
+    return True
+
+
+def clear_plan_cache():
+    _PLAN_CACHE.clear()
 
 
 def is_iterable(arr):
@@ -136,6 +215,18 @@ class StepRunner:
         self.use_graph = use_graph
         self.out = None
         self.calls = 0
+
+    def reset(self, data_sub):
+        """Re-use this runner for another call on the same complexes: only the start poses change (two H2D copies)."""
+        lp = torch.cat([g['ligand'].pos for g in data_sub]).float().pin_memory()
+        ap = torch.cat([g['atom'].pos for g in data_sub]).float().pin_memory()
+        assert lp.shape == self.pl.lig_pos.shape and ap.shape == self.pl.atom_pos.shape
+        self.pl.lig_pos.copy_(lp, non_blocking=True)
+        self.pl.atom_pos.copy_(ap, non_blocking=True)
+        self._keep = (lp, ap)                    # pinned sources stay alive until the copies have run
+        if self._ps is not None:
+            self._ps._host = None
+        self.out = None
 
     @property
     def ps(self):
@@ -251,11 +342,44 @@ def _sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_
     chunks = [list(range(i, min(i + batch_size, N))) for i in range(0, N, batch_size)]
     use_graph = bool(use_graph) and trace is None
     runners = [None] * len(chunks)
+    # resident state of an earlier call on the same input (see the module docstring)
+    cache_key = cached = None
+    LAST_CALL['plan_reused'] = False
+    if PLAN_CACHE_SIZE > 0 and trace is None and filtering_data_list is None and N > 0:
+        memo = []                                                     # (tables, key) of the distinct complexes seen so far
+
+        def gkey(g):
+            # samples of one complex share (or are deep copies of) the same tables: hash each distinct complex once, the
+            # others are compared with it exactly (memcmp speed)
+            tabs = _graph_tables(g, flexible_sidechains)
+            shape = (tuple(g['ligand'].pos.shape), tuple(g['atom'].pos.shape))
+            for tabs2, shape2, key2 in memo:
+                if shape2 == shape and _same_tables(tabs, tabs2):
+                    return key2
+            memo.append((tabs, shape, _graph_key(g, flexible_sidechains)))
+            return memo[-1][2]
+        cache_key = (id(model), id(confidence_model), getattr(model, 'conv_mode', None), getattr(model, 'group_convs', None),
+                     str(device), batch_size, bool(flexible_sidechains), bool(ma.no_torsion), use_graph, bool(concurrent_batches),
+                     tuple(gkey(g) for g in data_list))
+        cached = _PLAN_CACHE.get(cache_key)
+        if cached is not None and (cached['busy'] or cached['models'][0]() is not model or
+                                   (confidence_model is not None and cached['models'][1]() is not confidence_model)):
+            cached = None                                             # still owned by an unfinished (deferred) call / stale ids
     # independent mini-batches alternate between two streams (see StepRunner.ctx); host-visible intermediates
     # (trace, trajectories, visualisation) keep the single-stream order
     single = len(chunks) < 2 or trace is not None or return_full_trajectory or visualization_list is not None \
         or sidechain_visualization_list is not None or not concurrent_batches
+    if cached is not None and cached['single'] != single:
+        cached = None
     streams = [None] if single else [torch.cuda.Stream(device=device) for _ in range(2)]
+    if cached is not None:
+        cached['busy'] = True
+        _PLAN_CACHE.move_to_end(cache_key)
+        runners, streams = list(cached['runners']), cached['streams']
+        for idx, r in zip(chunks, runners):
+            r.reset([data_list[i] for i in idx])
+            r.sync_in()                                               # the start poses were uploaded on the caller's stream
+        LAST_CALL['plan_reused'] = True
     n_tor = [0 if ma.no_torsion else sum(int(data_list[i]['ligand'].edge_mask.sum()) for i in idx) for idx in chunks]
     n_sc = [sum(int(data_list[i]['flexResidues'].edge_idx.shape[0]) for i in idx
                 if flexible_sidechains and 'flexResidues' in data_list[i] and 'edge_idx' in data_list[i]['flexResidues'])
@@ -286,7 +410,7 @@ def _sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_
         for _ in range(2):                                            # the two loaders of utils/sampling.py:265-266
             torch.empty((), dtype=torch.int64).random_()
 
-    conf_plans = None
+    conf_plans = cached['conf_plans'] if cached is not None else None
     max_ahead = int(os.environ.get('DDP_MAX_AHEAD', 2))
     pace = [[] for _ in chunks]
 
@@ -394,6 +518,14 @@ def _sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_
             staged[0].synchronize()
             confidence = staged[1]
         write_back_all()                                              # the one device->host read of the poses
+        if cache_key is not None and all(r is not None for r in runners) and n_steps > 0:
+            # hand the resident state to the cache (or back to it): the next call on this input starts from here
+            import weakref
+            _PLAN_CACHE[cache_key] = {'runners': runners, 'conf_plans': conf_plans, 'streams': streams, 'single': single, 'busy': False,
+                                      'models': (weakref.ref(model), weakref.ref(confidence_model) if confidence_model is not None else None)}
+            _PLAN_CACHE.move_to_end(cache_key)
+            while len(_PLAN_CACHE) > PLAN_CACHE_SIZE:
+                _PLAN_CACHE.popitem(last=False)
         if filtering_data_list is not None:
             for i, g in enumerate(filtering_data_list):
                 g['ligand'].pos = data_list[i]['ligand'].pos

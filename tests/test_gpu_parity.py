@@ -471,3 +471,43 @@ def test_mixed_flexible_and_rigid_complexes_in_one_batch():
     # the pose state of the same mixed list: per-sample side-chain slices line up with the model's bond order
     st = du.PoseState(dl, DEV)
     assert st.S == got[3].numel() and st.T == got[2].numel()
+
+
+def test_resident_state_cache_reuse_equals_fresh_plans():
+    """sampling() keeps the resident state (plans, pose tables, launch programs) of its last inputs keyed by content: a second
+    call on the same complex with NEW start poses must reuse it and give exactly what freshly built plans give, a call on a
+    complex that differs in one receptor coordinate must not reuse it."""
+    m, c, om, oc, sa, ca = T.models(DEV, small=True)
+    m.conv_mode = 'fp32'
+    g = inputs.synthetic_complex(9, n_lig=18, n_res=36, flexible_residues=2)
+    steps = 4
+    sch = D.get_t_schedule(steps)
+
+    def run(dl, seed):
+        torch.manual_seed(seed)
+        out, conf = ps.sampling(copy.deepcopy(dl), m, steps, sch, sch, sch, sch, DEV, partial(du.t_to_sigma, args=sa), sa,
+                                confidence_model=c, filtering_model_args=ca, batch_size=3)
+        return torch.stack([o['ligand'].pos.cpu() for o in out]), torch.stack([o['atom'].pos.cpu() for o in out]), conf.cpu().clone()
+
+    dl_a, dl_b = T.randomized_list(g, 5, sa, seed=3), T.randomized_list(g, 5, sa, seed=4)
+    ps.clear_plan_cache()
+    first = run(dl_a, 21)
+    assert not ps.LAST_CALL['plan_reused']
+    reused = run(dl_b, 22)                      # same complex, other start poses and noise: resident state re-used
+    assert ps.LAST_CALL['plan_reused']
+    ps.clear_plan_cache()
+    fresh = run(dl_b, 22)
+    assert not ps.LAST_CALL['plan_reused']
+    # (the scatter-adds of the convs are atomic: two runs agree to rounding, not bit for bit)
+    close = lambda x, y: float((x.double() - y.double()).abs().max()) < 2e-3
+    for a, b in zip(reused, fresh):
+        assert close(a, b), float((a.double() - b.double()).abs().max())
+    again = run(dl_a, 21)                       # cache now holds dl_b's state (same key): re-use, same result as the very first run
+    assert ps.LAST_CALL['plan_reused']
+    for a, b in zip(again, first):
+        assert close(a, b), float((a.double() - b.double()).abs().max())
+    g2 = copy.deepcopy(g)
+    g2['receptor'].pos[1, 0] += 0.25
+    run(T.randomized_list(g2, 5, sa, seed=3), 21)
+    assert not ps.LAST_CALL['plan_reused']
+    ps.clear_plan_cache()
