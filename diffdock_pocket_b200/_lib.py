@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get('DDP_LIB', os.path.join(_HERE, 'libddp_b200.so'))     # DDP_LIB: A/B runs of two builds
 CSRC = os.path.join(_HERE, 'csrc')
-SOURCES = ['graph.cu', 'embed.cu', 'tpconv_fp32.cu', 'tpconv_umma.cu', 'pose.cu', 'capi.cu']
+SOURCES = ['graph.cu', 'embed.cu', 'tpconv_fp32.cu', 'tpconv_umma.cu', 'tpconv_bwd.cu', 'pose.cu', 'capi.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']
 
@@ -77,6 +77,7 @@ _SIGS = {
     'ddp_version': (C.c_char_p, []),
     'ddp_radius': (i32, [vp, vp, vp, vp, i32, i32, vp, f32, i32, i32, i32, vp, i32, vp, vp, i32, vp, vp]),
     'ddp_knn_graph': (i32, [vp, vp, i32, i32, i32, vp, i32, vp, vp, i32, vp, vp]),
+    'ddp_knn_set_grid': (i32, [i32]),
     'ddp_calpha_graph': (i32, [vp, vp, i32, i32, f32, i32, vp, i32, vp, vp, i32, vp, vp]),
     'ddp_degree': (i32, [vp, vp, i32, vp, vp]),
     'ddp_edge_embed': (i32, [vp, vp, vp, i32, vp, vp, vp, i32, vp, C.POINTER(EdgeMlp), vp, vp, vp]),
@@ -88,6 +89,7 @@ _SIGS = {
     'ddp_tpconv_umma': (i32, [C.POINTER(TpConv), vp, i32, C.POINTER(TpEdges), vp, vp]),
     'ddp_tpconv_umma_group': (i32, [vp, vp, i32, vp, vp, i32, vp]),
     'ddp_tpconv_umma_set_trace': (i32, [vp]),
+    'ddp_tp_backward': (i32, [C.POINTER(TpConv), vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp]),
     'ddp_node_update': (i32, [vp, i32, i32, C.POINTER(Update), i32, i32, i32, vp, i32, vp]),
     'ddp_node_update_multi': (i32, [C.POINTER(NodeUpdateJob), i32, vp]),
     'ddp_degree_multi': (i32, [C.POINTER(DegreeJob), i32, vp]),
@@ -104,7 +106,7 @@ _SIGS = {
 EXPORTS = sorted(_SIGS)
 _LIB = None
 # kernels launched per C-ABI call (for the bench's gpu_launches claim)
-KERNELS_PER_CALL = {'ddp_radius': 3, 'ddp_knn_graph': 3, 'ddp_calpha_graph': 3, 'ddp_version': 0, 'ddp_pose_max_ligand_atoms': 0, 'ddp_tpconv_pack': 0, 'ddp_tpconv_umma_set_trace': 0}
+KERNELS_PER_CALL = {'ddp_radius': 3, 'ddp_knn_graph': 3, 'ddp_calpha_graph': 3, 'ddp_version': 0, 'ddp_pose_max_ligand_atoms': 0, 'ddp_tpconv_pack': 0, 'ddp_tpconv_umma_set_trace': 0, 'ddp_knn_set_grid': 0}
 COUNTS = {}
 
 

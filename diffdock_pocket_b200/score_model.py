@@ -259,6 +259,70 @@ class PackedConv:
         return self.umma[mode]
 
 
+class _ConvFn(torch.autograd.Function):
+    """Autograd node of one TensorProductConvLayer call (training path; the reference differentiates
+    ``tp(node_attr[edge_dst], edge_sh, fc(edge_attr))`` + ``scatter(mean)`` with PyTorch / e3nn autograd,
+    models/score_model.py:105-125 under utils/training.py:147-191).  Forward = the fused kernels.  Backward: the Linear /
+    ReLU gradients and the two weight-gradient GEMMs are library GEMMs; the tensor-product part -- gradients with respect
+    to the per-edge weights, the gathered node features and the edge harmonics -- is ``ddp_tp_backward``, on chunks of
+    edges whose per-edge weights are re-materialised ([chunk, weight_numel] fp32).  BatchNorm, where present, is the
+    eval-mode affine map of the forward (running statistics are constants; its own parameters get no gradient)."""
+
+    @staticmethod
+    def forward(ctx, layer, edge_index, out_nodes, edge_weight, node_attr, edge_attr, edge_sh, w1, b1, w2, b2):
+        with torch.no_grad():
+            out = layer._forward_impl(node_attr, edge_index, edge_attr, edge_sh, out_nodes, edge_weight)
+        ctx.layer, ctx.out_nodes = layer, int(out_nodes or node_attr.shape[0])
+        ctx.has_ew = torch.is_tensor(edge_weight)
+        ctx.save_for_backward(node_attr, edge_attr, edge_sh, w1, b1, w2, b2, edge_index,
+                              edge_weight if ctx.has_ew else torch.empty(0))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        node_attr, edge_attr, edge_sh, w1, b1, w2, b2, edge_index, ew = ctx.saved_tensors
+        layer, n_out = ctx.layer, ctx.out_nodes
+        dev = node_attr.device
+        L = _lib.lib()
+        E = edge_index.shape[1]
+        x, A, sh = node_attr.detach().float().contiguous(), edge_attr.detach().float().contiguous(), edge_sh.detach().float().contiguous()
+        W1, B1, W2, B2 = (t.detach().float() for t in (w1, b1, w2, b2))
+        agg, src = edge_index[0].long(), edge_index[1].to(torch.int32).contiguous()
+        pk = layer.packed(dev, layer.fc[0].in_features, 0)
+        g = g.detach().float()
+        if pk.bn_scale is not None:
+            g = g * pk.bn_scale
+        deg = torch.bincount(agg, minlength=n_out).clamp(min=1).to(torch.float32)
+        g_node = (g / deg[:, None]).contiguous()
+        Hpre = torch.addmm(B1, A, W1.T)
+        H = torch.relu(Hpre)
+        Wn = W2.shape[0]
+        g_x, g_sh = torch.zeros_like(x), torch.zeros_like(sh)
+        g_W2, g_b2, g_H = torch.zeros_like(W2), torch.zeros_like(B2), torch.empty_like(H)
+        chunk = max(1024, (1 << 27) // max(Wn, 1))                    # two [chunk, weight_numel] fp32 buffers of <= 0.5 GB each
+        for c0 in range(0, E, chunk):
+            c1 = min(E, c0 + chunk)
+            Wt = torch.addmm(B2, H[c0:c1], W2.T).contiguous()        # per-edge weights of the chunk
+            ge = g_node[agg[c0:c1]]
+            if ctx.has_ew:
+                ge = ge * ew.detach().float().reshape(-1, 1)[c0:c1]
+            ge = ge.contiguous()
+            g_w = torch.empty_like(Wt)
+            _lib.check(L.ddp_tp_backward(C.byref(pk.cdesc), ptr(x), src[c0:c1].data_ptr(), x.shape[1], sh[c0:c1].data_ptr(), ptr(Wt),
+                                         ptr(ge), c1 - c0, ptr(g_w), ptr(g_x), g_sh[c0:c1].data_ptr(), _lib.stream_ptr()),
+                       'ddp_tp_backward')
+            g_W2.addmm_(g_w.T, H[c0:c1])
+            g_b2 += g_w.sum(0)
+            g_H[c0:c1] = g_w @ W2
+        g_pre = g_H * (Hpre > 0)
+        g_W1, g_b1, g_A = g_pre.T @ A, g_pre.sum(0), g_pre @ W1
+        need = ctx.needs_input_grad
+        cast = lambda t, like: t.to(like.dtype)
+        return (None, None, None, None, cast(g_x, node_attr) if need[4] else None, cast(g_A, edge_attr) if need[5] else None,
+                cast(g_sh, edge_sh) if need[6] else None, g_W1 if need[7] else None, g_b1 if need[8] else None,
+                g_W2 if need[9] else None, g_b2 if need[10] else None)
+
+
 class TensorProductConvLayer(nn.Module):
     """models/score_model.py:84-125 (operator-level drop-in)."""
 
@@ -287,7 +351,9 @@ class TensorProductConvLayer(nn.Module):
         return super()._load_from_state_dict(*a, **k)
 
     def packed(self, device, n_emb, ns, edge_fold=None, fold_bn=False):
-        key = (None if edge_fold is None else tuple(id(t) for t in edge_fold), bool(fold_bn))
+        # (parameter versions: an optimizer step between two training forwards invalidates the packed image)
+        key = (None if edge_fold is None else tuple(id(t) for t in edge_fold), bool(fold_bn),
+               tuple(p._version for p in self.fc.parameters()))
         if self._packed is None or self._packed.w1t.device != torch.device(device) or self._packed.cdesc.n_emb != n_emb \
                 or self._packed.fold_key != key:
             self._packed = PackedConv(self, device, n_emb, ns, edge_fold, fold_bn)
@@ -295,10 +361,20 @@ class TensorProductConvLayer(nn.Module):
         return self._packed
 
     def forward(self, node_attr, edge_index, edge_attr, edge_sh, out_nodes=None, reduce='mean', edge_weight=1.0):
-        """Stand-alone operator call (fp32 kernel): edge_attr is the already concatenated [E, n_edge_features]."""
+        """Stand-alone operator call: edge_attr is the already concatenated [E, n_edge_features].  With autograd enabled and
+        something to differentiate (inputs or the edge-MLP parameters) the call is recorded as one ``_ConvFn`` node."""
         if edge_index.numel() == 0:
             return torch.tensor(0, dtype=node_attr.dtype, device=node_attr.device)
         assert reduce == 'mean' and not self.residual
+        fc0, fc3 = self.fc[0], self.fc[3]
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (node_attr, edge_attr, edge_sh, fc0.weight, fc0.bias, fc3.weight, fc3.bias)):
+            if self.training and self.fc[2].p > 0:
+                raise NotImplementedError('dropout inside the fused edge MLP is not differentiated (train with dropout = 0 or eval())')
+            return _ConvFn.apply(self, edge_index, out_nodes, edge_weight, node_attr, edge_attr, edge_sh, fc0.weight, fc0.bias,
+                                 fc3.weight, fc3.bias)
+        return self._forward_impl(node_attr, edge_index, edge_attr, edge_sh, out_nodes, edge_weight)
+
+    def _forward_impl(self, node_attr, edge_index, edge_attr, edge_sh, out_nodes=None, edge_weight=1.0):
         dev = node_attr.device
         if dev.type != 'cuda':
             raise RuntimeError('TensorProductConvLayer runs on CUDA only (no CPU fallback)')

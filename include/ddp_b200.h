@@ -58,6 +58,10 @@ int ddp_radius(const float *x, const float *y, const int32_t *ptr_x, const int32
 int ddp_knn_graph(const float *x, const int32_t *ptr, int32_t num_examples, int32_t n, int32_t k,
                   int32_t *slab, int32_t slab_w, int32_t *counts, int32_t *edge, int32_t edge_cap,
                   int32_t *n_edges_dev, void *stream);
+/* Search strategy of the filtered k-NN (k = 8 / 12): 0 = ordered scan of the staged example (default), 1 = grid-binned
+ * (cell list built per block in shared memory; same edge lists, measured slower at pocket sizes -- see csrc/graph.cu).
+ * Returns the previous setting (-1: not set yet, DDP_KNN_GRID in the environment decides on first use). */
+int ddp_knn_set_grid(int32_t mode);
 
 /* ddp_calpha_graph: the receptor's residue contact graph, built once per complex by the reference's preprocessing
  * (datasets/process_mols.py:661-677): for every residue i of its complex the residues closer than r, in index order;
@@ -210,6 +214,19 @@ int ddp_tpconv_umma(const ddp_tpconv_t *conv, const void *packed, int32_t mode,
  * their 128-edge tiles, so small edge sets do not leave SMs idle.  Arrays of n_jobs HOST pointers. */
 int ddp_tpconv_umma_group(const ddp_tpconv_t *const *convs, const void *const *packed, int32_t mode,
                           const ddp_tpconv_edges_t *const *edges, float *const *sums, int32_t n_jobs, void *stream);
+
+/* Training path: backward of the tensor product of one TensorProductConvLayer.  Replaces what
+ * autograd does for `self.tp(node_attr[edge_dst], edge_sh, self.fc(edge_attr))` under `loss.backward()`
+ * (models/score_model.py:112-114, models/layers.py:40-85 / e3nn FullyConnectedTensorProduct; utils/training.py:147-191):
+ *   g_w[e][col]            = sum_k basis_k(x, sh) g_out[e][out(col)][k]
+ *   g_x[gather[e]][...]   += w[e][col] sum_{j,k} C[i][j][k] sh[e][j] g_out[e][...][k]      (atomic; may be NULL)
+ *   g_sh[e][j]            += w[e][col] sum_{i,k} C[i][j][k] x[...][i] g_out[e][...][k]       (atomic; may be NULL)
+ * w / g_w: [n_edges][w_numel] (the per-edge weights fc(edge_attr) and their gradient, materialised per chunk of
+ * edges by the caller), g_out: [n_edges][f_out] per-EDGE output gradients (the caller has applied the scatter-mean:
+ * g_sum[agg[e]] / deg).  The Linear / ReLU gradients around it are plain GEMMs on the caller's side
+ * (diffdock_pocket_b200/score_model.py:_ConvFn).  Uses conv->groups, ctab, n_groups, w_numel, f_out, sh_dim. */
+int ddp_tp_backward(const ddp_tpconv_t *conv, const float *x, const int32_t *gather, int32_t ldx, const float *sh,
+                    const float *w, const float *g_out, int32_t n_edges, float *g_w, float *g_x, float *g_sh, void *stream);
 
 /* Developer aid: when trace_dev != NULL, CTA 0 of every following tensor-core conv launch records clock64()
  * timestamps of its MMA-issue and epilogue roles per weight tile into trace_dev (device int64 buffer); NULL turns

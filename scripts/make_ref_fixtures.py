@@ -6,7 +6,7 @@
 written below is an output of those reference modules.  ``tests/test_reference_pin.py`` (CPU) checks the oracle
 against them, ``tests/test_gpu_refpin.py`` (GPU) the CUDA path.
 
-    python scripts/make_ref_fixtures.py [tables] [ops] [forward] [sampling_small] [sampling_full]
+    python scripts/make_ref_fixtures.py [tables] [ops] [conv_grads] [forward] [sampling_small] [sampling_full]
 
 (no argument = everything; ``sampling_full`` is the 20-step big-model run, several minutes of CPU.)
 The first run imports ``utils/so3.py`` / ``utils/torus.py`` without their ``.npy`` caches: ~9 minutes.
@@ -139,6 +139,32 @@ def make_ops(R):
     save('ref_ops.npz', d)
 
 
+# ------------------------------------------------------------------------------------------------- conv backward
+def make_conv_grads(R):
+    """Gradients of the reference's own ``TensorProductConvLayer`` (models/score_model.py:84-125 over models/layers.py /
+    the FCTP restatement) by PyTorch autograd, as ``loss.backward()`` computes them in utils/training.py:147-191: with
+    respect to the node features, edge attributes, edge harmonics and both Linears of the edge MLP.  The [weight_numel,
+    hidden] gradient of the second Linear is stored as a strided sample plus its sums (7 MB per case otherwise)."""
+    d = {}
+    for case, (in_ir, out_ir, nf, faster, sh_ir) in refpin.CONV_CASES.items():
+        conv = R.score_model.TensorProductConvLayer(in_ir, sh_ir, out_ir, nf, residual=False, batch_norm=True, faster=faster)
+        refpin.np_fill(conv, 7).eval()
+        x, ei, ea, sh = refpin.conv_inputs(case)
+        xs, eas, shs = (t.clone().requires_grad_(True) for t in (x, ea, sh))
+        out = conv(xs, ei, eas, shs, out_nodes=x.shape[0] + 3)
+        probe = torch.from_numpy(np.random.RandomState(11).standard_normal(tuple(out.shape)).astype(np.float32))
+        gs = torch.autograd.grad((out * probe).sum(), [xs, eas, shs, conv.fc[0].weight, conv.fc[0].bias, conv.fc[3].weight, conv.fc[3].bias])
+        for name, g in zip(('x', 'ea', 'sh', 'w1', 'b1', 'w2', 'b2'), gs):
+            g = g.detach().numpy()
+            if name == 'w2':
+                d[f'grad_{case}_w2_sample'] = g.reshape(-1)[::97].copy()
+                d[f'grad_{case}_w2_sums'] = np.array([g.astype(np.float64).sum(), np.abs(g).astype(np.float64).sum(),
+                                                      (g.astype(np.float64) ** 2).sum()])
+            else:
+                d[f'grad_{case}_{name}'] = g
+    save('ref_conv_grads.npz', d)
+
+
 # ------------------------------------------------------------------------------------------------- forward
 def run_forward(R, rm, b):
     cap = refpin.Capture(rm)
@@ -269,14 +295,14 @@ def make_sampling_full(R, n=8):
 
 
 def main():
-    what = sys.argv[1:] or ['tables', 'ops', 'forward', 'sampling_small', 'sampling_full']
+    what = sys.argv[1:] or ['tables', 'ops', 'conv_grads', 'forward', 'sampling_small', 'sampling_full']
     torch.set_num_threads(os.cpu_count())
     t0 = time.time()
     R = refshim.load()
     print(f'reference modules imported in {time.time() - t0:.1f} s', flush=True)
     os.makedirs(GOLD, exist_ok=True)
     for w in what:
-        {'tables': make_tables, 'ops': make_ops, 'forward': make_forward, 'sampling_small': make_sampling_small,
+        {'tables': make_tables, 'ops': make_ops, 'conv_grads': make_conv_grads, 'forward': make_forward, 'sampling_small': make_sampling_small,
          'sampling_full': make_sampling_full}[w](R)
 
 

@@ -511,3 +511,76 @@ def test_resident_state_cache_reuse_equals_fresh_plans():
     run(T.randomized_list(g2, 5, sa, seed=3), 21)
     assert not ps.LAST_CALL['plan_reused']
     ps.clear_plan_cache()
+
+
+# ------------------------------------------------------------------------------------------- conv backward (training path)
+@pytest.mark.parametrize('case', ['l1', 'l3', 'final', 'lmax2', 'small'])
+@pytest.mark.parametrize('mode', ['fp32', 'bf16x3'])
+def test_conv_layer_backward_vs_autograd_of_the_oracle(case, mode):
+    """Gradients of the conv operator (node features, edge attributes, edge harmonics, both Linears of the edge MLP) against
+    PyTorch autograd through the oracle layer, i.e. what `loss.backward()` computes in the reference's training loop
+    (utils/training.py:147-191).  Forward runs on the fused kernels (fp32 CUDA-core / fp32-grade tensor-core), backward on
+    ddp_tp_backward + library GEMMs."""
+    cfg = {'l1': (SEQ[1], SEQ[2], 180, True), 'l3': (SEQ[3], SEQ[3], 180, True), 'final': (SEQ[3], '2x1o + 2x1e', 120, True),
+           'lmax2': (SEQ[3], SEQ[3], 180, False),
+           'small': ('16x0e + 4x1o + 4x1e + 16x0o', '16x0e + 4x1o + 4x1e + 16x0o', 48, True)}[case]
+    in_ir, out_ir, nf, faster = cfg
+    if mode != 'fp32' and case in ('final',):
+        pytest.skip('head conv runs on the CUDA-core kernel only')
+    sh_ir = '1x0e+1x1o' if faster else '1x0e+1x1o+1x2e'
+    prod, ref = _conv_pair(in_ir, sh_ir, out_ir, nf, faster, seed=3)
+    prod.conv_mode = mode
+    torch.manual_seed(5)
+    n, e = 40, 301
+    x = torch.randn(n, E.Irreps(in_ir).dim)
+    ei = torch.randint(0, n, (2, e))
+    ei[0, :30] = 5
+    ea = torch.randn(e, nf)
+    sh = E.spherical_harmonics(sh_ir, torch.randn(e, 3))
+    probe = torch.randn(n + 2, E.Irreps(out_ir).dim)                  # d loss / d out
+
+    def grads(layer, dev):
+        xs, eas, shs = (t.clone().to(dev).requires_grad_(True) for t in (x, ea, sh))
+        out = layer(xs, ei.to(dev), eas, shs, out_nodes=n + 2)
+        params = [layer.fc[0].weight, layer.fc[0].bias, layer.fc[3].weight, layer.fc[3].bias]
+        gs = torch.autograd.grad((out * probe.to(dev)).sum(), [xs, eas, shs] + params)
+        return out.detach().cpu(), [t.cpu() for t in gs]
+    want_out, want = grads(ref, 'cpu')
+    got_out, got = grads(prod, DEV)
+    assert T.rel_err(got_out, want_out) < 1e-4
+    for name, a, b in zip(('x', 'edge_attr', 'edge_sh', 'W1', 'b1', 'W2', 'b2'), got, want):
+        assert a.shape == b.shape
+        assert T.rel_err(a, b) < 2e-4, (name, T.rel_err(a, b))
+    # an optimizer-style in-place update of the weights is seen by the next forward (packed images are re-built)
+    with torch.no_grad():
+        for lyr in (prod, ref):
+            lyr.fc[3].weight.mul_(0.5)
+    want2, _ = grads(ref, 'cpu')
+    got2, _ = grads(prod, DEV)
+    assert T.rel_err(got2, want2) < 1e-4
+
+
+def test_grid_binned_knn_graph_bit_exact_on_pockets_and_edge_cases():
+    """The atom graph (k = 8 and k = 12) through the grid-binned search: protein-pocket-like clouds (dense ball + sparse surface
+    atoms that need the wider retry radii), an example larger than one shared-memory stage (plain-scan fallback inside the kernel),
+    examples smaller than k + 1, coincident points, points far apart (one point per cell) -- identical edge lists, order included."""
+    g = torch.Generator().manual_seed(7)
+    parts = [torch.randn(1100, 3, generator=g) * 9.0,                                  # pocket-sized dense cloud
+             torch.cat([torch.randn(600, 3, generator=g) * 6.0, torch.randn(40, 3, generator=g) * 40.0]),   # core + far outliers
+             torch.randn(2500, 3, generator=g) * 12.0,                                  # > kKnnStage points
+             torch.randn(5, 3, generator=g), torch.randn(1, 3, generator=g),            # fewer than k + 1 points
+             torch.rand(200, 3, generator=g) * 400.0,                                   # extent >> 12 cells of 5.5 A
+             torch.zeros(30, 3) + 2.5]                                                  # all coincident
+    parts[0][100:120] = parts[0][100]
+    x = torch.cat(parts)
+    b = torch.cat([torch.full((p.shape[0],), i, dtype=torch.long) for i, p in enumerate(parts)])
+    from diffdock_pocket_b200 import _lib
+    L = _lib.lib()
+    prev = L.ddp_knn_set_grid(1)
+    try:
+        for grid in (1, 0):
+            L.ddp_knn_set_grid(grid)
+            for k in (8, 12):
+                assert torch.equal(ops.knn_graph(x.to(DEV), k, b.to(DEV)).cpu(), cluster.knn_graph(x, k, b)), (grid, k)
+    finally:
+        L.ddp_knn_set_grid(max(prev, 0))

@@ -279,3 +279,18 @@ def test_full_size_sampling_vs_reference(mode):
     order_ref = np.argsort(-z['confidence'])
     print(f'full-size sampling [{mode}]: worst RMSD {worst:.4f} A (ligands moved {moved:.2f} A), top-1 {int(order_ref[0])} vs '
           f'{int(np.argsort(-conf.cpu().numpy())[0])}')
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('case', list(refpin.CONV_CASES))
+def test_conv_backward_vs_reference_autograd(case):
+    """Training path: gradients of the conv operator -- node features, edge attributes, edge harmonics, both
+    Linears of the edge MLP -- from ddp_tp_backward + library GEMMs against PyTorch autograd through the reference's own
+    TensorProductConvLayer (models/score_model.py:84-125; fixture tests/golden/ref_conv_grads.npz, scripts/make_ref_fixtures.py)."""
+    from diffdock_pocket_b200.score_model import TensorProductConvLayer
+    from test_reference_pin import _conv_grads, check_conv_grads
+    in_ir, out_ir, nf, faster, sh_ir = refpin.CONV_CASES[case]
+    conv = TensorProductConvLayer(in_ir, sh_ir, out_ir, nf, residual=False, batch_norm=True, faster=faster)
+    refpin.np_fill(conv, 7)
+    conv = conv.to(DEV).eval()
+    check_conv_grads(_conv_grads(conv, case), case, 2e-4)

@@ -387,3 +387,35 @@ def test_live_small_model_forward_and_sampler_reference_vs_oracle(R):
         assert (a['ligand'].pos - b['ligand'].pos).abs().max() < 1e-3
         assert (a['atom'].pos - b['atom'].pos).abs().max() < 1e-3
     assert T.rel_err(conf, ref_conf) < 1e-4
+
+
+# =========================================================================================== conv backward (training path)
+def _conv_grads(conv, case):
+    x, ei, ea, sh = refpin.conv_inputs(case)
+    dev = next(conv.parameters()).device
+    xs, eas, shs = (t.clone().to(dev).requires_grad_(True) for t in (x, ea, sh))
+    out = conv(xs, ei.to(dev), eas, shs, out_nodes=x.shape[0] + 3)
+    probe = torch.from_numpy(np.random.RandomState(11).standard_normal(tuple(out.shape)).astype(np.float32)).to(dev)
+    gs = torch.autograd.grad((out * probe).sum(), [xs, eas, shs, conv.fc[0].weight, conv.fc[0].bias, conv.fc[3].weight, conv.fc[3].bias])
+    return dict(zip(('x', 'ea', 'sh', 'w1', 'b1', 'w2', 'b2'), [g.detach().cpu().numpy() for g in gs]))
+
+
+def check_conv_grads(got, case, rtol):
+    """Compare a dict of gradients with tests/golden/ref_conv_grads.npz (autograd through the reference's own layer)."""
+    z = _z('ref_conv_grads.npz')
+    for name in ('x', 'ea', 'sh', 'w1', 'b1', 'b2'):
+        want = z[f'grad_{case}_{name}']
+        assert got[name].shape == want.shape
+        assert T.rel_err(got[name], want) < rtol, (case, name, T.rel_err(got[name], want))
+    w2 = got['w2']
+    assert T.rel_err(w2.reshape(-1)[::97], z[f'grad_{case}_w2_sample']) < rtol
+    sums = np.array([w2.astype(np.float64).sum(), np.abs(w2).astype(np.float64).sum(), (w2.astype(np.float64) ** 2).sum()])
+    np.testing.assert_allclose(sums[1:], z[f'grad_{case}_w2_sums'][1:], rtol=10 * rtol)
+
+
+@pytest.mark.parametrize('case', list(refpin.CONV_CASES))
+def test_oracle_conv_gradients_match_reference_autograd(case):
+    in_ir, out_ir, nf, faster, sh_ir = refpin.CONV_CASES[case]
+    conv = TensorProductConvLayer(in_ir, sh_ir, out_ir, nf, residual=False, batch_norm=True, faster=faster)
+    refpin.np_fill(conv, 7).eval()
+    check_conv_grads(_conv_grads(conv, case), case, 2e-5)
