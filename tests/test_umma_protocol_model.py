@@ -1,6 +1,6 @@
 """Discrete-event model of the mbarrier protocol of ``tpconv_umma_kernel`` (csrc/tpconv_umma.cu), run on the CPU.
 
-The kernel's five roles (TMA producer, two MMA issuers, gather warp, epilogue warps) synchronise only through
+The kernel's roles (TMA producer, two MMA issuers, gather warp, two epilogue warpgroups -- one per accumulator) synchronise only through
 mbarrier phase-parity waits, tcgen05.commit arrivals and an issue-order token.  Three bugs of that protocol were found
 the hard way on the GPU (a token that was lapped when one issuer owned two slots in a row; a ring shorter than a tile's
 slabs + 1 letting an issuer wait on a slot two fills behind; and, without the token, a parity test that aliases when bulk
@@ -182,45 +182,39 @@ class Model:
             yield lambda: True
         self.done['gather'] = True
 
-    def epilogue(self):
-        tf_phase, tf_n = 0, [0, 0]
-        h_done = False
-
-        def convert(it):
-            nonlocal tf_phase
-            yield lambda p=tf_phase & 1, n=tf_n[0]: self.tmem_full[0].passes(p, n)
-            tf_phase ^= 1
-            tf_n[0] += 1
-            assert self.acc[0] == dict(state='done', tag=(it, -1)), f'hidden activations of item {it} read from {self.acc[0]}'
-            ab = it % self.nbuf
-            assert self.abuf[ab]['readers'] == 0, 'hidden activations overwrite an A buffer that MMAs still read'
-            self.abuf[ab]['content'] = ('H', it)
-            self.acc[0] = dict(state='free')
-            self.h_ready.arrive()
-            self.tmem_empty[0].arrive()
-
+    def epilogue(self, wg):
+        """One epilogue warpgroup per accumulator: warpgroup ``wg`` consumes the tiles that land in accumulator ``wg``
+        (acc_of); warpgroup 0 also converts the GEMM1 result at the start of every item (after its previous item's last
+        own tile and flush -- no early conversion any more)."""
+        tf_phase, tf_n = 0, 0
         for it, nt in enumerate(self.items):
-            if not h_done:
-                yield from convert(it)
-            h_done = False
-            has_next = it + 1 < len(self.items)
+            if wg == 0:
+                yield lambda p=tf_phase, n=tf_n: self.tmem_full[0].passes(p, n)
+                tf_phase ^= 1
+                tf_n += 1
+                assert self.acc[0] == dict(state='done', tag=(it, -1)), f'hidden activations of item {it} read from {self.acc[0]}'
+                ab = it % self.nbuf
+                assert self.abuf[ab]['readers'] == 0, 'hidden activations overwrite an A buffer that MMAs still read'
+                self.abuf[ab]['content'] = ('H', it)
+                self.acc[0] = dict(state='free')
+                self.h_ready.arrive()
+                self.tmem_empty[0].arrive()
             for tt in range(nt):
-                buf = acc_of(tt, nt)
-                yield lambda b=buf, p=(tf_phase >> buf) & 1, n=tf_n[buf]: self.tmem_full[b].passes(p, n)
-                tf_phase ^= 1 << buf
-                tf_n[buf] += 1
-                assert self.acc[buf] == dict(state='done', tag=(it, tt)), f'tile {(it, tt)} read from {self.acc[buf]}'
-                self.acc[buf] = dict(state='free')
-                self.tmem_empty[buf].arrive()
-                if tt == nt - 1 and has_next:
-                    yield from convert(it + 1)
-                    h_done = True
+                if acc_of(tt, nt) != wg:
+                    continue
+                yield lambda p=tf_phase, n=tf_n: self.tmem_full[wg].passes(p, n)
+                tf_phase ^= 1
+                tf_n += 1
+                assert self.acc[wg] == dict(state='done', tag=(it, tt)), f'tile {(it, tt)} read from {self.acc[wg]}'
+                self.acc[wg] = dict(state='free')
+                self.tmem_empty[wg].arrive()
                 yield lambda: True
-        self.done['epilogue'] = True
+        self.done[f'epilogue{wg}'] = True
 
     # ---------------------------------------------------------------- scheduler
     def run(self):
-        roles = {'producer': self.producer(), 'issuer0': self.issuer(0), 'gather': self.gather(), 'epilogue': self.epilogue()}
+        roles = {'producer': self.producer(), 'issuer0': self.issuer(0), 'gather': self.gather(), 'epilogue0': self.epilogue(0),
+                 'epilogue1': self.epilogue(1)}
         if self.dual:
             roles['issuer1'] = self.issuer(1)
         waiting = {k: None for k in roles}
