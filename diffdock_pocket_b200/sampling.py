@@ -343,7 +343,7 @@ def _sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_
     use_graph = bool(use_graph) and trace is None
     runners = [None] * len(chunks)
     # resident state of an earlier call on the same input (see the module docstring)
-    cache_key = cached = None
+    cache_key = cached = full_key = cache_sig = None
     LAST_CALL['plan_reused'] = False
     if PLAN_CACHE_SIZE > 0 and trace is None and filtering_data_list is None and N > 0:
         memo = []                                                     # (tables, key) of the distinct complexes seen so far
@@ -358,13 +358,19 @@ def _sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_
                     return key2
             memo.append((tabs, shape, _graph_key(g, flexible_sidechains)))
             return memo[-1][2]
-        cache_key = (id(model), id(confidence_model), getattr(model, 'conv_mode', None), getattr(model, 'group_convs', None),
-                     str(device), batch_size, bool(flexible_sidechains), bool(ma.no_torsion), use_graph, bool(concurrent_batches),
-                     tuple(gkey(g) for g in data_list))
-        cached = _PLAN_CACHE.get(cache_key)
-        if cached is not None and (cached['busy'] or cached['models'][0]() is not model or
-                                   (confidence_model is not None and cached['models'][1]() is not confidence_model)):
-            cached = None                                             # still owned by an unfinished (deferred) call / stale ids
+        def full_key():
+            return (id(model), id(confidence_model), getattr(model, 'conv_mode', None), getattr(model, 'group_convs', None),
+                    str(device), batch_size, bool(flexible_sidechains), bool(ma.no_torsion), use_graph, bool(concurrent_batches),
+                    tuple(gkey(g) for g in data_list))
+        # the content key costs ~0.1 ms per graph: on the critical path only when an entry of the same shape signature exists
+        # (a possible hit); otherwise it is computed after this call's launches are enqueued, under the GPU work
+        cache_sig = (N, tuple((g['ligand'].pos.shape[0], g['atom'].pos.shape[0], g['receptor'].pos.shape[0]) for g in data_list))
+        if any(e['sig'] == cache_sig for e in _PLAN_CACHE.values()):
+            cache_key = full_key()
+            cached = _PLAN_CACHE.get(cache_key)
+            if cached is not None and (cached['busy'] or cached['models'][0]() is not model or
+                                       (confidence_model is not None and cached['models'][1]() is not confidence_model)):
+                cached = None                                         # still owned by an unfinished (deferred) call / stale ids
     # independent mini-batches alternate between two streams (see StepRunner.ctx); host-visible intermediates
     # (trace, trajectories, visualisation) keep the single-stream order
     single = len(chunks) < 2 or trace is not None or return_full_trajectory or visualization_list is not None \
@@ -512,6 +518,9 @@ def _sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_
             staged = (torch.cuda.Event(), conf_host)
             staged[0].record()
 
+    if full_key is not None and cache_key is None and n_steps > 0:
+        cache_key = full_key()                                        # (everything is enqueued: this overlaps the GPU work)
+
     def finish():
         nonlocal confidence
         if staged is not None:
@@ -521,7 +530,7 @@ def _sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_
         if cache_key is not None and all(r is not None for r in runners) and n_steps > 0:
             # hand the resident state to the cache (or back to it): the next call on this input starts from here
             import weakref
-            _PLAN_CACHE[cache_key] = {'runners': runners, 'conf_plans': conf_plans, 'streams': streams, 'single': single, 'busy': False,
+            _PLAN_CACHE[cache_key] = {'runners': runners, 'conf_plans': conf_plans, 'streams': streams, 'single': single, 'busy': False, 'sig': cache_sig,
                                       'models': (weakref.ref(model), weakref.ref(confidence_model) if confidence_model is not None else None)}
             _PLAN_CACHE.move_to_end(cache_key)
             while len(_PLAN_CACHE) > PLAN_CACHE_SIZE:
