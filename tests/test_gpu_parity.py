@@ -492,7 +492,9 @@ def test_resident_state_cache_reuse_equals_fresh_plans():
     dl_a, dl_b = T.randomized_list(g, 5, sa, seed=3), T.randomized_list(g, 5, sa, seed=4)
     ps.clear_plan_cache()
     first = run(dl_a, 21)
-    assert not ps.LAST_CALL['plan_reused']
+    assert not ps.LAST_CALL['plan_reused'] and len(ps._PLAN_CACHE) == 0      # a first call keeps nothing alive
+    run(dl_a, 21)                               # first repeat: fresh plans once more, kept from here on
+    assert not ps.LAST_CALL['plan_reused'] and len(ps._PLAN_CACHE) == 1
     reused = run(dl_b, 22)                      # same complex, other start poses and noise: resident state re-used
     assert ps.LAST_CALL['plan_reused']
     ps.clear_plan_cache()
@@ -502,13 +504,13 @@ def test_resident_state_cache_reuse_equals_fresh_plans():
     close = lambda x, y: float((x.double() - y.double()).abs().max()) < 2e-3
     for a, b in zip(reused, fresh):
         assert close(a, b), float((a.double() - b.double()).abs().max())
-    again = run(dl_a, 21)                       # cache now holds dl_b's state (same key): re-use, same result as the very first run
-    assert ps.LAST_CALL['plan_reused']
+    again = run(dl_a, 21)                       # first repeat after the clear: fresh plans, kept; same result as the very first run
+    assert not ps.LAST_CALL['plan_reused'] and len(ps._PLAN_CACHE) == 1
     for a, b in zip(again, first):
         assert close(a, b), float((a.double() - b.double()).abs().max())
     g2 = copy.deepcopy(g)
     g2['receptor'].pos[1, 0] += 0.25
-    run(T.randomized_list(g2, 5, sa, seed=3), 21)
+    run(T.randomized_list(g2, 5, sa, seed=3), 21)   # same shapes, one receptor coordinate differs: content key misses
     assert not ps.LAST_CALL['plan_reused']
     ps.clear_plan_cache()
 
