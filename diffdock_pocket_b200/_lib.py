@@ -89,7 +89,7 @@ _SIGS = {
     'ddp_tpconv_umma': (i32, [C.POINTER(TpConv), vp, i32, C.POINTER(TpEdges), vp, vp]),
     'ddp_tpconv_umma_group': (i32, [vp, vp, i32, vp, vp, i32, vp]),
     'ddp_tpconv_umma_set_trace': (i32, [vp]),
-    'ddp_tp_backward': (i32, [C.POINTER(TpConv), vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp]),
+    'ddp_tp_backward': (i32, [C.POINTER(TpConv), i32, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp]),
     'ddp_node_update': (i32, [vp, i32, i32, C.POINTER(Update), i32, i32, i32, vp, i32, vp]),
     'ddp_node_update_multi': (i32, [C.POINTER(NodeUpdateJob), i32, vp]),
     'ddp_degree_multi': (i32, [C.POINTER(DegreeJob), i32, vp]),

@@ -40,6 +40,7 @@ tp_bwd_kernel(const ddp_tp_group_t *__restrict__ groups, int n_groups, const flo
     while (gi + 1 < n_groups && row >= row_start[gi + 1]) ++gi;
     const ddp_tp_group_t g = sg[gi];
     const int u = row - row_start[gi];
+    if (g.d1 > kMaxD || g.d2 > kMaxD || g.d_out > kMaxD) return;      // outside the contract (l <= 2): leave the gradients untouched
     const float *cg = ctab + g.c_off;
     const int node = gather[e];
     float xv[kMaxD], sv[kMaxD];
@@ -85,29 +86,20 @@ tp_bwd_kernel(const ddp_tp_group_t *__restrict__ groups, int n_groups, const flo
 
 }  // namespace
 
-extern "C" int ddp_tp_backward(const ddp_tpconv_t *conv, const float *x, const int32_t *gather, int32_t ldx, const float *sh,
-                               const float *w, const float *g_out, int32_t n_edges, float *g_w, float *g_x, float *g_sh,
+extern "C" int ddp_tp_backward(const ddp_tpconv_t *conv, int32_t rows_per_edge, const float *x, const int32_t *gather, int32_t ldx,
+                               const float *sh, const float *w, const float *g_out, int32_t n_edges, float *g_w, float *g_x, float *g_sh,
                                void *stream) {
     if (!conv || !x || !gather || !sh || !w || !g_out || !g_w) return DDP_E_ARG;
     const ddp_tpconv_t &c = *conv;
     if (!c.groups || !c.ctab) return DDP_E_ARG;
-    if (c.n_groups <= 0 || c.n_groups > kMaxGroups) return DDP_E_SHAPE;
+    if (c.n_groups <= 0 || c.n_groups > kMaxGroups || rows_per_edge <= 0) return DDP_E_SHAPE;
     if (n_edges <= 0) return 0;
-    // rows per edge and the irrep dimensions are host knowledge of the caller's spec: read the groups back once
-    ddp_tp_group_t hg[kMaxGroups];
-    cudaError_t err = cudaMemcpyAsync(hg, c.groups, sizeof(ddp_tp_group_t) * c.n_groups, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
-    if (err != cudaSuccess) return (int)err;
-    err = cudaStreamSynchronize((cudaStream_t)stream);
-    if (err != cudaSuccess) return (int)err;
-    int rows = 0;
-    for (int g = 0; g < c.n_groups; ++g) {
-        if (hg[g].d1 > kMaxD || hg[g].d2 > kMaxD || hg[g].d_out > kMaxD) return DDP_E_UNSUPPORTED;
-        rows += hg[g].mul_in;
-    }
-    const long long total = (long long)n_edges * rows;
+    // rows_per_edge = sum of mul_in over the groups (the groups themselves live on the device; irrep dimensions <= 5, i.e.
+    // l <= 2, are the caller's contract -- the host mirror checks them against its spec)
+    const long long total = (long long)n_edges * rows_per_edge;
     const int grid = (int)((total + 255) / 256);
-    tp_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c.groups, c.n_groups, c.ctab, rows, x, gather, ldx, sh, c.sh_dim, w, c.w_numel,
-                                                          g_out, c.f_out, n_edges, g_w, g_x, g_sh);
+    tp_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c.groups, c.n_groups, c.ctab, rows_per_edge, x, gather, ldx, sh, c.sh_dim, w,
+                                                          c.w_numel, g_out, c.f_out, n_edges, g_w, g_x, g_sh);
     DDP_LAUNCH_CHECK();
     return 0;
 }

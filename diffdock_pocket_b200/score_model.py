@@ -288,10 +288,10 @@ class _ConvFn(torch.autograd.Function):
         x, A, sh = node_attr.detach().float().contiguous(), edge_attr.detach().float().contiguous(), edge_sh.detach().float().contiguous()
         W1, B1, W2, B2 = (t.detach().float() for t in (w1, b1, w2, b2))
         agg, src = edge_index[0].long(), edge_index[1].to(torch.int32).contiguous()
-        pk = layer.packed(dev, layer.fc[0].in_features, 0)
+        bd = layer._backward_desc(dev)                                # spec only (row groups, coefficient table): no weights
         g = g.detach().float()
-        if pk.bn_scale is not None:
-            g = g * pk.bn_scale
+        if layer.batch_norm is not None:
+            g = g * layer.batch_norm.folded()[0].to(device=dev, dtype=torch.float32)
         deg = torch.bincount(agg, minlength=n_out).clamp(min=1).to(torch.float32)
         g_node = (g / deg[:, None]).contiguous()
         Hpre = torch.addmm(B1, A, W1.T)
@@ -308,7 +308,7 @@ class _ConvFn(torch.autograd.Function):
                 ge = ge * ew.detach().float().reshape(-1, 1)[c0:c1]
             ge = ge.contiguous()
             g_w = torch.empty_like(Wt)
-            _lib.check(L.ddp_tp_backward(C.byref(pk.cdesc), ptr(x), src[c0:c1].data_ptr(), x.shape[1], sh[c0:c1].data_ptr(), ptr(Wt),
+            _lib.check(L.ddp_tp_backward(C.byref(bd['cdesc']), bd['rows'], ptr(x), src[c0:c1].data_ptr(), x.shape[1], sh[c0:c1].data_ptr(), ptr(Wt),
                                          ptr(ge), c1 - c0, ptr(g_w), ptr(g_x), g_sh[c0:c1].data_ptr(), _lib.stream_ptr()),
                        'ddp_tp_backward')
             g_W2.addmm_(g_w.T, H[c0:c1])
@@ -349,6 +349,25 @@ class TensorProductConvLayer(nn.Module):
     def _load_from_state_dict(self, *a, **k):
         self._packed = None
         return super()._load_from_state_dict(*a, **k)
+
+    def _backward_desc(self, device):
+        """Descriptor of ``ddp_tp_backward``: the row groups and coefficient table of the spec on the device (weight-free, so it
+        survives optimizer steps) + the number of basis rows per edge."""
+        bd = getattr(self, '_bwd', None)
+        if bd is None or bd['device'] != torch.device(device):
+            spec = self.tp.spec
+            if any(max(g['d1'], g['d2'], g['d_out']) > 5 for g in spec.groups):
+                raise NotImplementedError('ddp_tp_backward handles irreps up to l = 2')
+            garr = (_lib.TpGroup * len(spec.groups))(*[_lib.TpGroup(**g) for g in spec.groups])
+            groups = torch.frombuffer(bytearray(bytes(garr)), dtype=torch.uint8).to(device)
+            ctab = torch.tensor(spec.ctab, dtype=torch.float32, device=device)
+            cdesc = _lib.TpConv(w1t=None, b1=None, w2t=None, b2=None, k1=self.fc[0].in_features, hid=self.fc[0].out_features,
+                                w_numel=spec.weight_numel, n_emb=self.fc[0].in_features, ns=0, groups=ptr(groups), ctab=ptr(ctab),
+                                ctab_len=len(spec.ctab), col_group=None, n_groups=len(spec.groups), f_in=spec.f_in, f_out=spec.f_out,
+                                sh_dim=spec.sh_dim)
+            bd = self._bwd = dict(device=torch.device(device), groups=groups, ctab=ctab, cdesc=cdesc,
+                                  rows=int(sum(g['mul_in'] for g in spec.groups)))
+        return bd
 
     def packed(self, device, n_emb, ns, edge_fold=None, fold_bn=False):
         # (parameter versions: an optimizer step between two training forwards invalidates the packed image)

@@ -224,9 +224,11 @@ int ddp_tpconv_umma_group(const ddp_tpconv_t *const *convs, const void *const *p
  * w / g_w: [n_edges][w_numel] (the per-edge weights fc(edge_attr) and their gradient, materialised per chunk of
  * edges by the caller), g_out: [n_edges][f_out] per-EDGE output gradients (the caller has applied the scatter-mean:
  * g_sum[agg[e]] / deg).  The Linear / ReLU gradients around it are plain GEMMs on the caller's side
- * (diffdock_pocket_b200/score_model.py:_ConvFn).  Uses conv->groups, ctab, n_groups, w_numel, f_out, sh_dim. */
-int ddp_tp_backward(const ddp_tpconv_t *conv, const float *x, const int32_t *gather, int32_t ldx, const float *sh,
-                    const float *w, const float *g_out, int32_t n_edges, float *g_w, float *g_x, float *g_sh, void *stream);
+ * (diffdock_pocket_b200/score_model.py:_ConvFn).  Uses conv->groups, ctab, n_groups, w_numel, f_out, sh_dim; irrep
+ * dimensions of the groups must be <= 5 (l <= 2). */
+int ddp_tp_backward(const ddp_tpconv_t *conv, int32_t rows_per_edge /* sum of mul_in over conv->groups */, const float *x,
+                    const int32_t *gather, int32_t ldx, const float *sh, const float *w, const float *g_out, int32_t n_edges,
+                    float *g_w, float *g_x, float *g_sh, void *stream);
 
 /* Developer aid: when trace_dev != NULL, CTA 0 of every following tensor-core conv launch records clock64()
  * timestamps of its MMA-issue and epilogue roles per weight tile into trace_dev (device int64 buffer); NULL turns
