@@ -1449,7 +1449,7 @@ static long long *g_umma_trace = nullptr;
 extern "C" int ddp_tpconv_umma_set_trace(void *trace_dev) {
 #ifdef DDP_UMMA_TRACE
     g_umma_trace = static_cast<long long *>(trace_dev);
-    return 3 * umma::TRACE_TILES * umma::TRACE_EVENTS;      // int64 slots the buffer must hold (watchdog build: 148 x 8 x 4 of them)
+    return 3 * umma::TRACE_TILES * umma::TRACE_EVENTS;      // int64 slots the buffer must hold (watchdog build: 148 x 12 x 4 of them)
 #else
     (void)trace_dev;
     return DDP_E_UNSUPPORTED;                               // library built without -DDDP_UMMA_TRACE
