@@ -10,7 +10,7 @@ contract (:238-436), but evaluates everything through the ddp_b200 CUDA kernels:
   ``sampling()`` keep the batch resident on the GPU for all steps.
 
 Supported configuration: ``parallel == 1``, no affinity head, ``separate_noise_schedule`` /
-``asyncronous_noise_schedule`` off, ``odd_parity`` off (the reference inference path).
+``odd_parity`` off (the reference inference path).
 The per-graph diffusion time is read from ``data.complex_t['tr']`` (``set_time`` broadcasts the same
 value to every node of a graph, utils/diffusion_utils.py:124-149).
 """
@@ -103,12 +103,13 @@ class TensorProductScoreModel(nn.Module):
                  no_aminoacid_identities=False, flexible_sidechains=False, include_miscellaneous_atoms=False,
                  use_old_atom_encoder=False):
         super().__init__()
-        if parallel != 1 or affinity_prediction or separate_noise_schedule or asyncronous_noise_schedule or odd_parity \
+        if parallel != 1 or affinity_prediction or separate_noise_schedule or odd_parity \
                 or smooth_edges or include_miscellaneous_atoms:
             raise NotImplementedError('configuration outside the accelerated inference path (see module docstring)')
         if not lm_embedding_type:
             lm_embedding_type = None
         self.t_to_sigma, self.timestep_emb_func = t_to_sigma, timestep_emb_func
+        self.asyncronous_noise_schedule = bool(asyncronous_noise_schedule)
         self.in_lig_edge_features, self.sigma_embed_dim = in_lig_edge_features, sigma_embed_dim
         self.lig_max_radius, self.rec_max_radius = lig_max_radius, rec_max_radius
         self.cross_max_distance, self.dynamic_max_cross = cross_max_distance, dynamic_max_cross
@@ -570,7 +571,8 @@ class TensorProductScoreModel(nn.Module):
         else:
             tr_s, rot_s, tor_s, sc_s = self.t_to_sigma(*ct)
         h = torch.zeros(pl.n_scal, dtype=torch.float32) if out is None else out
-        h[0:B] = ct[0]
+        # time of the sigma embedding: 'tr', or 't' under the asynchronous noise schedule (all_atom_score_model.py:370,450,492,517)
+        h[0:B] = torch.as_tensor(complex_t['t']).detach().float().cpu().reshape(-1)[:B] if self.asyncronous_noise_schedule else ct[0]
         h[B:2 * B] = tr_s
         if not self.confidence_mode:
             h[2 * B:3 * B] = so3.score_norm(rot_s.float())
@@ -931,6 +933,6 @@ class TensorProductScoreModel(nn.Module):
         for key in ('ligand', 'receptor', 'atom'):
             node_t = getattr(data[key], 'node_t', None)
             if node_t is not None:
-                data[key].node_sigma_emb = self.timestep_emb_func(torch.as_tensor(node_t['tr'], dtype=torch.float32).to(pl.device))
+                data[key].node_sigma_emb = self.timestep_emb_func(torch.as_tensor(node_t['t' if self.asyncronous_noise_schedule else 'tr'], dtype=torch.float32).to(pl.device))
         self._last_plan = pl
         return out

@@ -66,6 +66,10 @@ def set_time(complex_graphs, t, t_tr, t_rot, t_tor, t_sidechain_tor, batchsize, 
                                     'sc_tor': t_sidechain_tor * torch.ones(n)}
     complex_graphs.complex_t = {'tr': t_tr * torch.ones(batchsize), 'rot': t_rot * torch.ones(batchsize),
                                 'tor': t_tor * torch.ones(batchsize), 'sc_tor': t_sidechain_tor * torch.ones(batchsize)}
+    if asyncronous_noise_schedule:                                   # :158-165
+        for k in keys:
+            complex_graphs[k].node_t['t'] = t * torch.ones(complex_graphs[k].num_nodes)
+        complex_graphs.complex_t['t'] = t * torch.ones(batchsize)
 
 
 class PoseState:

@@ -23,7 +23,9 @@ coordinates).  A later call on the same complex(es) -- re-docking, more samples,
 recurring ligand -- only uploads the new start poses: the ~50 ms of host-side collation and plan building of the first
 call, during which the GPU starves inside step 0, are gone (``DDP_PLAN_CACHE=0`` disables the cache).
 
-SVGD (svgd_weight > 0) and ``pivot`` are outside the accelerated path and raise NotImplementedError.
+SVGD (svgd_weight > 0) and ``pivot`` are outside the accelerated path and raise NotImplementedError; the asynchronous
+noise schedule (``asyncronous_noise_schedule=True`` with ``t_schedule``, utils/sampling.py:116-117) is supported: the step's
+``t_schedule[t_idx]`` becomes the time of the sigma embeddings.
 """
 import collections
 import contextlib
@@ -247,10 +249,11 @@ class StepRunner:
                        sc_z=self.z[3] if self.use_sc else None)
 
     def stage(self, t4, coef, noise_row=None):
-        """Host side of one step: scalars + coefficients + this batch's noise -> one pinned row -> one H2D."""
+        """Host side of one step: scalars + coefficients + this batch's noise -> one pinned row -> one H2D.
+        ``t4``: (t_tr, t_rot, t_tor, t_sc[, t]) -- the fifth entry is the embedding time of the asynchronous noise schedule."""
         pl, b = self.pl, self.b
         row = torch.zeros(pl.n_scal + self.n_extra, dtype=torch.float32).pin_memory()
-        ct = {k: torch.full((b,), float(v)) for k, v in zip(('tr', 'rot', 'tor', 'sc_tor'), t4)}
+        ct = {k: torch.full((b,), float(v)) for k, v in zip(('tr', 'rot', 'tor', 'sc_tor', 't'), t4)}
         self.model._host_scalars(pl, ct, out=row[:pl.n_scal])
         row[pl.n_scal:pl.n_scal + 8] = torch.tensor([float(c) for c in coef])
         if noise_row is not None:
@@ -320,8 +323,10 @@ def _sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_
              svgd_sidechain_tor_rel_weight=1.0, temp_sampling=1.0, temp_psi=0.0, temp_sigma_data=0.5,
              flexible_sidechains=None, max_steps=None, trace=None, use_graph=False, concurrent_batches=True,
              loader_seed_draws=True, defer=False):
-    if svgd_weight > 0 or pivot is not None or asyncronous_noise_schedule:
-        raise NotImplementedError('SVGD / pivot / asynchronous schedules are outside the accelerated path')
+    if svgd_weight > 0 or pivot is not None:
+        raise NotImplementedError('SVGD / pivot are outside the accelerated path')
+    if asyncronous_noise_schedule and t_schedule is None:
+        raise ValueError('asyncronous_noise_schedule needs t_schedule (utils/sampling.py:116)')
     flexible_sidechains = model_args.flexible_sidechains if flexible_sidechains is None else flexible_sidechains
     no_sidechains_in_batch = False
     if flexible_sidechains:
@@ -445,6 +450,8 @@ def _sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_
         for t_idx in range(n_steps):
             t, coef = step_coefficients(t_idx, inference_steps, schedules, t_to_sigma, ma, ode, temp_sampling, temp_psi,
                                         temp_sigma_data, flexible_sidechains)
+            if asyncronous_noise_schedule:
+                t = list(t) + [t_schedule[t_idx]]                     # embedding time (set_time's `t`, utils/sampling.py:116)
             if return_full_trajectory:
                 write_back_all()
                 trajectory.append(np.asarray([g['ligand'].pos.cpu().numpy() for g in data_list]))
@@ -500,14 +507,14 @@ def _sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_
             for idx, r, cpl in zip(chunks, runners, conf_plans):
                 zt = torch.zeros(len(idx))
                 if r is None:
-                    conf.append(confidence_model.run_plan(cpl, {'tr': zt, 'rot': zt, 'tor': zt, 'sc_tor': zt}).clone())
+                    conf.append(confidence_model.run_plan(cpl, {'tr': zt, 'rot': zt, 'tor': zt, 'sc_tor': zt, 't': zt}).clone())
                     continue
                 r.sync_in()                                           # the confidence plans were uploaded on the caller's stream
                 with r.ctx():
                     cpl.lig_pos.copy_(r.pl.lig_pos)
                     if filtering_data_list is None:                   # filtering graphs keep their own receptor atoms
                         cpl.atom_pos.copy_(r.pl.atom_pos)
-                    conf.append(confidence_model.run_plan(cpl, {'tr': zt, 'rot': zt, 'tor': zt, 'sc_tor': zt}).clone())
+                    conf.append(confidence_model.run_plan(cpl, {'tr': zt, 'rot': zt, 'tor': zt, 'sc_tor': zt, 't': zt}).clone())
                     conf[-1].record_stream(cur)
             for r in runners:
                 if r is not None:

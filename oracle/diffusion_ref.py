@@ -47,13 +47,18 @@ def get_t_schedule(inference_steps, alpha=1, beta_=1, t_max=1):
     return beta.ppf(c, a=alpha, b=beta_)
 
 
-def set_time(g, t_tr, t_rot, t_tor, t_sc, batchsize):
+def set_time(g, t_tr, t_rot, t_tor, t_sc, batchsize, t=None):
+    """utils/diffusion_utils.py:124-165; ``t`` is given under the asynchronous noise schedule (:158-165)."""
     for key in ('ligand', 'receptor', 'atom'):
         n = g[key].num_nodes
         g[key].node_t = {'tr': t_tr * torch.ones(n), 'rot': t_rot * torch.ones(n),
                          'tor': t_tor * torch.ones(n), 'sc_tor': t_sc * torch.ones(n)}
+        if t is not None:
+            g[key].node_t['t'] = t * torch.ones(n)
     g.complex_t = {'tr': t_tr * torch.ones(batchsize), 'rot': t_rot * torch.ones(batchsize),
                    'tor': t_tor * torch.ones(batchsize), 'sc_tor': t_sc * torch.ones(batchsize)}
+    if t is not None:
+        g.complex_t['t'] = t * torch.ones(batchsize)
 
 
 # ----------------------------------------------------------------------------- geometry

@@ -21,7 +21,8 @@ def oracle_model(args, state_dict, so3_score_norm, torus_score_norm, confidence_
         dynamic_max_cross=args.dynamic_max_cross, lm_embedding_type='esm', confidence_mode=confidence_mode,
         fixed_center_conv=not args.not_fixed_center_conv if has('not_fixed_center_conv') else False,
         atom_max_neighbors=args.atom_max_neighbors, flexible_sidechains=args.flexible_sidechains,
-        use_old_atom_encoder=args.use_old_atom_encoder if has('use_old_atom_encoder') else True)
+        use_old_atom_encoder=args.use_old_atom_encoder if has('use_old_atom_encoder') else True,
+        asyncronous_noise_schedule=bool(getattr(args, 'asyncronous_noise_schedule', False)))
     sd = {k: v.detach().cpu() for k, v in state_dict.items()}
     missing, unexpected = m.load_state_dict(sd, strict=True), None
     m.eval()

@@ -44,9 +44,10 @@ def randomize_position(data_list, no_torsion, no_random, tr_sigma_max, flexible_
 def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_schedule, sidechain_tor_schedule,
              t_to_sigma, model_args, no_random=False, ode=False, confidence_model=None, batch_size=32,
              no_final_step_noise=False, temp_sampling=1.0, temp_psi=0.0, temp_sigma_data=0.5,
-             flexible_sidechains=None, max_steps=None, trace=None):
+             flexible_sidechains=None, max_steps=None, trace=None, asyncronous_noise_schedule=False, t_schedule=None):
     """Returns (data_list, confidence).  ``max_steps`` truncates the loop (bounded CPU-baseline
-    samples); ``trace`` (a list) receives the per-step scores for parity tests."""
+    samples); ``trace`` (a list) receives the per-step scores for parity tests.  Under the asynchronous noise schedule
+    ``set_time`` also receives ``t_schedule[t_idx]`` (utils/sampling.py:116-117; the confidence pass: 0, :273-278)."""
     flexible_sidechains = model_args.flexible_sidechains if flexible_sidechains is None else flexible_sidechains
     N = len(data_list)
     ma = model_args
@@ -60,7 +61,8 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
         tr_sigma, rot_sigma, tor_sigma, sc_sigma = t_to_sigma(t_tr, t_rot, t_tor, t_sc)
         scores = [[], [], [], []]
         for batch in DataLoader(data_list, batch_size=batch_size):
-            set_time(batch, t_tr, t_rot, t_tor, t_sc, batch.num_graphs)
+            set_time(batch, t_tr, t_rot, t_tor, t_sc, batch.num_graphs,
+                     t=(t_schedule[t_idx] if t_schedule is not None else None) if asyncronous_noise_schedule else None)
             with torch.no_grad():
                 out = model(batch)
             for lst, o in zip(scores, out):
@@ -133,7 +135,7 @@ def sampling(data_list, model, inference_steps, tr_schedule, rot_schedule, tor_s
             loader = DataLoader(data_list, batch_size=batch_size)
             iter(DataLoader(None, batch_size=batch_size))             # filtering_loader (:266): its iterator is created even without filtering data
             for batch in loader:
-                set_time(batch, 0, 0, 0, 0, N)
+                set_time(batch, 0, 0, 0, 0, N, t=0 if asyncronous_noise_schedule else None)
                 conf.append(confidence_model(batch))
         confidence = torch.cat(conf, 0)
     return data_list, confidence

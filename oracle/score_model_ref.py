@@ -210,9 +210,11 @@ class TensorProductScoreModel(nn.Module):
                  smooth_edges=False, lm_embedding_type=None, confidence_mode=False, confidence_dropout=0,
                  confidence_no_batchnorm=False, num_confidence_outputs=1, fixed_center_conv=False,
                  atom_max_neighbors=None, no_aminoacid_identities=False, flexible_sidechains=False,
-                 use_old_atom_encoder=False):
+                 use_old_atom_encoder=False, asyncronous_noise_schedule=False):
         super().__init__()
         self.t_to_sigma, self.timestep_emb_func = t_to_sigma, timestep_emb_func
+        # all_atom_score_model.py:370,450,492,517: the sigma embedding reads time 't' instead of 'tr' under the asynchronous schedule
+        self.asyncronous_noise_schedule, self._t_key = asyncronous_noise_schedule, 't' if asyncronous_noise_schedule else 'tr'
         self.so3_score_norm, self.torus_score_norm = so3_score_norm, torus_score_norm
         self.in_lig_edge_features = in_lig_edge_features
         self.lig_max_radius, self.rec_max_radius = lig_max_radius, rec_max_radius
@@ -296,7 +298,7 @@ class TensorProductScoreModel(nn.Module):
     # ------------------------------------------------------------------ graph builders
     def build_lig_conv_graph(self, data):                                # :444-484
         lig = data['ligand']
-        lig.node_sigma_emb = self.timestep_emb_func(lig.node_t['tr'])
+        lig.node_sigma_emb = self.timestep_emb_func(lig.node_t[self._t_key])
         radius_edges = cluster.radius_graph(lig.pos, self.lig_max_radius, lig.batch)
         edge_index = torch.cat([data['ligand', 'ligand'].edge_index, radius_edges], 1).long()
         edge_attr = torch.cat([data['ligand', 'ligand'].edge_attr,
@@ -310,7 +312,7 @@ class TensorProductScoreModel(nn.Module):
 
     def build_rec_conv_graph(self, data):                                # :486-511
         rec = data['receptor']
-        rec.node_sigma_emb = self.timestep_emb_func(rec.node_t['tr'])
+        rec.node_sigma_emb = self.timestep_emb_func(rec.node_t[self._t_key])
         node_attr = torch.cat([rec.x, rec.node_sigma_emb], 1)
         edge_index = data['receptor', 'receptor'].edge_index
         src, dst = edge_index
@@ -320,7 +322,7 @@ class TensorProductScoreModel(nn.Module):
 
     def build_atom_conv_graph(self, data):                               # :513-537
         atom = data['atom']
-        atom.node_sigma_emb = self.timestep_emb_func(atom.node_t['tr'])
+        atom.node_sigma_emb = self.timestep_emb_func(atom.node_t[self._t_key])
         node_attr = torch.cat([atom.x, atom.node_sigma_emb], 1)
         edge_index = cluster.knn_graph(atom.pos, k=self.atom_max_neighbors if self.atom_max_neighbors else 32,
                                        batch=atom.batch)
@@ -455,7 +457,7 @@ class TensorProductScoreModel(nn.Module):
         g = self.final_conv(lig_x, cei, cattr, csh, out_nodes=data.num_graphs)
         tr_pred = g[:, :3] + g[:, 6:9]
         rot_pred = g[:, 3:6] + g[:, 9:]
-        data.graph_sigma_emb = self.timestep_emb_func(data.complex_t['tr'])
+        data.graph_sigma_emb = self.timestep_emb_func(data.complex_t[self._t_key])
         tr_norm = torch.linalg.vector_norm(tr_pred, dim=1).unsqueeze(1)
         tr_pred = tr_pred / tr_norm * self.tr_final_layer(torch.cat([tr_norm, data.graph_sigma_emb], 1))
         rot_norm = torch.linalg.vector_norm(rot_pred, dim=1).unsqueeze(1)

@@ -6,7 +6,7 @@
 written below is an output of those reference modules.  ``tests/test_reference_pin.py`` (CPU) checks the oracle
 against them, ``tests/test_gpu_refpin.py`` (GPU) the CUDA path.
 
-    python scripts/make_ref_fixtures.py [tables] [ops] [conv_grads] [forward] [sampling_small] [sampling_full]
+    python scripts/make_ref_fixtures.py [tables] [ops] [conv_grads] [async] [forward] [sampling_small] [sampling_full]
 
 (no argument = everything; ``sampling_full`` is the 20-step big-model run, several minutes of CPU.)
 The first run imports ``utils/so3.py`` / ``utils/torus.py`` without their ``.npy`` caches: ~9 minutes.
@@ -137,6 +137,40 @@ def make_ops(R):
     d['collate_flex_edge_idx'] = b['flexResidues'].edge_idx.numpy()
     d['collate_flex_batch'] = b['flexResidues'].batch.numpy()
     save('ref_ops.npz', d)
+
+
+# ------------------------------------------------------------------------------------------------- asynchronous noise schedule
+ASYNC_KW = dict(ns=16, nv=4, num_conv_layers=4, sigma_embed_dim=32, distance_embed_dim=32, cross_distance_embed_dim=32,
+                asyncronous_noise_schedule=True)
+
+
+def make_async(R):
+    """Forward of the reference's all-atom model built with ``asyncronous_noise_schedule=True`` (sigma embeddings read time
+    't' of ``set_time``, models/all_atom_score_model.py:370,450,492,517; utils/diffusion_utils.py:158-165) and a 3-step
+    sampler run with a ``t_schedule`` different from the noise schedules (utils/sampling.py:116-117)."""
+    share_torus_table(R)
+    sa = putils.score_model_args(**ASYNC_KW)
+    rm, _, sa, _, ws, _ = ref_models(R, sa, None, seed=5)
+    g = inputs.synthetic_complex(3, n_lig=16, n_res=30, flexible_residues=2)
+    dl = randomized(R, g, 3, sa, seed=6)
+    d = {'weights': np.asarray(ws)}
+    b = pyg_mini.Batch.from_data_list(copy.deepcopy(dl))
+    R.diffusion_utils.set_time(b, 0.9, 0.4, 0.4, 0.4, 0.4, len(dl), True, True, torch.device('cpu'))
+    with torch.no_grad():
+        out = rm(b)
+    for k, v in zip(('tr', 'rot', 'tor', 'sc'), out):
+        d[f'fwd_{k}'] = v.numpy()
+    steps = 3
+    sch = R.diffusion_utils.get_t_schedule('expbeta', steps, 1, 1, 1)
+    t_sch = np.asarray(sch) ** 2 * 0.7 + 0.05
+    torch.manual_seed(8)
+    out, _ = R.sampling.sampling(copy.deepcopy(dl), rm, steps, sch, sch, sch, sch, torch.device('cpu'),
+                                 partial(R.diffusion_utils.t_to_sigma, args=sa), sa, batch_size=2, asyncronous_noise_schedule=True,
+                                 t_schedule=t_sch)
+    d['t_schedule'] = t_sch
+    d['lig_pos'] = torch.stack([o['ligand'].pos for o in out]).numpy()
+    d['atom_pos'] = torch.stack([o['atom'].pos for o in out]).numpy()
+    save('ref_async.npz', d)
 
 
 # ------------------------------------------------------------------------------------------------- conv backward
@@ -295,14 +329,14 @@ def make_sampling_full(R, n=8):
 
 
 def main():
-    what = sys.argv[1:] or ['tables', 'ops', 'conv_grads', 'forward', 'sampling_small', 'sampling_full']
+    what = sys.argv[1:] or ['tables', 'ops', 'conv_grads', 'async', 'forward', 'sampling_small', 'sampling_full']
     torch.set_num_threads(os.cpu_count())
     t0 = time.time()
     R = refshim.load()
     print(f'reference modules imported in {time.time() - t0:.1f} s', flush=True)
     os.makedirs(GOLD, exist_ok=True)
     for w in what:
-        {'tables': make_tables, 'ops': make_ops, 'conv_grads': make_conv_grads, 'forward': make_forward, 'sampling_small': make_sampling_small,
+        {'tables': make_tables, 'ops': make_ops, 'conv_grads': make_conv_grads, 'async': make_async, 'forward': make_forward, 'sampling_small': make_sampling_small,
          'sampling_full': make_sampling_full}[w](R)
 
 

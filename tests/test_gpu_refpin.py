@@ -294,3 +294,33 @@ def test_conv_backward_vs_reference_autograd(case):
     refpin.np_fill(conv, 7)
     conv = conv.to(DEV).eval()
     check_conv_grads(_conv_grads(conv, case), case, 2e-4)
+
+
+def test_asynchronous_noise_schedule_vs_reference():
+    """asyncronous_noise_schedule=True (sigma embeddings at set_time's `t`): forward through forward(data) and a 3-step sampling()
+    run with a separate t_schedule against the reference's own model / sampler (tests/golden/ref_async.npz)."""
+    from functools import partial
+    from test_reference_pin import async_case
+    from diffdock_pocket_b200 import diffusion_utils as du, sampling as ps
+    from diffdock_pocket_b200.hetero import Batch
+    m, sa, dl, z = async_case(DEV)
+    m.conv_mode = 'fp32'
+    g = inputs.synthetic_complex(3, n_lig=16, n_res=30, flexible_residues=2)
+    pl_dl = []
+    for o in dl:                                                      # product-side graphs at the oracle-randomised start poses
+        x = copy.deepcopy(g)
+        x['ligand'].pos, x['atom'].pos = o['ligand'].pos.clone(), o['atom'].pos.clone()
+        pl_dl.append(x)
+    b = Batch.from_data_list(copy.deepcopy(pl_dl))
+    du.set_time(b, 0.9, 0.4, 0.4, 0.4, 0.4, len(dl), True, True, DEV)
+    with torch.no_grad():
+        out = m(b)
+    for k, v in zip(('tr', 'rot', 'tor', 'sc'), out):
+        assert T.rel_err(v, z[f'fwd_{k}']) < 1e-4, (k, T.rel_err(v, z[f'fwd_{k}']))
+    steps = 3
+    sch = du.get_t_schedule('expbeta', steps)
+    torch.manual_seed(8)
+    got, _ = ps.sampling(copy.deepcopy(pl_dl), m, steps, sch, sch, sch, sch, DEV, partial(du.t_to_sigma, args=sa), sa, batch_size=2,
+                         asyncronous_noise_schedule=True, t_schedule=z['t_schedule'])
+    assert (torch.stack([o['ligand'].pos.cpu() for o in got]) - torch.from_numpy(z['lig_pos'])).abs().max() < 5e-3
+    assert (torch.stack([o['atom'].pos.cpu() for o in got]) - torch.from_numpy(z['atom_pos'])).abs().max() < 5e-3

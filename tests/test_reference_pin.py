@@ -419,3 +419,45 @@ def test_oracle_conv_gradients_match_reference_autograd(case):
     conv = TensorProductConvLayer(in_ir, sh_ir, out_ir, nf, residual=False, batch_norm=True, faster=faster)
     refpin.np_fill(conv, 7).eval()
     check_conv_grads(_conv_grads(conv, case), case, 2e-5)
+
+
+# =========================================================================================== asynchronous noise schedule
+ASYNC_KW = dict(ns=16, nv=4, num_conv_layers=4, sigma_embed_dim=32, distance_embed_dim=32, cross_distance_embed_dim=32,
+                asyncronous_noise_schedule=True)
+
+
+def async_case(device):
+    """Seeded model / inputs of scripts/make_ref_fixtures.py:make_async -> (product model, score args, sample list, fixture)."""
+    sa = utils.score_model_args(**ASYNC_KW)
+    m, _, sa, _ = utils.build_models(device, score_args=sa, seed=5, with_confidence=False)
+    z = _z('ref_async.npz')
+    np.testing.assert_allclose(refpin.weight_checksum(m.state_dict()), z['weights'], rtol=1e-6)
+    g = inputs.synthetic_complex(3, n_lig=16, n_res=30, flexible_residues=2)
+    np.random.seed(6)
+    torch.manual_seed(6)
+    dl = [pyg_mini.from_any(g) for _ in range(3)]
+    S.randomize_position(dl, False, False, sa.tr_sigma_max, flexible_sidechains=True)
+    return m, sa, dl, z
+
+
+def test_oracle_asynchronous_noise_schedule_matches_reference():
+    """all_atom_score_model.py:370,450,492,517 + utils/diffusion_utils.py:158-165 + utils/sampling.py:116-117: the sigma embeddings
+    read set_time's `t`; forward and a 3-step sampler run of the reference's own model against the oracle."""
+    m, sa, dl, z = async_case(torch.device('cpu'))
+    om = factory.oracle_model(sa, m.state_dict(), so3.score_norm_np, torus.score_norm)
+    b = pyg_mini.Batch.from_data_list(copy.deepcopy(dl))
+    D.set_time(b, 0.4, 0.4, 0.4, 0.4, len(dl), t=0.9)
+    with torch.no_grad():
+        out = om(b)
+    for k, v in zip(('tr', 'rot', 'tor', 'sc'), out):
+        _close(v.numpy(), z[f'fwd_{k}'], rtol=2e-4, atol=2e-5)
+    D.set_time(b, 0.4, 0.4, 0.4, 0.4, len(dl), t=0.4)                 # the embedding time matters
+    with torch.no_grad():
+        assert T.rel_err(om(b)[0], z['fwd_tr']) > 1e-3
+    steps = 3
+    sch = D.get_t_schedule(steps)
+    torch.manual_seed(8)
+    out, _ = S.sampling(copy.deepcopy(dl), om, steps, sch, sch, sch, sch, partial(D.t_to_sigma, args=sa), sa, batch_size=2,
+                        asyncronous_noise_schedule=True, t_schedule=z['t_schedule'])
+    assert (torch.stack([o['ligand'].pos for o in out]) - torch.from_numpy(z['lig_pos'])).abs().max() < 2e-3
+    assert (torch.stack([o['atom'].pos for o in out]) - torch.from_numpy(z['atom_pos'])).abs().max() < 2e-3
