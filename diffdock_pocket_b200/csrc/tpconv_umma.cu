@@ -363,6 +363,11 @@ __host__ __device__ constexpr int stage_k_of(int ks, bool split) { return ks == 
 #ifndef DDP_UMMA_SEGSCAN
 #define DDP_UMMA_SEGSCAN 1
 #endif
+// Diagnostic only (wrong results): 2 = full epilogue (default); 1 = TMEM loads kept, tensor-product FMAs skipped -- "what
+// would the launch cost if the CUDA-core part of the epilogue were free" (profiles/r2_conv_energy_diag.txt).
+#ifndef DDP_DIAG_EPI
+#define DDP_DIAG_EPI 2
+#endif
 __host__ __device__ constexpr bool use_ts(bool split) { return DDP_UMMA_TS != 0 && !split; }
 __host__ __device__ constexpr int rows_scalar(int ns, bool ts) { return (ts ? 192 : 240) / ns; }
 __host__ __device__ constexpr int ncol_scalar(int ns, bool ts) { return (rows_scalar(ns, ts) * ns + 15) / 16 * 16; }
@@ -1041,7 +1046,7 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
 #pragma unroll
                         for (int q = 0; q < 16; ++q) {
                             const int c = c16 * 16 + q;
-                            if (c < C::NVAL_S) acc[c % NS] = fmaf(__uint_as_float(w[c16 & 1][q]), b[c / NS], acc[c % NS]);
+                            if (DDP_DIAG_EPI >= 2 && c < C::NVAL_S) acc[c % NS] = fmaf(__uint_as_float(w[c16 & 1][q]), b[c / NS], acc[c % NS]);
                         }
                     }
                     tc_fence_before();
@@ -1090,7 +1095,7 @@ tpconv_umma_kernel(const __grid_constant__ Jobs jobs) {
 #pragma unroll
                             for (int q = 0; q < 16; ++q) {
                                 const int c = c16 * 16 + q;
-                                if (c < NCOLS) u[c % NV] = fmaf(__uint_as_float(w[c16 & 1][q]), xn[c / NV], u[c % NV]);
+                                if (DDP_DIAG_EPI >= 2 && c < NCOLS) u[c % NV] = fmaf(__uint_as_float(w[c16 & 1][q]), xn[c / NV], u[c % NV]);
                             }
                         }
                     }
